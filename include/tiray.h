@@ -1,0 +1,140 @@
+/* tiray.h — C-ABI of libtiray.so, the B200 (sm_100a) replacement for the Taichi kernels on the
+ * hot path of lyd405121/ti-raytrace.
+ *
+ * The reference has no FFI layer: its device work is Taichi `@ti.kernel`s reached from the Python
+ * classes Scene / Camera / LBvh.Bvh / PT_RGB.PathTrace.  Each entry point below replaces one of
+ * those kernel groups; the Python classes in ti-raytrace_b200/ (same names and methods as the
+ * reference's) call them through ctypes.  Plain pointers and sizes only; host arrays are borrowed
+ * for the duration of the call; all device memory is owned by the context.
+ *
+ * Every function returns TR_OK (0) or a negative tr_status; tr_last_error() gives the text.
+ * A context is bound to one CUDA device and one non-default stream and is not thread-safe.
+ * Citations are file:line in the reference tree (commit 70ccd57).
+ */
+#ifndef TIRAY_H
+#define TIRAY_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tr_ctx tr_ctx;
+
+typedef enum tr_status {
+    TR_OK = 0,
+    TR_ERR_CUDA = -1,          /* CUDA runtime error (text in tr_last_error) */
+    TR_ERR_INVALID = -2,       /* bad argument / call order */
+    TR_ERR_AABB = -3,          /* "aabb gen error": refit did not reach n-1 nodes (accel/LBvh.py:215-216) */
+    TR_ERR_NO_DEVICE = -4,     /* no CUDA device: there is no CPU fallback */
+    TR_ERR_STACK = -5          /* "overflow, need larger stack" (Scene.py:741-742) */
+} tr_status;
+
+/* Counters and timings of the last tr_render_pt_rgb batch (device counters, CUDA events). */
+typedef struct tr_stats {
+    uint64_t rays_closest;     /* closest-hit traversals  (integrator/PT_RGB.py:65)  */
+    uint64_t rays_shadow;      /* shadow traversals       (integrator/PT_RGB.py:104) */
+    uint64_t node_visits;      /* internal-node visits (only when built with -DTR_COUNTERS) */
+    uint64_t leaf_tests;       /* leaf tests           (only when built with -DTR_COUNTERS) */
+    uint64_t kernel_launches;  /* kernels launched by the last render call */
+    float    ms_total;         /* device time of the last render call (CUDA events on ctx stream) */
+    float    ms_trace;         /* sum over stages, only when stage timing is enabled */
+    float    ms_shade;
+    float    ms_shadow;
+    float    ms_build;         /* device time of the last tr_bvh_build */
+    int32_t  frames;           /* frames rendered by the last call */
+    int32_t  paths_in_flight;  /* path slots per batch */
+    uint64_t node_visits_shadow; /* shadow-query visits (only with -DTR_COUNTERS) */
+    uint64_t leaf_tests_shadow;
+} tr_stats;
+
+/* ---- context ---------------------------------------------------------------------------- */
+/* replaces ti.init(arch=ti.gpu) (example/cornell_box.py:15) */
+int  tr_ctx_create(int device, tr_ctx** out);
+void tr_ctx_destroy(tr_ctx* ctx);
+const char* tr_last_error(tr_ctx* ctx);          /* ctx may be NULL: last global error */
+int  tr_device_count(void);
+int  tr_synchronize(tr_ctx* ctx);
+/* run all subsequent work of this context on the caller's CUDA stream (cudaStream_t as void*), e.g.
+ * torch's current stream, so that host-side events and NCCL calls order naturally; NULL restores the
+ * context's own stream. */
+int  tr_stream_set(tr_ctx* ctx, void* cuda_stream);
+
+/* ---- scene upload: replaces the from_numpy calls of Scene.setup_data_gpu (Scene.py:299-309) ---
+ * vertex nv x 9 f32, prim np x 3 i32, material nm x 10 f32, shape ns x 10 f32 (may be NULL, ns=0),
+ * light nl i32 (may be NULL, nl=0): exactly the tables packed at Scene.py:225-273. */
+int tr_scene_upload(tr_ctx* ctx, const float* vertex, int nv, const int32_t* prim, int np,
+                    const float* material, int nm, const float* shape, int ns,
+                    const int32_t* light, int nl, const float bmin[3], const float bmax[3]);
+/* material table may be re-uploaded alone (values frozen at first launch in Taichi) */
+int tr_material_upload(tr_ctx* ctx, const float* material, int nm);
+/* replaces Texture.setup_data_gpu (texture/Texture.py:41-42): buf[x][y] packed RGB i32 */
+int tr_env_upload(tr_ctx* ctx, const int32_t* rgb, int w, int h, float power);
+
+/* ---- LBVH: replaces Bvh.setup_data_gpu (accel/LBvh.py:192-226): build_morton_3d, radix_sort_host,
+ * build_lbvh, gen_aabb loop and the host-side flatten_tree, all on the device. */
+int tr_bvh_build(tr_ctx* ctx);
+/* reference-layout views (any pointer may be NULL): morton_code_s n x 2 i32 (code, prim) after the
+ * sort; bvh_node (2n-1) x 11 f32 (UtilsFunc.py:24-26); compact_node (2n-1) x 9 f32 (:28-30) */
+int tr_bvh_download(tr_ctx* ctx, int32_t* morton_sorted, float* bvh_node, float* compact_node);
+/* unsorted Morton codes as written by build_morton_3d (accel/LBvh.py:318-336): n x 2 i32 */
+int tr_morton_download(tr_ctx* ctx, int32_t* morton_unsorted);
+
+/* replaces Scene.process_normal (Scene.py:754-798) and Scene.total_area (:747-750) */
+int tr_process_normal(tr_ctx* ctx);
+int tr_vertex_download(tr_ctx* ctx, float* vertex /* nv x 9 */);
+int tr_total_area(tr_ctx* ctx, float* area);
+
+/* ---- camera: replaces the from_numpy calls of Camera.update (Camera.py:87-93) */
+int tr_camera_set(tr_ctx* ctx, const float view[16], const float view_inv[16], const float eye[3],
+                  float fx, float fy, float cx, float cy);
+
+/* ---- film: replaces the hdr / rgb_film fields (integrator/PT_RGB.py:27-37); index [x*H+y][3] */
+int tr_film_create(tr_ctx* ctx, int W, int H);
+int tr_film_clear(tr_ctx* ctx);
+int tr_film_download(tr_ctx* ctx, float* hdr /* W*H*3 or NULL */, float* rgb /* W*H*3 or NULL */);
+int tr_film_upload(tr_ctx* ctx, const float* hdr /* W*H*3 */);
+/* device pointer of hdr (W*H*3 f32) for zero-copy interop (NCCL reduce through torch.distributed) */
+int tr_film_device_ptr(tr_ctx* ctx, void** hdr_dev, void** rgb_dev);
+
+/* pixel-tile sharding: this context renders the 32x32 tiles t with (tx + 3*ty) % nranks == rank;
+ * pixels of other ranks stay 0 in hdr so that a SUM over ranks gives the image. Default (0,1). */
+int tr_set_shard(tr_ctx* ctx, int rank, int nranks);
+
+/* ---- integrators ------------------------------------------------------------------------ */
+/* replaces PT_RGB.PathTrace.render (integrator/PT_RGB.py:44-136) for frames
+ * [frame_begin, frame_begin+n_frames): wavefront generate -> trace -> shade -> shadow -> accumulate.
+ * Asynchronous on the context stream. stack_size is accepted for API parity (the traversal is
+ * stackless); max_depth is the reference's MAX_DEPTH (15). */
+int tr_render_pt_rgb(tr_ctx* ctx, int frame_begin, int n_frames, int max_depth, uint64_t seed);
+/* replaces Debug.render (integrator/Debug.py:44-66); also fills the first-hit buffers */
+int tr_render_debug(tr_ctx* ctx);
+/* frame-0 primary rays and first hits, index [x*H+y]; any pointer may be NULL */
+int tr_first_hit_download(tr_ctx* ctx, float* t, int32_t* prim, float* uv /*2*/, float* pos /*3*/,
+                          float* gnormal /*3*/, float* normal /*3*/, float* dir /*3*/);
+/* replaces UF.tone_map (UtilsFunc.py:583-586): rgb = srgb(ACES(hdr * exposure)) */
+int tr_tonemap(tr_ctx* ctx, float exposure);
+int tr_stats_get(tr_ctx* ctx, tr_stats* out);
+/* tuning: frames per wavefront batch (0 = auto), stage timing on/off, CUDA-graph replay on/off */
+int tr_set_option(tr_ctx* ctx, const char* name, int value);
+
+/* ---- unit hooks: the device functions of the shading/traversal kernels run on arrays, for parity
+ * tests against the oracle (brdf/Disney.py:17-108, brdf/Glass.py:9-34, UtilsFunc.py:440-461,
+ * Scene.py:671-744). Host pointers in, host pointers out. */
+int tr_test_disney_evaluate_pdf(tr_ctx* ctx, int n, const float* N, const float* V, const float* L,
+                                float metal, float rough, float* out /* n x 2 */);
+int tr_test_disney_sample(tr_ctx* ctx, int n, const float* dir, const float* N, float metal,
+                          float rough, const float* u /* n x 3 */, float* out /* n x 3 */);
+int tr_test_glass_sample(tr_ctx* ctx, int n, const float* dir, const float* N, float ior,
+                         const float* u /* n */, float* out /* n x 4 */);
+int tr_test_offset_ray(tr_ctx* ctx, int n, const float* p, const float* nrm, float* out /* n x 3 */);
+int tr_test_rng(tr_ctx* ctx, uint64_t seed, uint32_t pixel, uint32_t frame, uint32_t block, float* out4);
+/* arbitrary rays through the traversal kernels; shadow != 0 uses the nearest-hit shadow query */
+int tr_test_trace(tr_ctx* ctx, int n, const float* o, const float* d, int shadow,
+                  float* t, int32_t* prim, float* uv /* n x 2 or NULL */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TIRAY_H */

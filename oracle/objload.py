@@ -185,7 +185,12 @@ def load_scene(paths, shapes=(), material_edit=None):
             a = [verts[i + 1][k] - verts[i][k] for k in range(3)]
             b = [verts[i + 2][k] - verts[i][k] for k in range(3)]
             n = [a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]]
-            l = 1.0 / (n[0] * n[0] + n[1] * n[1] + n[2] * n[2]) ** 0.5
+            ln = (n[0] * n[0] + n[1] * n[1] + n[2] * n[2]) ** 0.5
+            if ln == 0.0:
+                # degenerate triangle (mc.obj has some): the reference raises ZeroDivisionError here
+                # (Scene.py:176); both this oracle and the product keep the zero normal instead.
+                continue
+            l = 1.0 / ln
             n = [n[0] * l, n[1] * l, n[2] * l]
             for j in range(3):
                 verts[i + j][3:6] = n

@@ -1,0 +1,71 @@
+import os
+import sys
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "ti-raytrace_b200")
+for p in (PKG, os.path.join(PKG, "integrator"), os.path.join(PKG, "example"), os.path.join(PKG, "brdf"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+def model(name):
+    return os.path.join(PKG, "model", name)
+
+
+SCENES = {
+    "cornell": dict(files=["cornell_box.obj"]),
+    "sphere": dict(files=["sphere.obj"]),
+    "teapot": dict(files=["Teapot.obj"]),
+    "teapot_mc": dict(files=["mc.obj", "Teapot.obj"]),
+}
+
+
+@pytest.fixture(scope="session")
+def oracle_tables():
+    """name -> oracle-side packed tables (oracle/objload.py), cached per session"""
+    from oracle import objload
+    cache = {}
+
+    def get(name, sphere_light=False, glass0=False):
+        key = (name, sphere_light, glass0)
+        if key not in cache:
+            shapes = [objload.sphere_light_rows()] if sphere_light else []
+
+            def edit(mats):
+                if glass0:
+                    mats[0][0] = 1.0; mats[0][5] = 1.3; mats[0][6] = 5.0
+            cache[key] = objload.load_scene([model(f) for f in SCENES[name]["files"]], shapes=shapes, material_edit=edit)
+        return cache[key]
+    return get
+
+
+def make_product_scene(name, sphere_light=False, glass0=False, env_power=0.0):
+    """product-side Scene (host packing only; no device calls)"""
+    import Scene
+    import SceneData as SCD
+    s = Scene.Scene()
+    for f in SCENES[name]["files"]:
+        s.add_obj("model/" + f)
+    if glass0:
+        m = s.material_cpu[0]; m.type = SCD.MAT_GLASS; m.setIor(1.3); m.setExtinciton(5.0)
+    if sphere_light:
+        sh = SCD.Shape(); sh.type = SCD.SHPAE_SPHERE; sh.pos = [0.0, 20.0, 0.0]; sh.setRadius(5.0)
+        mt = SCD.Material(); mt.type = SCD.MAT_LIGHT; mt.setColor([50.0, 50.0, 50.0])
+        s.add_shape(sh, mt)
+    if env_power:
+        s.add_env("image/env.png", env_power)
+    return s
+
+
+@pytest.fixture()
+def gpu_ctx():
+    """fresh device context (ti.init semantics)"""
+    import _native
+    return _native.reset_context()

@@ -1,0 +1,288 @@
+"""ctypes binding of libtiray.so (include/tiray.h) and the process-wide device context.
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is visible, every
+device operation raises.  One context per process (one process per GPU), like Taichi's single program.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+LIB_NAME = os.environ.get("TIRAY_LIB", "libtiray.so")
+
+_f32 = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_i32 = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_vp = C.c_void_p
+
+
+class Stats(C.Structure):
+    _fields_ = [("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64), ("node_visits", C.c_uint64),
+                ("leaf_tests", C.c_uint64), ("kernel_launches", C.c_uint64), ("ms_total", C.c_float),
+                ("ms_trace", C.c_float), ("ms_shade", C.c_float), ("ms_shadow", C.c_float), ("ms_build", C.c_float),
+                ("frames", C.c_int32), ("paths_in_flight", C.c_int32),
+                ("node_visits_shadow", C.c_uint64), ("leaf_tests_shadow", C.c_uint64)]
+
+
+# every symbol include/tiray.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "tr_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "tr_ctx_destroy": (None, [_vp]),
+    "tr_last_error": (C.c_char_p, [_vp]),
+    "tr_device_count": (C.c_int, []),
+    "tr_synchronize": (C.c_int, [_vp]),
+    "tr_stream_set": (C.c_int, [_vp, _vp]),
+    "tr_scene_upload": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp]),
+    "tr_material_upload": (C.c_int, [_vp, _vp, C.c_int]),
+    "tr_env_upload": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_float]),
+    "tr_bvh_build": (C.c_int, [_vp]),
+    "tr_bvh_download": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "tr_morton_download": (C.c_int, [_vp, _vp]),
+    "tr_process_normal": (C.c_int, [_vp]),
+    "tr_vertex_download": (C.c_int, [_vp, _vp]),
+    "tr_total_area": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "tr_camera_set": (C.c_int, [_vp, _vp, _vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float]),
+    "tr_film_create": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "tr_film_clear": (C.c_int, [_vp]),
+    "tr_film_download": (C.c_int, [_vp, _vp, _vp]),
+    "tr_film_upload": (C.c_int, [_vp, _vp]),
+    "tr_film_device_ptr": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
+    "tr_set_shard": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "tr_render_pt_rgb": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_uint64]),
+    "tr_render_debug": (C.c_int, [_vp]),
+    "tr_first_hit_download": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tr_tonemap": (C.c_int, [_vp, C.c_float]),
+    "tr_stats_get": (C.c_int, [_vp, C.POINTER(Stats)]),
+    "tr_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),
+    "tr_test_disney_evaluate_pdf": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_float, C.c_float, _vp]),
+    "tr_test_disney_sample": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_float, C.c_float, _vp, _vp]),
+    "tr_test_glass_sample": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_float, _vp, _vp]),
+    "tr_test_offset_ray": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
+    "tr_test_rng": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _vp]),
+    "tr_test_trace": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp]),
+}
+
+_libs = {}
+
+
+def lib_path(name=None):
+    return os.path.join(ROOT, name or LIB_NAME)
+
+
+def load_library(name=None):
+    """Load libtiray.so (built in-tree by __graft_entry__.build / csrc/Makefile). Raises if absent.
+    name selects another flavour of the same ABI (libtiray_counters.so: per-ray visit counters)."""
+    name = name or LIB_NAME
+    if name not in _libs:
+        path = lib_path(name)
+        if not os.path.exists(path):
+            raise RuntimeError("%s not found: build it with `make -C %s` (there is no CPU fallback)"
+                               % (path, os.path.join(ROOT, "csrc")))
+        lib = C.CDLL(path)
+        for sym, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, sym)           # AttributeError if the library does not export the symbol
+            fn.restype, fn.argtypes = res, args
+        _libs[name] = lib
+    return _libs[name]
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def _f(a, shape=None):
+    a = np.ascontiguousarray(a, np.float32)
+    return a if shape is None else a.reshape(shape)
+
+
+class Context:
+    """Owner of one tr_ctx. All methods raise RuntimeError with the library's error text on failure."""
+
+    def __init__(self, device=None, lib_name=None):
+        self.lib = load_library(lib_name)
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        h = _vp()
+        rc = self.lib.tr_ctx_create(int(device), C.byref(h))
+        if rc != 0:
+            raise RuntimeError("tr_ctx_create(%d) failed: %s" % (device, (self.lib.tr_last_error(None) or b"").decode()))
+        self.h, self.device = h, int(device)
+        self.W = self.H = 0
+        self.n_prims = self.n_verts = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.tr_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise RuntimeError("%s failed (%d): %s" % (what, rc, (self.lib.tr_last_error(self.h) or b"").decode()))
+
+    # ---- scene
+    def scene_upload(self, vertex, prim, material, shape, light, bmin, bmax):
+        v = _f(vertex); p = np.ascontiguousarray(prim, np.int32); m = _f(material)
+        s = _f(shape) if shape is not None and len(shape) else None
+        l = np.ascontiguousarray(light, np.int32) if light is not None and len(light) else None
+        self._ck(self.lib.tr_scene_upload(self.h, _ptr(v), v.shape[0], _ptr(p), p.shape[0], _ptr(m), m.shape[0],
+                                          _ptr(s), 0 if s is None else s.shape[0], _ptr(l), 0 if l is None else l.shape[0],
+                                          _ptr(_f(bmin).reshape(-1)), _ptr(_f(bmax).reshape(-1))), "tr_scene_upload")
+        self.n_prims, self.n_verts = p.shape[0], v.shape[0]
+
+    def material_upload(self, material):
+        m = _f(material); self._ck(self.lib.tr_material_upload(self.h, _ptr(m), m.shape[0]), "tr_material_upload")
+
+    def env_upload(self, packed, w, h, power):
+        a = np.ascontiguousarray(packed, np.int32)
+        self._ck(self.lib.tr_env_upload(self.h, _ptr(a), int(w), int(h), float(power)), "tr_env_upload")
+
+    def bvh_build(self):
+        self._ck(self.lib.tr_bvh_build(self.h), "tr_bvh_build")
+
+    def bvh_download(self):
+        n = self.n_prims
+        morton = np.zeros((n, 2), np.int32); node = np.zeros((2 * n - 1, 11), np.float32); comp = np.zeros((2 * n - 1, 9), np.float32)
+        self._ck(self.lib.tr_bvh_download(self.h, _ptr(morton), _ptr(node), _ptr(comp)), "tr_bvh_download")
+        return morton, node, comp
+
+    def morton_download(self):
+        out = np.zeros((self.n_prims, 2), np.int32)
+        self._ck(self.lib.tr_morton_download(self.h, _ptr(out)), "tr_morton_download"); return out
+
+    def process_normal(self):
+        self._ck(self.lib.tr_process_normal(self.h), "tr_process_normal")
+
+    def vertex_download(self):
+        out = np.zeros((self.n_verts, 9), np.float32)
+        self._ck(self.lib.tr_vertex_download(self.h, _ptr(out)), "tr_vertex_download"); return out
+
+    def total_area(self):
+        a = C.c_float(0.0); self._ck(self.lib.tr_total_area(self.h, C.byref(a)), "tr_total_area"); return float(a.value)
+
+    # ---- camera / film
+    def camera_set(self, view, view_inv, eye, fx, fy, cx, cy):
+        self._ck(self.lib.tr_camera_set(self.h, _ptr(_f(view).reshape(-1)), _ptr(_f(view_inv).reshape(-1)),
+                                        _ptr(_f(eye).reshape(-1)), fx, fy, cx, cy), "tr_camera_set")
+
+    def film_create(self, W, H):
+        self._ck(self.lib.tr_film_create(self.h, int(W), int(H)), "tr_film_create"); self.W, self.H = int(W), int(H)
+
+    def film_clear(self):
+        self._ck(self.lib.tr_film_clear(self.h), "tr_film_clear")
+
+    def film_download(self, hdr=True, rgb=False):
+        a = np.zeros((self.W, self.H, 3), np.float32) if hdr else None
+        b = np.zeros((self.W, self.H, 3), np.float32) if rgb else None
+        self._ck(self.lib.tr_film_download(self.h, _ptr(a), _ptr(b)), "tr_film_download")
+        return a, b
+
+    def film_upload(self, hdr):
+        a = _f(hdr); assert a.size == self.W * self.H * 3
+        self._ck(self.lib.tr_film_upload(self.h, _ptr(a)), "tr_film_upload")
+
+    def film_device_ptr(self):
+        a, b = _vp(), _vp()
+        self._ck(self.lib.tr_film_device_ptr(self.h, C.byref(a), C.byref(b)), "tr_film_device_ptr")
+        return a.value, b.value
+
+    def set_shard(self, rank, nranks):
+        self._ck(self.lib.tr_set_shard(self.h, int(rank), int(nranks)), "tr_set_shard")
+
+    # ---- integrators
+    def render_pt_rgb(self, frame_begin, n_frames, max_depth=15, seed=0):
+        self._ck(self.lib.tr_render_pt_rgb(self.h, int(frame_begin), int(n_frames), int(max_depth), int(seed)), "tr_render_pt_rgb")
+
+    def render_debug(self):
+        self._ck(self.lib.tr_render_debug(self.h), "tr_render_debug")
+
+    def first_hit_download(self):
+        n = self.W * self.H
+        t = np.zeros(n, np.float32); prim = np.zeros(n, np.int32); uv = np.zeros((n, 2), np.float32)
+        pos = np.zeros((n, 3), np.float32); gn = np.zeros((n, 3), np.float32); nr = np.zeros((n, 3), np.float32); d = np.zeros((n, 3), np.float32)
+        self._ck(self.lib.tr_first_hit_download(self.h, _ptr(t), _ptr(prim), _ptr(uv), _ptr(pos), _ptr(gn), _ptr(nr), _ptr(d)), "tr_first_hit_download")
+        W, H = self.W, self.H
+        return dict(t=t.reshape(W, H), prim=prim.reshape(W, H), uv=uv.reshape(W, H, 2), pos=pos.reshape(W, H, 3),
+                    gnormal=gn.reshape(W, H, 3), normal=nr.reshape(W, H, 3), dir=d.reshape(W, H, 3))
+
+    def tonemap(self, exposure):
+        self._ck(self.lib.tr_tonemap(self.h, float(exposure)), "tr_tonemap")
+
+    def stream_set(self, cuda_stream):
+        """run on the caller's stream (e.g. torch.cuda.current_stream().cuda_stream); None restores"""
+        self._ck(self.lib.tr_stream_set(self.h, cuda_stream), "tr_stream_set")
+
+    def synchronize(self):
+        self._ck(self.lib.tr_synchronize(self.h), "tr_synchronize")
+
+    def stats(self):
+        s = Stats(); self._ck(self.lib.tr_stats_get(self.h, C.byref(s)), "tr_stats_get")
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    def set_option(self, name, value):
+        self._ck(self.lib.tr_set_option(self.h, name.encode(), int(value)), "tr_set_option")
+
+    # ---- unit hooks
+    def test_disney_evaluate_pdf(self, N, V, L, metal, rough):
+        N, V, L = _f(N, (-1, 3)), _f(V, (-1, 3)), _f(L, (-1, 3)); out = np.zeros((N.shape[0], 2), np.float32)
+        self._ck(self.lib.tr_test_disney_evaluate_pdf(self.h, N.shape[0], _ptr(N), _ptr(V), _ptr(L), metal, rough, _ptr(out)), "hook"); return out
+
+    def test_disney_sample(self, d, N, metal, rough, u):
+        d, N, u = _f(d, (-1, 3)), _f(N, (-1, 3)), _f(u, (-1, 3)); out = np.zeros((d.shape[0], 3), np.float32)
+        self._ck(self.lib.tr_test_disney_sample(self.h, d.shape[0], _ptr(d), _ptr(N), metal, rough, _ptr(u), _ptr(out)), "hook"); return out
+
+    def test_glass_sample(self, d, N, ior, u):
+        d, N, u = _f(d, (-1, 3)), _f(N, (-1, 3)), _f(u, (-1,)); out = np.zeros((d.shape[0], 4), np.float32)
+        self._ck(self.lib.tr_test_glass_sample(self.h, d.shape[0], _ptr(d), _ptr(N), ior, _ptr(u), _ptr(out)), "hook"); return out
+
+    def test_offset_ray(self, p, n):
+        p, n = _f(p, (-1, 3)), _f(n, (-1, 3)); out = np.zeros_like(p)
+        self._ck(self.lib.tr_test_offset_ray(self.h, p.shape[0], _ptr(p), _ptr(n), _ptr(out)), "hook"); return out
+
+    def test_rng(self, seed, pixel, frame, block):
+        out = np.zeros(4, np.float32); self._ck(self.lib.tr_test_rng(self.h, seed, pixel, frame, block, _ptr(out)), "hook"); return out
+
+    def test_trace(self, o, d, shadow=False):
+        o, d = _f(o, (-1, 3)), _f(d, (-1, 3)); n = o.shape[0]
+        t = np.zeros(n, np.float32); prim = np.zeros(n, np.int32); uv = np.zeros((n, 2), np.float32)
+        self._ck(self.lib.tr_test_trace(self.h, n, _ptr(o), _ptr(d), int(shadow), _ptr(t), _ptr(prim), _ptr(uv)), "tr_test_trace")
+        return t, prim, uv
+
+
+_ctx = None
+
+
+def context():
+    """The process-wide context (created on first use or by ti.init)."""
+    global _ctx
+    if _ctx is None:
+        _ctx = Context()
+    return _ctx
+
+
+def reset_context(device=None):
+    """ti.init() semantics: drop all device state and start a fresh program."""
+    global _ctx
+    if _ctx is not None:
+        _ctx.close()
+    _ctx = Context(device)
+    return _ctx
+
+
+class Field:
+    """Stand-in for a Taichi field on the reference's API surface: .to_numpy() / .from_numpy()."""
+
+    def __init__(self, getter, setter=None):
+        self._get, self._set = getter, setter
+
+    def to_numpy(self):
+        return self._get()
+
+    def from_numpy(self, a):
+        if self._set is None:
+            raise RuntimeError("this field is read-only on the host")
+        self._set(a)

@@ -1,0 +1,123 @@
+// ctx.h — the per-GPU context behind the C-ABI of include/tiray.h
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/tiray.h"
+
+#define TR_MAX_DEPTH_CAP 64       // counters are sized for this many wavefront stages
+#define TR_TILE 32                // framebuffer tile edge used for sharding and ray coherence
+
+// Traversal node, 32 B, left-first pre-order (left child = idx+1), threaded with an escape index.
+//   lo = (min.x, min.y, min.z, as_float(escape))      escape = idx + subtree size
+//   hi = (max.x, max.y, max.z, as_float(link))        link >= 0: pre-order index of the right child
+//                                                     link <  0: leaf, sorted position k = -link-1
+struct TrNode { float4 lo, hi; };
+// Leaf record, 48 B, in sorted (Morton) order:
+//   a = (v0.xyz, as_float(prim id)), b = (E1.xyz, as_float(kind)), c = (E2.xyz, as_float(material id))   kind 0: triangle
+//   a = (centre.xyz, prim id),       b = (radius, 0, 0, kind)                         kind 1: sphere
+//   kind 2: shape that never intersects (Scene.py:597-598)
+struct TrLeaf { float4 a, b, c; };
+// Shading record per primitive, 96 B (built lazily: process_normal may rewrite normals)
+//   q0 = (v1, as_float(mat)), q1 = (v2, as_float(kind)), q2 = (v3, area), q3..q5 = (n1), (n2), (n3)
+//   sphere: q0 = (centre, mat), q1 = (radius,0,0,kind=1), q2 = (0,0,0,area)
+struct TrShade { float4 q[6]; };
+
+struct TrCamera { float view_inv[16]; float eye[3]; float fx, fy, cx, cy; };
+
+// device-side counters of one wavefront batch
+struct TrCounters {
+    int nq[TR_MAX_DEPTH_CAP + 1];        // live paths entering stage d
+    int nshadow[TR_MAX_DEPTH_CAP + 1];   // shadow rays emitted by stage d
+    int ncls[TR_MAX_DEPTH_CAP + 1][4];   // material-sorted shade queue sizes: terminal, disney, glass
+    int wf_trace[TR_MAX_DEPTH_CAP + 1];  // work-fetch cursors of the persistent trace kernels
+    int wf_shadow[TR_MAX_DEPTH_CAP + 1];
+    unsigned long long visits[4];        // closest: nodes, leaves; shadow: nodes, leaves (only with -DTR_COUNTERS)
+};
+
+struct tr_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // scene tables (reference layouts, device copies)
+    float* d_vertex = nullptr; int nv = 0;
+    int*   d_prim = nullptr;   int np = 0;
+    float* d_material = nullptr; int nm = 0;
+    float* d_shape = nullptr;  int ns = 0;
+    int*   d_light = nullptr;  int nl = 0;
+    float bmin[3] = {0, 0, 0}, bmax[3] = {0, 0, 0};
+    int*   d_env = nullptr; int env_w = 0, env_h = 0; float env_power = 0.0f;
+
+    // LBVH build products
+    bool bvh_ready = false;
+    int*   d_morton_unsorted = nullptr;  // n x 2
+    int*   d_keys[2] = {nullptr, nullptr};
+    int*   d_vals[2] = {nullptr, nullptr};
+    int    sorted_buf = 0;
+    int*   d_left = nullptr; int* d_right = nullptr; int* d_parent = nullptr;   // 2n-1 (build-order ids)
+    float* d_boxes = nullptr;            // (2n-1) x 6
+    int*   d_leafcount = nullptr; int* d_flag = nullptr; int* d_pre = nullptr;
+    int*   d_build_status = nullptr;     // [0] = refit-completed internal nodes
+    TrNode* d_nodes = nullptr; TrLeaf* d_leaves = nullptr; int* d_leaf_of_prim = nullptr;
+    TrShade* d_shade = nullptr; bool shade_ready = false;
+    int*   d_hist = nullptr; size_t hist_cap = 0;
+
+    // camera + film
+    TrCamera cam; bool cam_set = false;
+    int W = 0, H = 0;
+    float* d_hdr = nullptr; float* d_rgb = nullptr;
+    // first-hit buffers (Debug integrator)
+    float* d_fh = nullptr;      // W*H*16 floats: t, prim, u, v, pos3, gn3, n3, dir3
+    bool fh_ready = false;
+
+    // sharding
+    int rank = 0, nranks = 1;
+    int* d_tiles = nullptr; int n_local_tiles = 0; bool tiles_ready = false;
+
+    // wavefront buffers
+    size_t wf_cap = 0;              // path slots allocated
+    float4* d_path[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    float4* d_hit = nullptr;
+    int*    d_cls = nullptr;        // 3 x cap indices (material-sorted shade queues)
+    float4* d_shq[3] = {nullptr, nullptr, nullptr};
+    float4* d_L = nullptr;          // per-sample radiance
+    TrCounters* d_ctr = nullptr;
+    TrCounters h_ctr;
+
+    // options
+    int opt_batch_frames = 0;       // 0 = auto
+    int opt_stage_timing = 0;
+    int opt_graph = 1;
+    int opt_smem_bvh = 1;
+    size_t opt_max_paths = (size_t)8 << 20;
+
+    // cuda graph cache for the batch pipeline
+    cudaGraphExec_t graph_exec = nullptr; int graph_launches = 0, graph_depth = 0;
+    unsigned long long gen = 0, graph_gen = 0;   // any state change bumps gen; a captured graph is valid for one gen
+    void* d_batch_params = nullptr;
+
+    tr_stats stats;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> stage_ev;
+    cudaStream_t own_stream = nullptr;   // ctx->stream may be redirected to a caller's stream (tr_stream_set)
+};
+
+int tr_fail(tr_ctx* ctx, int code, const char* fmt, ...);
+#define TR_CUDA(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return tr_fail(ctx, TR_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
+#define TR_CHECK_LAUNCH(ctx) TR_CUDA(ctx, cudaGetLastError())
+
+template <typename T> static inline int tr_realloc(tr_ctx* ctx, T** p, size_t count) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count == 0) count = 1;
+    TR_CUDA(ctx, cudaMalloc((void**)p, count * sizeof(T)));
+    return TR_OK;
+}
+
+// implemented across the .cu files
+int tr_build_shade_table(tr_ctx* ctx);
+int tr_build_tiles(tr_ctx* ctx);

@@ -1,0 +1,209 @@
+// trace.cuh — stackless (threaded pre-order) LBVH traversal + Moller-Trumbore, device side.
+//
+// Replaces Scene.closet_hit / closet_hit_shadow (Scene.py:671-744), which walk the same pre-order
+// node array with an explicit per-pixel stack in global memory, unordered and unpruned.  Here the
+// walk follows escape links (no stack), prunes sub-trees whose slab entry lies beyond the best hit
+// (with a relative guard band so exact/near ties are still tested) and keeps the reference's result:
+// the reference pops the right child first and accepts strict t < best, so among equal-t hits the
+// leaf with the LARGEST sorted position wins; a left-first walk reproduces that with t <= best.
+#pragma once
+#include "ctx.h"
+#include "common.cuh"
+
+#define TR_PRUNE_GUARD 1.0001f
+
+struct RayPre {
+    V3 o, d;
+    float ix, iy, iz;      // 1/d per axis (UtilsFunc.py:510), unused when the axis is "parallel"
+    bool px, py, pz;       // |d| < 1e-6 (UtilsFunc.py:506)
+};
+
+__device__ __forceinline__ RayPre make_ray(V3 o, V3 d) {
+    RayPre r; r.o = o; r.d = d;
+    r.px = fabsf(d.x) < 0.000001f; r.py = fabsf(d.y) < 0.000001f; r.pz = fabsf(d.z) < 0.000001f;
+    r.ix = 1.0f / d.x; r.iy = 1.0f / d.y; r.iz = 1.0f / d.z;
+    return r;
+}
+
+// UtilsFunc.py:494-523, plus tmin returned for pruning
+__device__ __forceinline__ bool slabs(const RayPre& r, float4 lo, float4 hi, float& tmin_out) {
+    bool ret = true; float tmin = 0.0f, tmax = TR_INF;
+    if (r.px) { if (r.o.x < lo.x || r.o.x > hi.x) ret = false; }
+    else { float t1 = (lo.x - r.o.x) * r.ix, t2 = (hi.x - r.o.x) * r.ix; tmin = fmaxf(tmin, fminf(t1, t2)); tmax = fminf(tmax, fmaxf(t1, t2)); }
+    if (r.py) { if (r.o.y < lo.y || r.o.y > hi.y) ret = false; }
+    else { float t1 = (lo.y - r.o.y) * r.iy, t2 = (hi.y - r.o.y) * r.iy; tmin = fmaxf(tmin, fminf(t1, t2)); tmax = fminf(tmax, fmaxf(t1, t2)); }
+    if (r.pz) { if (r.o.z < lo.z || r.o.z > hi.z) ret = false; }
+    else { float t1 = (lo.z - r.o.z) * r.iz, t2 = (hi.z - r.o.z) * r.iz; tmin = fmaxf(tmin, fminf(t1, t2)); tmax = fminf(tmax, fmaxf(t1, t2)); }
+    tmin_out = tmin;
+    return ret && !(tmin > tmax);
+}
+
+// Scene.py:603-638 with E1/E2 precomputed at build time (same single-rounding subtractions)
+__device__ __forceinline__ void intersect_tri(V3 o, V3 d, V3 v0, V3 E1, V3 E2, float& t, float& u, float& v) {
+    t = TR_INF; u = 0.0f; v = 0.0f;
+    V3 P = cross3(d, E2);
+    float det = dot3(E1, P);
+    V3 T;
+    if (det > 0.0f) T = o - v0; else { T = v0 - o; det = -det; }
+    if (det > 0.0f) {
+        u = dot3(T, P);
+        if (u >= 0.0f && u <= det) {
+            V3 Q = cross3(T, E1);
+            v = dot3(d, Q);
+            if (v >= 0.0f && u + v <= det) {
+                t = dot3(E2, Q);
+                float inv = 1.0f / det;
+                t *= inv; u *= inv; v *= inv;
+            }
+        }
+    }
+}
+
+// Scene.py:565-596 / 653-665: analytic sphere, nearest root only; returns the reference's scalar c
+__device__ __forceinline__ bool intersect_sphere(V3 o, V3 d, V3 ce, float r, float& t, float& c_out) {
+    V3 oc = ce - o; float oc2 = dot3(oc, oc), op = dot3(d, oc);
+    float cp = sqrtf(oc2 - op * op);
+    t = TR_INF; c_out = 0.0f;
+    if (cp < r) {
+        float a = dot3(d, d), b = -2.0f * op, c = oc2 - r * r;
+        t = (-b - sqrtf(b * b - 4.0f * a * c)) / 2.0f / a;
+        c_out = c;
+        return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ float intersect_leaf(const RayPre& r, float4 la, float4 lb, float4 lc, float& u, float& v) {
+    int kind = __float_as_int(lb.w);
+    float t;
+    if (kind == 0) {
+        intersect_tri(r.o, r.d, f4xyz(la), f4xyz(lb), f4xyz(lc), t, u, v);
+    } else if (kind == 1) {
+        float c; u = 0.0f; v = 0.0f;
+        intersect_sphere(r.o, r.d, f4xyz(la), lb.x, t, c);
+    } else { t = TR_INF; u = v = 0.0f; }
+    return t;
+}
+
+struct HitRec { float t, u, v; int prim; int mat; };
+
+#ifdef TR_COUNTERS
+#define TR_COUNT_NODE() (++cnt_nodes)
+#define TR_COUNT_LEAF() (++cnt_leaves)
+#else
+#define TR_COUNT_NODE()
+#define TR_COUNT_LEAF()
+#endif
+
+// Closest hit (Scene.py:702-744 semantics).  nodes/leaves may point to shared or global memory.
+__device__ __forceinline__ HitRec trace_closest(const TrNode* __restrict__ nodes, const TrLeaf* __restrict__ leaves, int nnodes,
+                                                 const RayPre& r, unsigned long long* cnt) {
+    HitRec h; h.t = TR_INF; h.u = 0.0f; h.v = 0.0f; h.prim = -1; h.mat = 0;
+#ifdef TR_COUNTERS
+    unsigned cnt_nodes = 0, cnt_leaves = 0;
+#endif
+    int idx = 0;
+    while (idx < nnodes) {
+        float4 lo = nodes[idx].lo, hi = nodes[idx].hi;
+        int link = __float_as_int(hi.w);
+        if (link < 0) {
+            TR_COUNT_LEAF();
+            const TrLeaf* lf = leaves + (-link - 1);
+            float4 la = lf->a, lb = lf->b, lc = lf->c;
+            float u, v, t = intersect_leaf(r, la, lb, lc, u, v);
+            if (t <= h.t && t > 0.0f && t < TR_INF) { h.t = t; h.u = u; h.v = v; h.prim = __float_as_int(la.w); h.mat = __float_as_int(lc.w); }
+            idx += 1;
+        } else {
+            TR_COUNT_NODE();
+            float tmin;
+            bool hit = slabs(r, lo, hi, tmin) && !(tmin > h.t * TR_PRUNE_GUARD);
+            idx = hit ? idx + 1 : __float_as_int(lo.w);
+        }
+    }
+#ifdef TR_COUNTERS
+    if (cnt) { atomicAdd(cnt, (unsigned long long)cnt_nodes); atomicAdd(cnt + 1, (unsigned long long)cnt_leaves); }
+#endif
+    return h;
+}
+
+// Shadow query.  The reference (integrator/PT_RGB.py:104-105, Scene.py:671-699) finds the nearest
+// hit of the light->surface ray and tests `shadow_prim == prim_id`.  Equivalent early-exit form:
+// intersect the target primitive first (t_t), then walk the tree looking for ANY other primitive
+// that would have won the reference's comparison (t < t_t, or t == t_t at a later leaf position).
+// Returns the reference's (hit_t, hit_prim) only as far as the caller needs it: prim == target or not.
+__device__ __forceinline__ bool trace_shadow_visible(const TrNode* __restrict__ nodes, const TrLeaf* __restrict__ leaves, int nnodes,
+                                                     const RayPre& r, int target_prim, int target_leaf, unsigned long long* cnt) {
+#ifdef TR_COUNTERS
+    unsigned cnt_nodes = 0, cnt_leaves = 0;
+#endif
+    bool visible;
+    {
+        const TrLeaf* lf = leaves + target_leaf;
+        float u, v; float tt = intersect_leaf(r, lf->a, lf->b, lf->c, u, v);
+        TR_COUNT_LEAF();
+        visible = (tt > 0.0f && tt < TR_INF);
+        if (visible) {
+            // the target only counts if the walk actually reaches its leaf (every ancestor passes slabs)
+            bool found = false;
+            int idx = 0;
+            while (idx < nnodes) {
+                float4 lo = nodes[idx].lo, hi = nodes[idx].hi;
+                int link = __float_as_int(hi.w);
+                if (link < 0) {
+                    int k = -link - 1;
+                    if (k == target_leaf) found = true;
+                    else {
+                        TR_COUNT_LEAF();
+                        const TrLeaf* l2 = leaves + k;
+                        float t = intersect_leaf(r, l2->a, l2->b, l2->c, u, v);
+                        if (t > 0.0f && t < TR_INF && (t < tt || (t == tt && k > target_leaf))) { visible = false; break; }
+                    }
+                    idx += 1;
+                } else {
+                    TR_COUNT_NODE();
+                    float tmin;
+                    bool hit = slabs(r, lo, hi, tmin) && !(tmin > tt * TR_PRUNE_GUARD);
+                    idx = hit ? idx + 1 : __float_as_int(lo.w);
+                }
+            }
+            visible = visible && found;
+        }
+    }
+    (void)target_prim;
+#ifdef TR_COUNTERS
+    if (cnt) { atomicAdd(cnt, (unsigned long long)cnt_nodes); atomicAdd(cnt + 1, (unsigned long long)cnt_leaves); }
+#endif
+    return visible;
+}
+
+// ---- TMA bulk staging of the whole BVH into shared memory (small scenes, e.g. the Cornell box)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// One thread issues cp.async.bulk (global -> shared, mbarrier completion); everybody waits.
+// bytes must be a multiple of 16 and both pointers 16-byte aligned.
+__device__ __forceinline__ void tma_stage_to_smem(void* smem_dst, const void* gsrc, unsigned bytes, void* smem_dst2,
+                                                  const void* gsrc2, unsigned bytes2, unsigned long long* bar) {
+    const unsigned bar_a = smem_u32(bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes + bytes2) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(bar_a) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(smem_dst2)), "l"(gsrc2), "r"(bytes2), "r"(bar_a) : "memory");
+    }
+    // wait for phase 0
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar_a) : "memory");
+}

@@ -1,0 +1,677 @@
+// wavefront.cu — the PT_RGB hot path as a wavefront of persistent-thread kernels.
+//
+// Replaces PathTrace.render (integrator/PT_RGB.py:44-136), a one-thread-per-pixel mega-kernel with a
+// per-pixel traversal stack in global memory, by
+//     generate -> [ trace -> shade{terminal | disney | glass} -> shadow ] x max_depth -> accumulate
+// over compacted SoA queues that live in HBM:
+//   path queue (ping-pong)  A=(o.xyz, d.x)  B=(d.y, d.z, brdf_pdf, slot|spec<<31)  C=(T.rgb, pixel id)
+//   hit queue               (t, prim, u, v)                                   16 B
+//   shadow queue            (p.xyz, d.x) (d.y, d.z, target prim, slot) (contribution.rgb, -)   48 B
+//   sample radiance L       float4 per (frame-in-batch, pixel)
+// Queue sizes are device counters, so the whole batch is one fixed launch sequence (CUDA-graph
+// replayable); trace kernels are persistent and fetch 32-ray chunks with one atomic per warp; live
+// paths are compacted with warp-ballot appends; shade work is sorted by material class.
+// Per-path RNG is counter based (Philox4x32-10 keyed by seed; pixel, frame, block), see common.cuh.
+#include "ctx.h"
+#include "common.cuh"
+#include "trace.cuh"
+
+#define WF_THREADS 256
+#define SPEC_BIT 0x80000000u
+
+struct BatchParams { int frame_begin; int n_frames; unsigned long long seed; int max_depth; int pad; };
+
+struct WfArgs {
+    // scene
+    const TrNode* nodes; const TrLeaf* leaves; int nnodes; int nleaves;
+    const TrShade* shade; const float* material; const int* light; int nl; const int* leaf_of_prim;
+    const int* env; int env_w, env_h; float env_power;
+    TrCamera cam;
+    // film / tiles
+    int W, H; const int* tiles; int npix;          // npix = local pixel slots = n_local_tiles * 1024
+    float* hdr;
+    // queues
+    float4* pa[2]; float4* pb[2]; float4* pc[2];
+    float4* hit; int* cls; size_t cap;
+    float4* sa; float4* sb; float4* sc;
+    float4* L;
+    TrCounters* ctr;
+    const BatchParams* bp;
+    unsigned smem_nodes_bytes, smem_leaves_bytes;
+};
+
+// local pixel slot p -> pixel coordinates.  32x32 tiles, inside a tile 4(x) x 8(y) pixel blocks per warp
+__device__ __forceinline__ bool slot_to_pixel(const WfArgs& a, int p, int& x, int& y) {
+    int tile = a.tiles[p >> 10];
+    int ntx = (a.W + TR_TILE - 1) / TR_TILE;
+    int tx = tile % ntx, ty = tile / ntx;
+    int w = p & 1023, b = w >> 5, l = w & 31;
+    x = tx * TR_TILE + (b & 7) * 4 + (l >> 3);
+    y = ty * TR_TILE + (b >> 3) * 8 + (l & 7);
+    return x < a.W && y < a.H;
+}
+
+// Camera.py:122-142
+__device__ __forceinline__ V3 camera_dir(const TrCamera& c, int i, int j, float jx, float jy) {
+    float x = ((float)i + jx - c.cx) / c.fx, y = ((float)j + jy - c.cy) / c.fy, z = -1.0f;
+    const float* m = c.view_inv;
+    V3 w = mk3((m[0] * x + m[1] * y) + m[2] * z, (m[4] * x + m[5] * y) + m[6] * z, (m[8] * x + m[9] * y) + m[10] * z);
+    return normalize3(w);
+}
+
+// warp-aggregated append: returns the queue position for lanes with pred, -1 otherwise
+__device__ __forceinline__ int warp_append(int* counter, bool pred) {
+    unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (m == 0) return -1;
+    int lane = threadIdx.x & 31, leader = __ffs(m) - 1, base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return pred ? base + __popc(m & ((1u << lane) - 1u)) : -1;
+}
+
+// ------------------------------------------------------------------ generate
+__global__ void __launch_bounds__(WF_THREADS) k_generate(WfArgs a) {
+    const BatchParams bp = *a.bp;
+    const int total = bp.n_frames * a.npix;
+    const int stride = gridDim.x * blockDim.x;
+    const int total_r = (total + 31) & ~31;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < total_r; s += stride) {
+        bool valid = false; int x = 0, y = 0, frame = 0;
+        if (s < total) {
+            int f = s / a.npix, p = s - f * a.npix;
+            frame = bp.frame_begin + f;
+            valid = slot_to_pixel(a, p, x, y);
+            a.L[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+        int q = warp_append(&a.ctr->nq[0], valid);
+        if (valid) {
+            unsigned pix = ((unsigned)x << 16) | (unsigned)y;
+            float jx = 0.0f, jy = 0.0f;
+            if (frame != 0) { float4 r = rng4(bp.seed, pix, (unsigned)frame, 0u); jx = r.x - 0.5f; jy = r.y - 0.5f; }
+            V3 d = camera_dir(a.cam, x, y, jx, jy);
+            a.pa[0][q] = make_float4(a.cam.eye[0], a.cam.eye[1], a.cam.eye[2], d.x);
+            a.pb[0][q] = make_float4(d.y, d.z, 1.0f, __uint_as_float((unsigned)s | SPEC_BIT));
+            a.pc[0][q] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(pix));
+        }
+    }
+}
+
+// ------------------------------------------------------------------ BVH staging
+extern __shared__ __align__(128) unsigned char wf_smem[];
+
+template <bool SMEM>
+__device__ __forceinline__ void bvh_view(const WfArgs& a, const TrNode*& nodes, const TrLeaf*& leaves) {
+    if (SMEM) {
+        __shared__ unsigned long long bar;
+        TrNode* sn = (TrNode*)wf_smem; TrLeaf* sl = (TrLeaf*)(wf_smem + a.smem_nodes_bytes);
+        tma_stage_to_smem(sn, a.nodes, a.smem_nodes_bytes, sl, a.leaves, a.smem_leaves_bytes, &bar);
+        nodes = sn; leaves = sl;
+    } else { nodes = a.nodes; leaves = a.leaves; }
+}
+
+// ------------------------------------------------------------------ trace (closest hit)
+template <bool SMEM>
+__global__ void __launch_bounds__(WF_THREADS) k_trace(WfArgs a, int depth) {
+    const TrNode* nodes; const TrLeaf* leaves;
+    bvh_view<SMEM>(a, nodes, leaves);
+    const int n = a.ctr->nq[depth];
+    const int pp = depth & 1;
+    const float4* __restrict__ pa = a.pa[pp]; const float4* __restrict__ pb = a.pb[pp];
+    int* cursor = &a.ctr->wf_trace[depth];
+    const int lane = threadIdx.x & 31;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(cursor, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        int q = base + lane;
+        bool active = q < n;
+        int c = -1;
+        if (active) {
+            float4 A = pa[q], B = pb[q];
+            RayPre r = make_ray(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y));
+            HitRec h = trace_closest(nodes, leaves, a.nnodes, r, a.ctr->visits);
+            a.hit[q] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
+            if (h.prim < 0) c = 0;
+            else {
+                int mt = (int)__ldg(a.material + (size_t)h.mat * 10);
+                c = (mt == TR_MAT_LIGHT) ? 0 : (mt == TR_MAT_GLASS ? 2 : 1);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            int pos = warp_append(&a.ctr->ncls[depth][k], c == k);
+            if (c == k) a.cls[(size_t)k * a.cap + pos] = q;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ shading helpers
+struct Surf { V3 pos, gn, n; int mat; float area; };
+
+// attribute reconstruction of Scene.intersect_prim (Scene.py:537-600) from (prim, u, v)
+__device__ __forceinline__ Surf surface_at(const WfArgs& a, int prim, float u, float v, V3 o, V3 d, float t) {
+    const float4* q = a.shade[prim].q;
+    float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+    Surf s; s.mat = __float_as_int(q0.w); s.area = q2.w;
+    int kind = __float_as_int(q1.w);
+    if (kind == 0) {
+        float4 q3 = __ldg(q + 3), q4 = __ldg(q + 4), q5 = __ldg(q + 5);
+        V3 v1 = f4xyz(q0), v2 = f4xyz(q1), v3 = f4xyz(q2);
+        float aa = 1.0f - u - v, bb = u, cc = v;
+        V3 v13 = v3 - v1, v12 = v2 - v1;
+        s.gn = normalize3(cross3(v12, v13));
+        s.pos = (aa * v1 + bb * v2) + cc * v3;
+        s.n = normalize3((aa * f4xyz(q3) + bb * f4xyz(q4)) + cc * f4xyz(q5));
+    } else {
+        // sphere: hit_nor = hit_pos - c with the scalar quadratic coefficient c (sic, Scene.py:588,595)
+        V3 ce = f4xyz(q0); float r = q1.x;
+        V3 oc = ce - o; float c = dot3(oc, oc) - r * r;
+        s.pos = o + t * d;
+        s.n = normalize3(s.pos - mk3(c, c, c)); s.gn = s.n;
+    }
+    return s;
+}
+
+// texture/Texture.py:36-69
+__device__ __forceinline__ V3 env_texel(const WfArgs& a, float fx, float fy) {
+    int x = min(max((int)fx, 0), a.env_w - 1), y = min(max((int)fy, 0), a.env_h - 1);
+    int c = __ldg(a.env + (size_t)x * a.env_h + y);
+    return mk3((float)((c & 0x00FF0000) >> 16) / 255.0f, (float)((c & 0x0000FF00) >> 8) / 255.0f, (float)(c & 0xFF) / 255.0f);
+}
+__device__ __forceinline__ V3 env_texture2d(const WfArgs& a, float u, float v) {
+    float x = clampf(u * (float)a.env_w, 0.0f, (float)a.env_w - 1.0f), y = clampf(v * (float)a.env_h, 0.0f, (float)a.env_h - 1.0f);
+    float lx = floorf(x), ly = floorf(y);
+    float wbt = y - floorf(y), wlr = x - floorf(x);
+    return mix3(mix3(env_texel(a, lx, ly), env_texel(a, lx + 1.0f, ly), wlr),
+                mix3(env_texel(a, lx, ly + 1.0f), env_texel(a, lx + 1.0f, ly + 1.0f), wlr), wbt);
+}
+
+struct LightSample { V3 pos, normal, dir, emission; float dist, choice_pdf; int prim; };
+// Scene.sample_li (Scene.py:477-518) with get_random_light_prim_index (:423-428),
+// get_prim_random_point_normal (:381-420) and get_prim_area (:324-350, precomputed per primitive)
+__device__ __forceinline__ LightSample sample_li(const WfArgs& a, V3 p, float u_idx, float ua, float ub) {
+    LightSample L;
+    int index = (int)(u_idx * (float)a.nl); if (index >= a.nl) index = a.nl - 1;
+    int pi = __ldg(a.light + index);
+    const float4* q = a.shade[pi].q;
+    float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+    int kind = __float_as_int(q1.w);
+    V3 pos, nor;
+    if (kind == 0) {
+        float4 q3 = __ldg(q + 3), q4 = __ldg(q + 4), q5 = __ldg(q + 5);
+        V3 v1 = f4xyz(q0), v2 = f4xyz(q1), v3 = f4xyz(q2);
+        if (ua + ub > 1.0f) { ua = 1.0f - ua; ub = 1.0f - ub; }
+        pos = (v1 + (v3 - v1) * ua) + (v2 - v1) * ub;
+        nor = normalize3(((1.0f - ua - ub) * f4xyz(q3) + f4xyz(q4) * ua) + f4xyz(q5) * ub);   // roles as in Scene.py:401-402
+    } else if (kind == 1) {
+        nor = uniform_sample_sphere(ua, ub); pos = f4xyz(q0) + nor * q1.x;
+    } else { nor = mk3(q1.x, q1.y, q1.z); pos = f4xyz(q0); }
+    nor = normalize3(nor);      // Scene.py:420
+    int mid = __float_as_int(q0.w);
+    const float* m = a.material + (size_t)mid * 10;
+    L.emission = mk3(__ldg(m + 2), __ldg(m + 3), __ldg(m + 4));
+    L.choice_pdf = 1.0f / ((float)a.nl * q2.w);
+    nor = normalize3(nor);      // Scene.py:486
+    V3 dir = p - pos; float dist = length3(dir); dir = dir / dist;
+    L.pos = pos; L.normal = nor; L.dir = dir; L.dist = dist; L.prim = pi;
+    return L;
+}
+
+// ------------------------------------------------------------------ shade
+// One launch covers the three material-sorted queues back to back: [terminal | disney | glass].
+__global__ void __launch_bounds__(WF_THREADS) k_shade(WfArgs a, int depth) {
+    const BatchParams bp = *a.bp;
+    const int n0 = a.ctr->ncls[depth][0], n1 = a.ctr->ncls[depth][1], n2 = a.ctr->ncls[depth][2];
+    const int n = n0 + n1 + n2;
+    const int pp = depth & 1, np_ = pp ^ 1;
+    const int stride = gridDim.x * blockDim.x;
+    const int n_r = (n + 31) & ~31;
+    const bool last = depth + 1 >= bp.max_depth;
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_r; w += stride) {
+        bool cont = false, shadow = false;
+        float4 nA, nB, nC, sA, sB, sC;
+        if (w < n) {
+            int cl = (w < n0) ? 0 : (w < n0 + n1 ? 1 : 2);
+            int q = a.cls[(size_t)cl * a.cap + (w - (cl == 0 ? 0 : (cl == 1 ? n0 : n0 + n1)))];
+            float4 A = a.pa[pp][q], B = a.pb[pp][q], C = a.pc[pp][q], Hh = a.hit[q];
+            V3 o = mk3(A.x, A.y, A.z), d = mk3(A.w, B.x, B.y);
+            float brdf_pdf = B.z;
+            unsigned sw = __float_as_uint(B.w); unsigned slot = sw & ~SPEC_BIT; bool perfect_spec = (sw & SPEC_BIT) != 0;
+            V3 T = mk3(C.x, C.y, C.z); unsigned pix = __float_as_uint(C.w);
+            float t = Hh.x; int prim = __float_as_int(Hh.y);
+            if (prim < 0) {
+                // miss: equirect environment lookup (integrator/PT_RGB.py:127-132)
+                if (a.env_w > 0) {
+                    float dis = sqrtf(d.x * d.x + d.z * d.z);
+                    float tx = (atan2f(d.z, d.x) + TR_PI_ENV) / TR_PI_ENV / 2.0f;
+                    float ty = atan2f(d.y, dis) / TR_PI_ENV + 0.5f;
+                    V3 e = (srgb_to_lrgb(env_texture2d(a, tx, ty)) * T) * a.env_power;
+                    float4 Lv = a.L[slot]; Lv.x += e.x; Lv.y += e.y; Lv.z += e.z; a.L[slot] = Lv;
+                }
+            } else {
+                Surf s = surface_at(a, prim, Hh.z, Hh.w, o, d, t);
+                V3 fn = signf_(dot3(-d, s.gn)) * s.n;                 // UF.faceforward(normal, -direction, gnormal)
+                const float* m = a.material + (size_t)s.mat * 10;
+                V3 mcol = mk3(__ldg(m + 2), __ldg(m + 3), __ldg(m + 4));
+                float p0 = __ldg(m + 5), p1 = __ldg(m + 6);
+                if (cl == 0) {
+                    // emitter (integrator/PT_RGB.py:72-81)
+                    V3 e;
+                    if (perfect_spec) e = T * mcol;
+                    else {
+                        float fCos = fabsf(dot3(d, s.gn));
+                        float area = s.area * (float)a.nl;
+                        float light_pdf = (t * t) / (area * fCos);
+                        e = power_heuristic(brdf_pdf, light_pdf) * T * mcol;
+                    }
+                    float4 Lv = a.L[slot]; Lv.x += e.x; Lv.y += e.y; Lv.z += e.z; a.L[slot] = Lv;
+                } else {
+                    V3 rc = srgb_to_lrgb(mcol);
+                    unsigned frame = (unsigned)bp.frame_begin + slot / (unsigned)a.npix;
+                    float4 R0 = rng4(bp.seed, pix, frame, 1u + 2u * (unsigned)depth);
+                    float4 R1 = rng4(bp.seed, pix, frame, 2u + 2u * (unsigned)depth);
+                    V3 next_d; float f_or_b = 1.0f, brdf, pdf; bool spec;
+                    if (cl == 2) {
+                        spec = true;
+                        next_d = glass_sample(d, s.n, p0, R0.w, f_or_b);      // brdf/Glass.py:9-34
+                        brdf = 1.0f; pdf = 1.0f;
+                    } else {
+                        spec = false;
+                        if (a.nl > 0) {
+                            LightSample ls = sample_li(a, s.pos, R0.x, R0.y, R0.z);
+                            float NdotL_s = dot3(fn, ls.dir), NdotL_l = dot3(ls.normal, ls.dir);
+                            if (NdotL_s < 0.0f && NdotL_l > 0.0f) {
+                                float b2, p2; disney_evaluate_pdf(fn, -d, -ls.dir, p0, p1, b2, p2);
+                                V3 c = mk3(0.0f, 0.0f, 0.0f);
+                                if (p2 > 0.0f) {
+                                    float light_pdf = ls.dist * ls.dist * ls.choice_pdf / NdotL_l;
+                                    float wgt = power_heuristic(light_pdf, p2) / fmaxf(0.0001f, light_pdf);
+                                    c = ((((wgt * ls.emission) * T) * rc) * b2) * fabsf(NdotL_s);
+                                }
+                                shadow = true;
+                                sA = make_float4(ls.pos.x, ls.pos.y, ls.pos.z, ls.dir.x);
+                                sB = make_float4(ls.dir.y, ls.dir.z, __int_as_float(prim), __uint_as_float(slot));
+                                sC = make_float4(c.x, c.y, c.z, 0.0f);
+                            }
+                        }
+                        next_d = disney_sample(d, fn, p0, p1, R0.w, R1.x, R1.y);
+                        disney_evaluate_pdf(fn, -d, next_d, p0, p1, brdf, pdf);
+                        brdf *= fabsf(dot3(s.n, next_d));
+                    }
+                    V3 next_o = offset_ray(s.pos, signf_(f_or_b) * fn);
+                    if (pdf > 0.0f) {
+                        bool alive = true;
+                        if (f_or_b < 0.0f) { float Rr = expf(-t / p1); if (R1.z >= Rr) alive = false; }   // PT_RGB.py:118-122
+                        if (alive && !last) {
+                            T = T * ((brdf / pdf) * rc);
+                            cont = true;
+                            nA = make_float4(next_o.x, next_o.y, next_o.z, next_d.x);
+                            nB = make_float4(next_d.y, next_d.z, pdf, __uint_as_float(slot | (spec ? SPEC_BIT : 0u)));
+                            nC = make_float4(T.x, T.y, T.z, __uint_as_float(pix));
+                        }
+                    }
+                }
+            }
+        }
+        int qn = warp_append(&a.ctr->nq[depth + 1], cont);
+        if (cont) { a.pa[np_][qn] = nA; a.pb[np_][qn] = nB; a.pc[np_][qn] = nC; }
+        int qs = warp_append(&a.ctr->nshadow[depth], shadow);
+        if (shadow) { a.sa[qs] = sA; a.sb[qs] = sB; a.sc[qs] = sC; }
+    }
+}
+
+// ------------------------------------------------------------------ shadow
+template <bool SMEM>
+__global__ void __launch_bounds__(WF_THREADS) k_shadow(WfArgs a, int depth) {
+    const TrNode* nodes; const TrLeaf* leaves;
+    bvh_view<SMEM>(a, nodes, leaves);
+    const int n = a.ctr->nshadow[depth];
+    int* cursor = &a.ctr->wf_shadow[depth];
+    const int lane = threadIdx.x & 31;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(cursor, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        int q = base + lane;
+        if (q < n) {
+            float4 A = a.sa[q], B = a.sb[q];
+            int target = __float_as_int(B.z);
+            RayPre r = make_ray(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y));
+            bool vis = trace_shadow_visible(nodes, leaves, a.nnodes, r, target, __ldg(a.leaf_of_prim + target), a.ctr->visits + 2);
+            if (vis) {
+                float4 C = a.sc[q]; unsigned slot = __float_as_uint(B.w);
+                float4 Lv = a.L[slot]; Lv.x += C.x; Lv.y += C.y; Lv.z += C.z; a.L[slot] = Lv;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ accumulate (PT_RGB.py:134-136)
+__global__ void __launch_bounds__(WF_THREADS) k_accumulate(WfArgs a) {
+    const BatchParams bp = *a.bp;
+    const int stride = gridDim.x * blockDim.x;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < a.npix; p += stride) {
+        int x, y;
+        if (!slot_to_pixel(a, p, x, y)) continue;
+        float* o = a.hdr + ((size_t)x * a.H + y) * 3;
+        float r = o[0], g = o[1], b = o[2];
+        for (int f = 0; f < bp.n_frames; ++f) {
+            float4 Lv = a.L[(size_t)f * a.npix + p];
+            float coff = 1.0f / ((float)(bp.frame_begin + f) + 1.0f);
+            r = Lv.x * coff + r * (1.0f - coff);
+            g = Lv.y * coff + g * (1.0f - coff);
+            b = Lv.z * coff + b * (1.0f - coff);
+        }
+        o[0] = r; o[1] = g; o[2] = b;
+    }
+}
+
+// ------------------------------------------------------------------ tone map (UtilsFunc.py:583-586)
+__global__ void k_tonemap(const float* __restrict__ hdr, float* __restrict__ rgb, int n, float exposure) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rgb[i] = lrgb_to_srgb1(tone_aces1(hdr[i] * exposure));
+}
+
+// ------------------------------------------------------------------ Debug integrator + first hits
+// integrator/Debug.py:44-66; one thread per pixel, frame-0 rays (no jitter)
+__global__ void k_debug(WfArgs a, float* __restrict__ fh) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.W * a.H) return;
+    int i = p / a.H, j = p - i * a.H;
+    V3 o = mk3(a.cam.eye[0], a.cam.eye[1], a.cam.eye[2]), d = camera_dir(a.cam, i, j, 0.0f, 0.0f);
+    RayPre r = make_ray(o, d);
+    HitRec h = trace_closest(a.nodes, a.leaves, a.nnodes, r, a.ctr->visits);
+    float* f = fh + (size_t)p * 16;
+    V3 col = mk3(0, 0, 0), pos = mk3(0, 0, 0), gn = mk3(0, 0, 0), nn = mk3(0, 0, 0);
+    if (h.prim >= 0) {
+        Surf s = surface_at(a, h.prim, h.u, h.v, o, d, h.t);
+        const float* m = a.material + (size_t)s.mat * 10;
+        col = mk3(m[2], m[3], m[4]); pos = s.pos; gn = s.gn; nn = s.n;
+    }
+    f[0] = h.t; f[1] = __int_as_float(h.prim); f[2] = h.u; f[3] = h.v;
+    f[4] = pos.x; f[5] = pos.y; f[6] = pos.z; f[7] = gn.x; f[8] = gn.y; f[9] = gn.z;
+    f[10] = nn.x; f[11] = nn.y; f[12] = nn.z; f[13] = d.x; f[14] = d.y; f[15] = d.z;
+    float* hd = a.hdr + (size_t)p * 3; hd[0] = col.x; hd[1] = col.y; hd[2] = col.z;
+}
+
+// ------------------------------------------------------------------ shading table
+// per-primitive record with precomputed area (Scene.get_prim_area, Scene.py:324-350)
+__global__ void k_shade_table(const float* __restrict__ vertex, const int* __restrict__ prim, const float* __restrict__ shape,
+                              int n, TrShade* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int type = prim[i * 3], vi = prim[i * 3 + 1], mat = prim[i * 3 + 2];
+    TrShade s;
+    if (type == TR_PRIM_TRI) {
+        const float* p = vertex + (size_t)vi * 9;
+        V3 v1 = mk3(p[0], p[1], p[2]), v2 = mk3(p[9], p[10], p[11]), v3 = mk3(p[18], p[19], p[20]);
+        float la = length3(v1 - v2), lb = length3(v1 - v3), lc = length3(v3 - v2);
+        float sum = ((la + lb) + lc) * 0.5f;
+        float area = sqrtf(sum * (sum - la) * (sum - lb) * (sum - lc));
+        s.q[0] = make_float4(v1.x, v1.y, v1.z, __int_as_float(mat));
+        s.q[1] = make_float4(v2.x, v2.y, v2.z, __int_as_float(0));
+        s.q[2] = make_float4(v3.x, v3.y, v3.z, area);
+        s.q[3] = make_float4(p[3], p[4], p[5], 0.0f);
+        s.q[4] = make_float4(p[12], p[13], p[14], 0.0f);
+        s.q[5] = make_float4(p[21], p[22], p[23], 0.0f);
+    } else {
+        const float* sp = shape + (size_t)vi * 10;
+        int st = (int)sp[0];
+        float area = 0.0f;
+        if (st == TR_SHAPE_SPHERE || st == TR_SHAPE_SPOT || st == TR_SHAPE_LASER) area = sp[4] * sp[4] * TR_PI_ENV;
+        s.q[0] = make_float4(sp[1], sp[2], sp[3], __int_as_float(mat));
+        if (st == TR_SHAPE_SPHERE) s.q[1] = make_float4(sp[4], 0.0f, 0.0f, __int_as_float(1));
+        else s.q[1] = make_float4(sp[7], sp[8], sp[9], __int_as_float(2));
+        s.q[2] = make_float4(0.0f, 0.0f, 0.0f, area);
+        s.q[3] = s.q[4] = s.q[5] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    out[i] = s;
+}
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+int tr_build_shade_table(tr_ctx* ctx) {
+    if (ctx->shade_ready) return TR_OK;
+    int rc; if ((rc = tr_realloc(ctx, &ctx->d_shade, (size_t)ctx->np))) return rc;
+    k_shade_table<<<cdiv(ctx->np, 256), 256, 0, ctx->stream>>>(ctx->d_vertex, ctx->d_prim, ctx->d_shape, ctx->np, ctx->d_shade);
+    TR_CHECK_LAUNCH(ctx);
+    ctx->shade_ready = true;
+    return TR_OK;
+}
+
+static int fill_args(tr_ctx* ctx, WfArgs& a) {
+    if (!ctx->bvh_ready) return tr_fail(ctx, TR_ERR_INVALID, "render: BVH not built (call tr_bvh_build)");
+    if (!ctx->cam_set) return tr_fail(ctx, TR_ERR_INVALID, "render: camera not set");
+    if (!ctx->d_hdr) return tr_fail(ctx, TR_ERR_INVALID, "render: film not created");
+    int rc;
+    if ((rc = tr_build_shade_table(ctx))) return rc;
+    if ((rc = tr_build_tiles(ctx))) return rc;
+    memset(&a, 0, sizeof(a));
+    a.nodes = ctx->d_nodes; a.leaves = ctx->d_leaves; a.nnodes = 2 * ctx->np - 1; a.nleaves = ctx->np;
+    a.shade = ctx->d_shade; a.material = ctx->d_material; a.light = ctx->d_light; a.nl = ctx->nl; a.leaf_of_prim = ctx->d_leaf_of_prim;
+    a.env = ctx->d_env; a.env_w = ctx->d_env ? ctx->env_w : 0; a.env_h = ctx->env_h; a.env_power = ctx->env_power;
+    a.cam = ctx->cam; a.W = ctx->W; a.H = ctx->H; a.tiles = ctx->d_tiles; a.npix = ctx->n_local_tiles * TR_TILE * TR_TILE;
+    a.hdr = ctx->d_hdr;
+    for (int k = 0; k < 2; ++k) { a.pa[k] = ctx->d_path[k][0]; a.pb[k] = ctx->d_path[k][1]; a.pc[k] = ctx->d_path[k][2]; }
+    a.hit = ctx->d_hit; a.cls = ctx->d_cls; a.cap = ctx->wf_cap;
+    a.sa = ctx->d_shq[0]; a.sb = ctx->d_shq[1]; a.sc = ctx->d_shq[2]; a.L = ctx->d_L;
+    a.ctr = ctx->d_ctr; a.bp = (const BatchParams*)ctx->d_batch_params;
+    a.smem_nodes_bytes = (unsigned)((size_t)a.nnodes * sizeof(TrNode));
+    a.smem_leaves_bytes = (unsigned)((size_t)a.nleaves * sizeof(TrLeaf));
+    return TR_OK;
+}
+
+static int ensure_wavefront(tr_ctx* ctx, size_t slots) {
+    if (slots <= ctx->wf_cap) return TR_OK;
+    int rc;
+    for (int k = 0; k < 2; ++k) for (int j = 0; j < 3; ++j) if ((rc = tr_realloc(ctx, &ctx->d_path[k][j], slots))) return rc;
+    if ((rc = tr_realloc(ctx, &ctx->d_hit, slots))) return rc;
+    if ((rc = tr_realloc(ctx, &ctx->d_cls, slots * 3))) return rc;
+    for (int j = 0; j < 3; ++j) if ((rc = tr_realloc(ctx, &ctx->d_shq[j], slots))) return rc;
+    if ((rc = tr_realloc(ctx, &ctx->d_L, slots))) return rc;
+    ctx->wf_cap = slots; ctx->gen++;
+    return TR_OK;
+}
+
+struct LaunchCfg { int grid_trace, grid_shadow, grid_simple; size_t smem; bool use_smem; };
+
+static int launch_cfg(tr_ctx* ctx, const WfArgs& a, LaunchCfg& c) {
+    size_t bytes = (size_t)a.smem_nodes_bytes + a.smem_leaves_bytes;
+    c.use_smem = ctx->opt_smem_bvh && bytes <= 96 * 1024;
+    c.smem = c.use_smem ? bytes : 0;
+    int bt = 0, bs = 0;
+    if (c.use_smem) {
+        TR_CUDA(ctx, cudaFuncSetAttribute(k_trace<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+        TR_CUDA(ctx, cudaFuncSetAttribute(k_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+        TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, k_trace<true>, WF_THREADS, c.smem));
+        TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_shadow<true>, WF_THREADS, c.smem));
+    } else {
+        TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, k_trace<false>, WF_THREADS, 0));
+        TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_shadow<false>, WF_THREADS, 0));
+    }
+    if (bt < 1) bt = 1; if (bs < 1) bs = 1;
+    c.grid_trace = ctx->num_sms * bt; c.grid_shadow = ctx->num_sms * bs;
+    c.grid_simple = ctx->num_sms * 8;
+    return TR_OK;
+}
+
+// the fixed launch sequence of one batch (captured into a CUDA graph when opt_graph is on).
+// ev != nullptr (stage timing, non-graph mode): 4 events per depth bracket trace / shade / shadow.
+static int enqueue_batch(tr_ctx* ctx, const WfArgs& a, const LaunchCfg& c, int max_depth, cudaStream_t s, uint64_t* launches, cudaEvent_t* ev) {
+    TR_CUDA(ctx, cudaMemsetAsync(ctx->d_ctr, 0, sizeof(TrCounters), s));
+    k_generate<<<c.grid_simple, WF_THREADS, 0, s>>>(a); ++*launches;
+    for (int d = 0; d < max_depth; ++d) {
+        if (ev) cudaEventRecord(ev[4 * d + 0], s);
+        if (c.use_smem) k_trace<true><<<c.grid_trace, WF_THREADS, c.smem, s>>>(a, d);
+        else k_trace<false><<<c.grid_trace, WF_THREADS, 0, s>>>(a, d);
+        if (ev) cudaEventRecord(ev[4 * d + 1], s);
+        k_shade<<<c.grid_simple, WF_THREADS, 0, s>>>(a, d);
+        if (ev) cudaEventRecord(ev[4 * d + 2], s);
+        if (a.nl > 0) {
+            if (c.use_smem) k_shadow<true><<<c.grid_shadow, WF_THREADS, c.smem, s>>>(a, d);
+            else k_shadow<false><<<c.grid_shadow, WF_THREADS, 0, s>>>(a, d);
+            ++*launches;
+        }
+        if (ev) cudaEventRecord(ev[4 * d + 3], s);
+        *launches += 2;
+    }
+    k_accumulate<<<c.grid_simple, WF_THREADS, 0, s>>>(a); ++*launches;
+    TR_CHECK_LAUNCH(ctx);
+    return TR_OK;
+}
+
+extern "C" int tr_render_pt_rgb(tr_ctx* ctx, int frame_begin, int n_frames, int max_depth, uint64_t seed) {
+    if (!ctx || n_frames <= 0 || frame_begin < 0 || max_depth <= 0 || max_depth > TR_MAX_DEPTH_CAP)
+        return tr_fail(ctx, TR_ERR_INVALID, "tr_render_pt_rgb: bad arguments (frames %d+%d, depth %d)", frame_begin, n_frames, max_depth);
+    TR_CUDA(ctx, cudaSetDevice(ctx->device));
+    WfArgs a; int rc;
+    if ((rc = fill_args(ctx, a))) return rc;
+    if (a.npix == 0) { ctx->stats.frames = n_frames; return TR_OK; }    // this rank owns no tile
+    // frames per batch: enough paths in flight to fill the chip a few times, bounded by max_paths
+    int F = ctx->opt_batch_frames;
+    if (F <= 0) { F = (int)(((size_t)4 << 20) / (size_t)a.npix); if (F < 1) F = 1; }
+    while (F > 1 && (size_t)F * a.npix > ctx->opt_max_paths) --F;
+    if (F > n_frames) F = n_frames;
+    if ((rc = ensure_wavefront(ctx, (size_t)F * a.npix))) return rc;
+    if ((rc = fill_args(ctx, a))) return rc;
+    LaunchCfg cfg; if ((rc = launch_cfg(ctx, a, cfg))) return rc;
+    cudaStream_t s = ctx->stream;
+    const bool timing = ctx->opt_stage_timing != 0;
+    if (timing && ctx->stage_ev.empty()) {
+        ctx->stage_ev.resize(4 * TR_MAX_DEPTH_CAP);
+        for (auto& e : ctx->stage_ev) TR_CUDA(ctx, cudaEventCreate(&e));
+    }
+    uint64_t launches = 0, rays_c = 0, rays_s = 0, vis[4] = {0, 0, 0, 0};
+    float ms_trace = 0.0f, ms_shade = 0.0f, ms_shadow = 0.0f;
+    TR_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    for (int f0 = 0; f0 < n_frames; f0 += F) {
+        int nf = (n_frames - f0 < F) ? n_frames - f0 : F;
+        BatchParams bp; bp.frame_begin = frame_begin + f0; bp.n_frames = nf; bp.seed = seed; bp.max_depth = max_depth; bp.pad = 0;
+        TR_CUDA(ctx, cudaMemcpyAsync(ctx->d_batch_params, &bp, sizeof(bp), cudaMemcpyHostToDevice, s));
+        if (ctx->opt_graph && !timing) {
+            if (!ctx->graph_exec || ctx->graph_depth != max_depth || ctx->graph_gen != ctx->gen) {
+                if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+                cudaGraph_t g; uint64_t l2 = 0;
+                TR_CUDA(ctx, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+                rc = enqueue_batch(ctx, a, cfg, max_depth, s, &l2, nullptr);
+                cudaError_t e = cudaStreamEndCapture(s, &g);
+                if (rc) return rc;
+                if (e != cudaSuccess) return tr_fail(ctx, TR_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+                TR_CUDA(ctx, cudaGraphInstantiate(&ctx->graph_exec, g, 0));
+                cudaGraphDestroy(g);
+                ctx->graph_depth = max_depth; ctx->graph_launches = (int)l2; ctx->graph_gen = ctx->gen;
+            }
+            TR_CUDA(ctx, cudaGraphLaunch(ctx->graph_exec, s));
+            launches += (uint64_t)ctx->graph_launches;
+        } else {
+            if ((rc = enqueue_batch(ctx, a, cfg, max_depth, s, &launches, timing ? ctx->stage_ev.data() : nullptr))) return rc;
+        }
+        // ray counters of this batch = queue sizes (device counters)
+        TR_CUDA(ctx, cudaMemcpyAsync(&ctx->h_ctr, ctx->d_ctr, sizeof(TrCounters), cudaMemcpyDeviceToHost, s));
+        TR_CUDA(ctx, cudaStreamSynchronize(s));
+        for (int d = 0; d < max_depth; ++d) { rays_c += (uint64_t)ctx->h_ctr.nq[d]; rays_s += (uint64_t)ctx->h_ctr.nshadow[d]; }
+        for (int k = 0; k < 4; ++k) vis[k] += ctx->h_ctr.visits[k];
+        if (timing) for (int d = 0; d < max_depth; ++d) {
+            float t0 = 0, t1 = 0, t2 = 0; cudaEvent_t* e = ctx->stage_ev.data() + 4 * d;
+            cudaEventElapsedTime(&t0, e[0], e[1]); cudaEventElapsedTime(&t1, e[1], e[2]); cudaEventElapsedTime(&t2, e[2], e[3]);
+            ms_trace += t0; ms_shade += t1; ms_shadow += t2;
+        }
+    }
+    TR_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+    TR_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    float ms = 0.0f; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->stats.rays_closest = rays_c; ctx->stats.rays_shadow = rays_s;
+    ctx->stats.node_visits = vis[0]; ctx->stats.leaf_tests = vis[1]; ctx->stats.node_visits_shadow = vis[2]; ctx->stats.leaf_tests_shadow = vis[3];
+    ctx->stats.kernel_launches = launches; ctx->stats.ms_total = ms; ctx->stats.frames = n_frames; ctx->stats.paths_in_flight = (int)((size_t)F * a.npix);
+    ctx->stats.ms_trace = ms_trace; ctx->stats.ms_shade = ms_shade; ctx->stats.ms_shadow = ms_shadow;
+    return TR_OK;
+}
+
+extern "C" int tr_render_debug(tr_ctx* ctx) {
+    if (!ctx) return TR_ERR_INVALID;
+    TR_CUDA(ctx, cudaSetDevice(ctx->device));
+    WfArgs a; int rc;
+    if ((rc = fill_args(ctx, a))) return rc;
+    TR_CUDA(ctx, cudaMemsetAsync(ctx->d_ctr, 0, sizeof(TrCounters), ctx->stream));
+    k_debug<<<cdiv(ctx->W * ctx->H, 128), 128, 0, ctx->stream>>>(a, ctx->d_fh);
+    TR_CHECK_LAUNCH(ctx);
+    TR_CUDA(ctx, cudaMemcpyAsync(&ctx->h_ctr, ctx->d_ctr, sizeof(TrCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    TR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.rays_closest = (uint64_t)ctx->W * ctx->H; ctx->stats.rays_shadow = 0;
+    ctx->stats.node_visits = ctx->h_ctr.visits[0]; ctx->stats.leaf_tests = ctx->h_ctr.visits[1];
+    ctx->fh_ready = true;
+    return TR_OK;
+}
+
+extern "C" int tr_first_hit_download(tr_ctx* ctx, float* t, int32_t* prim, float* uv, float* pos, float* gnormal, float* normal, float* dir) {
+    if (!ctx || !ctx->fh_ready) return tr_fail(ctx, TR_ERR_INVALID, "tr_first_hit_download: call tr_render_debug first");
+    TR_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t n = (size_t)ctx->W * ctx->H;
+    float* h = (float*)malloc(n * 16 * 4);
+    if (!h) return tr_fail(ctx, TR_ERR_INVALID, "out of host memory");
+    cudaError_t e = cudaMemcpyAsync(h, ctx->d_fh, n * 64, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { free(h); return tr_fail(ctx, TR_ERR_CUDA, "first-hit download: %s", cudaGetErrorString(e)); }
+    for (size_t p = 0; p < n; ++p) {
+        const float* f = h + p * 16;
+        if (t) t[p] = f[0];
+        if (prim) memcpy(&prim[p], &f[1], 4);
+        if (uv) { uv[p * 2] = f[2]; uv[p * 2 + 1] = f[3]; }
+        if (pos) memcpy(pos + p * 3, f + 4, 12);
+        if (gnormal) memcpy(gnormal + p * 3, f + 7, 12);
+        if (normal) memcpy(normal + p * 3, f + 10, 12);
+        if (dir) memcpy(dir + p * 3, f + 13, 12);
+    }
+    free(h);
+    return TR_OK;
+}
+
+extern "C" int tr_tonemap(tr_ctx* ctx, float exposure) {
+    if (!ctx || !ctx->d_hdr) return tr_fail(ctx, TR_ERR_INVALID, "tr_tonemap: no film");
+    TR_CUDA(ctx, cudaSetDevice(ctx->device));
+    int n = ctx->W * ctx->H * 3;
+    k_tonemap<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->d_hdr, ctx->d_rgb, n, exposure);
+    TR_CHECK_LAUNCH(ctx);
+    return TR_OK;
+}
+
+// ------------------------------------------------------------------ arbitrary-ray test hook
+__global__ void k_test_trace(WfArgs a, int n, const float* __restrict__ o, const float* __restrict__ d, int shadow,
+                             float* __restrict__ t, int* __restrict__ prim, float* __restrict__ uv) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    RayPre r = make_ray(mk3(o[k * 3], o[k * 3 + 1], o[k * 3 + 2]), mk3(d[k * 3], d[k * 3 + 1], d[k * 3 + 2]));
+    HitRec h = trace_closest(a.nodes, a.leaves, a.nnodes, r, nullptr);
+    if (shadow && h.prim >= 0) {
+        // cross-check the early-exit shadow query against the closest-hit answer it must reproduce
+        bool vis = trace_shadow_visible(a.nodes, a.leaves, a.nnodes, r, h.prim, a.leaf_of_prim[h.prim], nullptr);
+        if (!vis) h.prim = -2;
+    }
+    t[k] = h.t; prim[k] = h.prim;
+    if (uv) { uv[k * 2] = h.u; uv[k * 2 + 1] = h.v; }
+}
+
+extern "C" int tr_test_trace(tr_ctx* ctx, int n, const float* o, const float* d, int shadow, float* t, int32_t* prim, float* uv) {
+    if (!ctx || n <= 0 || !o || !d || !t || !prim) return tr_fail(ctx, TR_ERR_INVALID, "tr_test_trace: bad arguments");
+    TR_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->bvh_ready) return tr_fail(ctx, TR_ERR_INVALID, "tr_test_trace: BVH not built");
+    int rc; if ((rc = tr_build_shade_table(ctx))) return rc;
+    WfArgs a; memset(&a, 0, sizeof(a));
+    a.nodes = ctx->d_nodes; a.leaves = ctx->d_leaves; a.nnodes = 2 * ctx->np - 1; a.leaf_of_prim = ctx->d_leaf_of_prim;
+    float *d_o, *d_d, *d_t, *d_uv; int* d_p;
+    TR_CUDA(ctx, cudaMalloc((void**)&d_o, (size_t)n * 12)); TR_CUDA(ctx, cudaMalloc((void**)&d_d, (size_t)n * 12));
+    TR_CUDA(ctx, cudaMalloc((void**)&d_t, (size_t)n * 4)); TR_CUDA(ctx, cudaMalloc((void**)&d_p, (size_t)n * 4));
+    TR_CUDA(ctx, cudaMalloc((void**)&d_uv, (size_t)n * 8));
+    cudaStream_t s = ctx->stream;
+    cudaMemcpyAsync(d_o, o, (size_t)n * 12, cudaMemcpyHostToDevice, s); cudaMemcpyAsync(d_d, d, (size_t)n * 12, cudaMemcpyHostToDevice, s);
+    k_test_trace<<<cdiv(n, 128), 128, 0, s>>>(a, n, d_o, d_d, shadow, d_t, d_p, d_uv);
+    cudaMemcpyAsync(t, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, s); cudaMemcpyAsync(prim, d_p, (size_t)n * 4, cudaMemcpyDeviceToHost, s);
+    if (uv) cudaMemcpyAsync(uv, d_uv, (size_t)n * 8, cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_p); cudaFree(d_uv);
+    if (e != cudaSuccess) return tr_fail(ctx, TR_ERR_CUDA, "tr_test_trace: %s", cudaGetErrorString(e));
+    TR_CHECK_LAUNCH(ctx);
+    return TR_OK;
+}
