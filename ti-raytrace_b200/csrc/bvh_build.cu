@@ -231,7 +231,7 @@ __global__ void k_flatten(const float* __restrict__ vertex, const int* __restric
                           const int* __restrict__ sorted_prim, int n, const int* __restrict__ left, const int* __restrict__ right,
                           const int* __restrict__ parent, const float* __restrict__ boxes, const int* __restrict__ leafcount,
                           int* __restrict__ pre_out, TrNode* __restrict__ nodes, TrLeaf* __restrict__ leaves,
-                          int* __restrict__ leaf_of_prim) {
+                          int* __restrict__ leaf_of_prim, float leaf_guard) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int nn = 2 * n - 1;
     if (x >= nn) return;
@@ -246,9 +246,13 @@ __global__ void k_flatten(const float* __restrict__ vertex, const int* __restric
     int lc = leafcount[x];
     bool leaf = x >= n - 1;
     int link = leaf ? -((x - (n - 1)) + 1) : pre + 2 * leafcount[left[x]];
+    // traversal copy of the box: leaf boxes are grown by a guard band (the reference never tests a leaf's
+    // own box; the band keeps the cull strictly weaker than the triangle test).  The reference-layout
+    // views (tr_bvh_download) come from `boxes`, untouched.
+    float g = leaf ? leaf_guard : 0.0f;
     TrNode nd;
-    nd.lo = make_float4(b[0], b[1], b[2], __int_as_float(pre + 2 * lc - 1));
-    nd.hi = make_float4(b[3], b[4], b[5], __int_as_float(link));
+    nd.lo = make_float4(b[0] - g, b[1] - g, b[2] - g, __int_as_float(pre + 2 * lc - 1));
+    nd.hi = make_float4(b[3] + g, b[4] + g, b[5] + g, __int_as_float(link));
     nodes[pre] = nd;
     if (leaf) {
         int k = x - (n - 1), pi = sorted_prim[k];
@@ -332,6 +336,11 @@ extern "C" int tr_bvh_build(tr_ctx* ctx) {
     TR_CUDA(ctx, cudaMemsetAsync(ctx->d_build_status, 0, 16 * 4, s));
 
     V3 mn = mk3(ctx->bmin[0], ctx->bmin[1], ctx->bmin[2]), mx = mk3(ctx->bmax[0], ctx->bmax[1], ctx->bmax[2]);
+    // guard band of the leaf-box cull: 1e-4 of the scene diagonal (Moller-Trumbore's acceptance region
+    // exceeds the exact triangle by ~1e-6 of the ray-origin distance)
+    const float ext[3] = {ctx->bmax[0] - ctx->bmin[0], ctx->bmax[1] - ctx->bmin[1], ctx->bmax[2] - ctx->bmin[2]};
+    float leaf_guard = 1e-4f * sqrtf(ext[0] * ext[0] + ext[1] * ext[1] + ext[2] * ext[2]);
+    if (!(leaf_guard > 0.0f) || !(leaf_guard < 1e30f)) leaf_guard = 1e-4f;
     k_morton<<<cdiv(n, 256), 256, 0, s>>>(ctx->d_vertex, ctx->d_prim, ctx->d_shape, n, mn, mx, ctx->d_keys[0], ctx->d_vals[0], ctx->d_morton_unsorted);
     TR_CHECK_LAUNCH(ctx);
     int cur = 0;
@@ -354,7 +363,7 @@ extern "C" int tr_bvh_build(tr_ctx* ctx) {
     TR_CHECK_LAUNCH(ctx);
     k_flatten<<<cdiv(nn, 256), 256, 0, s>>>(ctx->d_vertex, ctx->d_prim, ctx->d_shape, ctx->d_vals[cur], n, ctx->d_left, ctx->d_right,
                                            ctx->d_parent, ctx->d_boxes, ctx->d_leafcount, ctx->d_pre, ctx->d_nodes, ctx->d_leaves,
-                                           ctx->d_leaf_of_prim);
+                                           ctx->d_leaf_of_prim, leaf_guard);
     TR_CHECK_LAUNCH(ctx);
     TR_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
     int status[16];

@@ -93,7 +93,7 @@ struct tr_ctx {
     int opt_stage_timing = 0;
     int opt_graph = 1;
     int opt_smem_bvh = 1;
-    size_t opt_max_paths = (size_t)8 << 20;
+    size_t opt_max_paths = (size_t)20 << 20;   // path slots per batch (188 B each): more paths in flight amortise the per-stage tails
 
     // cuda graph cache for the batch pipeline
     cudaGraphExec_t graph_exec = nullptr; int graph_launches = 0, graph_depth = 0;

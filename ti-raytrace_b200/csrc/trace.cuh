@@ -95,85 +95,119 @@ struct HitRec { float t, u, v; int prim; int mat; };
 #define TR_COUNT_LEAF()
 #endif
 
+// Fast slab test for rays without a "parallel" axis (the common case): same arithmetic, no flags.
+__device__ __forceinline__ bool slabs_fast(const RayPre& r, float4 lo, float4 hi, float& tmin_out) {
+    float t1 = (lo.x - r.o.x) * r.ix, t2 = (hi.x - r.o.x) * r.ix;
+    float tmin = fmaxf(0.0f, fminf(t1, t2)), tmax = fminf(TR_INF, fmaxf(t1, t2));
+    t1 = (lo.y - r.o.y) * r.iy; t2 = (hi.y - r.o.y) * r.iy;
+    tmin = fmaxf(tmin, fminf(t1, t2)); tmax = fminf(tmax, fmaxf(t1, t2));
+    t1 = (lo.z - r.o.z) * r.iz; t2 = (hi.z - r.o.z) * r.iz;
+    tmin = fmaxf(tmin, fminf(t1, t2)); tmax = fminf(tmax, fmaxf(t1, t2));
+    tmin_out = tmin;
+    return !(tmin > tmax);
+}
+
+// Warp-cooperative traversal schedule ("postponed leaves").
+// Every node visit is the same instruction stream for internal nodes and leaves: one slab test on the
+// node's box (leaf nodes carry their triangle's box, grown by a guard band at build time so that a
+// Moller-Trumbore hit can never be culled by it).  A lane that reaches a leaf whose box is hit parks the
+// leaf in `pend` and waits; the Moller-Trumbore block runs for the whole warp only when at least
+// TR_LEAF_BATCH lanes have a parked leaf (or nobody can advance), so both blocks execute with most lanes
+// active instead of serialising leaf and box work on every step.  Per-lane leaf order is unchanged, so the
+// reference's tie rule (t <= best: the later sorted leaf wins) still holds.
+#ifndef TR_LEAF_BATCH
+#define TR_LEAF_BATCH 1
+#endif
+
 // Closest hit (Scene.py:702-744 semantics).  nodes/leaves may point to shared or global memory.
+// Warp-synchronous: all 32 lanes must call it together; lanes without a ray pass active = false.
 __device__ __forceinline__ HitRec trace_closest(const TrNode* __restrict__ nodes, const TrLeaf* __restrict__ leaves, int nnodes,
-                                                 const RayPre& r, unsigned long long* cnt) {
+                                                 const RayPre& r, bool active, unsigned long long* cnt) {
     HitRec h; h.t = TR_INF; h.u = 0.0f; h.v = 0.0f; h.prim = -1; h.mat = 0;
 #ifdef TR_COUNTERS
     unsigned cnt_nodes = 0, cnt_leaves = 0;
 #endif
-    int idx = 0;
-    while (idx < nnodes) {
-        float4 lo = nodes[idx].lo, hi = nodes[idx].hi;
-        int link = __float_as_int(hi.w);
-        if (link < 0) {
-            TR_COUNT_LEAF();
-            const TrLeaf* lf = leaves + (-link - 1);
-            float4 la = lf->a, lb = lf->b, lc = lf->c;
-            float u, v, t = intersect_leaf(r, la, lb, lc, u, v);
-            if (t <= h.t && t > 0.0f && t < TR_INF) { h.t = t; h.u = u; h.v = v; h.prim = __float_as_int(la.w); h.mat = __float_as_int(lc.w); }
-            idx += 1;
-        } else {
-            TR_COUNT_NODE();
+    const bool anypar = r.px || r.py || r.pz;
+    int idx = active ? 0 : nnodes, pend = -1;
+    while (true) {
+        if (pend < 0 && idx < nnodes) {
+            float4 lo = nodes[idx].lo, hi = nodes[idx].hi;
+            int link = __float_as_int(hi.w);
             float tmin;
-            bool hit = slabs(r, lo, hi, tmin) && !(tmin > h.t * TR_PRUNE_GUARD);
-            idx = hit ? idx + 1 : __float_as_int(lo.w);
+            bool hit = (anypar ? slabs(r, lo, hi, tmin) : slabs_fast(r, lo, hi, tmin)) && !(tmin > h.t * TR_PRUNE_GUARD);
+            if (link < 0) { if (hit) pend = -link - 1; } else { TR_COUNT_NODE(); }
+            idx = (hit && link >= 0) ? idx + 1 : __float_as_int(lo.w);      // leaf: escape == idx + 1
+        }
+        const unsigned parked = __ballot_sync(0xffffffffu, pend >= 0);
+        const unsigned walking = __ballot_sync(0xffffffffu, pend < 0 && idx < nnodes);
+        if (parked == 0u && walking == 0u) break;
+        if (__popc(parked) >= TR_LEAF_BATCH || walking == 0u) {
+            if (pend >= 0) {
+                TR_COUNT_LEAF();
+                const TrLeaf* lf = leaves + pend;
+                float4 la = lf->a, lb = lf->b, lc = lf->c;
+                float u, v, t = intersect_leaf(r, la, lb, lc, u, v);
+                if (t <= h.t && t > 0.0f && t < TR_INF) { h.t = t; h.u = u; h.v = v; h.prim = __float_as_int(la.w); h.mat = __float_as_int(lc.w); }
+                pend = -1;
+            }
         }
     }
 #ifdef TR_COUNTERS
-    if (cnt) { atomicAdd(cnt, (unsigned long long)cnt_nodes); atomicAdd(cnt + 1, (unsigned long long)cnt_leaves); }
+    if (cnt && active) { atomicAdd(cnt, (unsigned long long)cnt_nodes); atomicAdd(cnt + 1, (unsigned long long)cnt_leaves); }
 #endif
     return h;
 }
 
 // Shadow query.  The reference (integrator/PT_RGB.py:104-105, Scene.py:671-699) finds the nearest
 // hit of the light->surface ray and tests `shadow_prim == prim_id`.  Equivalent early-exit form:
-// intersect the target primitive first (t_t), then walk the tree looking for ANY other primitive
-// that would have won the reference's comparison (t < t_t, or t == t_t at a later leaf position).
-// Returns the reference's (hit_t, hit_prim) only as far as the caller needs it: prim == target or not.
+// intersect the target primitive first (t_t), then walk the tree (bounded by t_t) looking for ANY other
+// primitive that would have won the reference's comparison (t < t_t, or t == t_t at a later leaf
+// position); the target only counts if the walk reaches its leaf (every ancestor passes the slab test).
+// Warp-synchronous like trace_closest.
 __device__ __forceinline__ bool trace_shadow_visible(const TrNode* __restrict__ nodes, const TrLeaf* __restrict__ leaves, int nnodes,
-                                                     const RayPre& r, int target_prim, int target_leaf, unsigned long long* cnt) {
+                                                     const RayPre& r, bool active, int target_leaf, unsigned long long* cnt) {
 #ifdef TR_COUNTERS
     unsigned cnt_nodes = 0, cnt_leaves = 0;
 #endif
-    bool visible;
-    {
+    bool visible = false, found = false;
+    float tt = TR_INF;
+    if (active) {
         const TrLeaf* lf = leaves + target_leaf;
-        float u, v; float tt = intersect_leaf(r, lf->a, lf->b, lf->c, u, v);
+        float u, v; tt = intersect_leaf(r, lf->a, lf->b, lf->c, u, v);
         TR_COUNT_LEAF();
         visible = (tt > 0.0f && tt < TR_INF);
-        if (visible) {
-            // the target only counts if the walk actually reaches its leaf (every ancestor passes slabs)
-            bool found = false;
-            int idx = 0;
-            while (idx < nnodes) {
-                float4 lo = nodes[idx].lo, hi = nodes[idx].hi;
-                int link = __float_as_int(hi.w);
-                if (link < 0) {
-                    int k = -link - 1;
-                    if (k == target_leaf) found = true;
-                    else {
-                        TR_COUNT_LEAF();
-                        const TrLeaf* l2 = leaves + k;
-                        float t = intersect_leaf(r, l2->a, l2->b, l2->c, u, v);
-                        if (t > 0.0f && t < TR_INF && (t < tt || (t == tt && k > target_leaf))) { visible = false; break; }
-                    }
-                    idx += 1;
-                } else {
-                    TR_COUNT_NODE();
-                    float tmin;
-                    bool hit = slabs(r, lo, hi, tmin) && !(tmin > tt * TR_PRUNE_GUARD);
-                    idx = hit ? idx + 1 : __float_as_int(lo.w);
-                }
+    }
+    const bool anypar = r.px || r.py || r.pz;
+    int idx = visible ? 0 : nnodes, pend = -1;
+    while (true) {
+        if (pend < 0 && idx < nnodes) {
+            float4 lo = nodes[idx].lo, hi = nodes[idx].hi;
+            int link = __float_as_int(hi.w);
+            float tmin;
+            bool hit = (anypar ? slabs(r, lo, hi, tmin) : slabs_fast(r, lo, hi, tmin)) && !(tmin > tt * TR_PRUNE_GUARD);
+            if (link < 0) {
+                int k = -link - 1;
+                if (k == target_leaf) found = true; else if (hit) pend = k;
+            } else { TR_COUNT_NODE(); }
+            idx = (hit && link >= 0) ? idx + 1 : __float_as_int(lo.w);
+        }
+        const unsigned parked = __ballot_sync(0xffffffffu, pend >= 0);
+        const unsigned walking = __ballot_sync(0xffffffffu, pend < 0 && idx < nnodes);
+        if (parked == 0u && walking == 0u) break;
+        if (__popc(parked) >= TR_LEAF_BATCH || walking == 0u) {
+            if (pend >= 0) {
+                TR_COUNT_LEAF();
+                const TrLeaf* l2 = leaves + pend;
+                float u, v, t = intersect_leaf(r, l2->a, l2->b, l2->c, u, v);
+                if (t > 0.0f && t < TR_INF && (t < tt || (t == tt && pend > target_leaf))) { visible = false; idx = nnodes; }
+                pend = -1;
             }
-            visible = visible && found;
         }
     }
-    (void)target_prim;
 #ifdef TR_COUNTERS
-    if (cnt) { atomicAdd(cnt, (unsigned long long)cnt_nodes); atomicAdd(cnt + 1, (unsigned long long)cnt_leaves); }
+    if (cnt && active) { atomicAdd(cnt, (unsigned long long)cnt_nodes); atomicAdd(cnt + 1, (unsigned long long)cnt_leaves); }
 #endif
-    return visible;
+    return visible && found;
 }
 
 // ---- TMA bulk staging of the whole BVH into shared memory (small scenes, e.g. the Cornell box)

@@ -110,40 +110,149 @@ __device__ __forceinline__ void bvh_view(const WfArgs& a, const TrNode*& nodes, 
 }
 
 // ------------------------------------------------------------------ trace (closest hit)
+// Persistent warps with per-lane ray replacement: a warp takes WF_CHUNK consecutive rays of the queue with
+// one atomic, hands them to lanes as they become free, and never waits for its slowest ray.  Inside the
+// loop every lane runs the same three blocks (refill / node step / batched leaf step, see trace.cuh), so
+// the issue slots are spent with most lanes active although the per-ray walk lengths differ by 10x.
+#ifndef WF_NODE_STEPS
+#define WF_NODE_STEPS 4
+#endif
+#ifndef WF_REFILL_MIN
+#define WF_REFILL_MIN 8
+#endif
+
+struct WarpFeed { int cb, ce, chunk; bool more; };
+
+// rays a warp takes per atomic: large enough to amortise the atomic, small enough that every resident
+// warp gets work when the queue is short (deep bounces) and that the end-of-kernel tail stays short
+__device__ __forceinline__ WarpFeed make_feed(int n) {
+    WarpFeed f; f.cb = f.ce = 0; f.more = true;
+    int warps = gridDim.x * (blockDim.x >> 5);
+    int c = n / (warps * 8);
+    f.chunk = min(256, max(32, (c + 31) & ~31));
+    return f;
+}
+
+// hand the next queue entries to the idle lanes (idle = warp-uniform mask); returns this lane's new queue
+// index or -1 and removes the served lanes from `idle`
+__device__ __forceinline__ int feed_lanes(WarpFeed& f, int* cursor, int n, unsigned& idle, int lane) {
+    if (f.cb >= f.ce && f.more) {
+        int b = 0;
+        if (lane == 0) b = atomicAdd(cursor, f.chunk);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= n) { f.more = false; f.cb = f.ce = 0; } else { f.cb = b; f.ce = min(b + f.chunk, n); }
+    }
+    const int avail = f.ce - f.cb;
+    int q = -1;
+    if (avail > 0) {
+        const int rank = __popc(idle & ((1u << lane) - 1u));
+        const bool mine = ((idle >> lane) & 1u) && rank < avail;
+        if (mine) q = f.cb + rank;
+        f.cb += min(__popc(idle), avail);
+        idle &= ~__ballot_sync(0xffffffffu, mine);
+    }
+    return q;
+}
+
+// append the top `take` (<= 32) buffered (queue index | class << 30) entries to the material-sorted shade queues
+__device__ __forceinline__ void flush_retired(const WfArgs& a, int depth, const int* rbuf, int rcount, int take, int lane) {
+    unsigned e = (lane < take) ? (unsigned)rbuf[rcount - take + lane] : 0u;
+    int c = (lane < take) ? (int)(e >> 30) : -1, qq = (int)(e & 0x3fffffffu);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int pos = warp_append(&a.ctr->ncls[depth][k], c == k);
+        if (c == k) a.cls[(size_t)k * a.cap + pos] = qq;
+    }
+    __syncwarp();
+}
+
 template <bool SMEM>
 __global__ void __launch_bounds__(WF_THREADS) k_trace(WfArgs a, int depth) {
     const TrNode* nodes; const TrLeaf* leaves;
     bvh_view<SMEM>(a, nodes, leaves);
-    const int n = a.ctr->nq[depth];
+    __shared__ int retire_buf[WF_THREADS / 32][64];      // finished (queue index | class << 30), flushed 32 at a time
+    const int n = a.ctr->nq[depth], nnodes = a.nnodes;
     const int pp = depth & 1;
     const float4* __restrict__ pa = a.pa[pp]; const float4* __restrict__ pb = a.pb[pp];
     int* cursor = &a.ctr->wf_trace[depth];
     const int lane = threadIdx.x & 31;
+    int* rbuf = retire_buf[threadIdx.x >> 5];
+    int rcount = 0;
+    WarpFeed feed = make_feed(n);
+    unsigned idle = 0xffffffffu;                        // warp-uniform: lanes without a ray
+    bool anypar = false; int q = 0, idx = nnodes, pend = -1;
+    RayPre r = make_ray(mk3(0.f, 0.f, 0.f), mk3(1.f, 1.f, 1.f));
+    HitRec h; h.t = TR_INF; h.u = h.v = 0.0f; h.prim = -1; h.mat = 0;
+#ifdef TR_COUNTERS
+    unsigned long long cnt_nodes = 0, cnt_leaves = 0;
+#endif
     while (true) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(cursor, 32);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        int q = base + lane;
-        bool active = q < n;
-        int c = -1;
-        if (active) {
-            float4 A = pa[q], B = pb[q];
-            RayPre r = make_ray(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y));
-            HitRec h = trace_closest(nodes, leaves, a.nnodes, r, a.ctr->visits);
-            a.hit[q] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
-            if (h.prim < 0) c = 0;
-            else {
-                int mt = (int)__ldg(a.material + (size_t)h.mat * 10);
-                c = (mt == TR_MAT_LIGHT) ? 0 : (mt == TR_MAT_GLASS ? 2 : 1);
+        // ---- refill: only when enough lanes are free (the ray set-up runs at the utilisation of the idle set)
+        if ((__popc(idle) >= WF_REFILL_MIN || idle == 0xffffffffu) && (feed.more || feed.cb < feed.ce)) {
+            int nq = feed_lanes(feed, cursor, n, idle, lane);
+            if (nq >= 0) {
+                float4 A = pa[nq], B = pb[nq];
+                r = make_ray(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y));
+                anypar = r.px || r.py || r.pz;
+                h.t = TR_INF; h.u = h.v = 0.0f; h.prim = -1; h.mat = 0;
+                q = nq; idx = 0; pend = -1;
             }
         }
+        if (idle == 0xffffffffu) { if (!feed.more && feed.cb >= feed.ce) break; else continue; }
+        const bool has = !((idle >> lane) & 1u);
+        // ---- WF_NODE_STEPS node steps per round (same code for internal nodes and leaves); the warp-level
+        //      bookkeeping below is paid once per round
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            int pos = warp_append(&a.ctr->ncls[depth][k], c == k);
-            if (c == k) a.cls[(size_t)k * a.cap + pos] = q;
+        for (int step = 0; step < WF_NODE_STEPS; ++step) {
+            if (has && pend < 0 && idx < nnodes) {
+                float4 lo = nodes[idx].lo, hi = nodes[idx].hi;
+                int link = __float_as_int(hi.w);
+                float tmin;
+                bool hit = (anypar ? slabs(r, lo, hi, tmin) : slabs_fast(r, lo, hi, tmin)) && !(tmin > h.t * TR_PRUNE_GUARD);
+                if (link < 0) { if (hit) pend = -link - 1; }
+#ifdef TR_COUNTERS
+                else ++cnt_nodes;
+#endif
+                idx = (hit && link >= 0) ? idx + 1 : __float_as_int(lo.w);
+            }
         }
+        // ---- batched leaf step
+        const unsigned parked = __ballot_sync(0xffffffffu, has && pend >= 0);
+        const unsigned finm = __ballot_sync(0xffffffffu, has && pend < 0 && idx >= nnodes);
+        const unsigned walking = ~idle & ~parked & ~finm;
+        if (__popc(parked) >= TR_LEAF_BATCH || (walking == 0u && parked != 0u)) {
+            if (has && pend >= 0) {
+#ifdef TR_COUNTERS
+                ++cnt_leaves;
+#endif
+                const TrLeaf* lf = leaves + pend;
+                float4 la = lf->a, lb = lf->b, lc = lf->c;
+                float u, v, t = intersect_leaf(r, la, lb, lc, u, v);
+                if (t <= h.t && t > 0.0f && t < TR_INF) { h.t = t; h.u = u; h.v = v; h.prim = __float_as_int(la.w); h.mat = __float_as_int(lc.w); }
+                pend = -1;
+            }
+        }
+        // ---- retire finished rays: hit record now, material-sorted queue entries through the warp's buffer
+        if (finm != 0u) {
+            if ((finm >> lane) & 1u) {
+                a.hit[q] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
+                int c = 0;
+                if (h.prim >= 0) {
+                    int mt = (int)__ldg(a.material + (size_t)h.mat * 10);
+                    c = (mt == TR_MAT_LIGHT) ? 0 : (mt == TR_MAT_GLASS ? 2 : 1);
+                }
+                rbuf[rcount + __popc(finm & ((1u << lane) - 1u))] = q | (c << 30);
+            }
+            rcount += __popc(finm);
+            idle |= finm;
+            __syncwarp();
+        }
+        if (rcount >= 32) { flush_retired(a, depth, rbuf, rcount, 32, lane); rcount -= 32; }
     }
+    if (rcount > 0) flush_retired(a, depth, rbuf, rcount, rcount, lane);
+#ifdef TR_COUNTERS
+    atomicAdd(a.ctr->visits, cnt_nodes); atomicAdd(a.ctr->visits + 1, cnt_leaves);
+#endif
 }
 
 // ------------------------------------------------------------------ shading helpers
@@ -322,30 +431,81 @@ __global__ void __launch_bounds__(WF_THREADS) k_shade(WfArgs a, int depth) {
 }
 
 // ------------------------------------------------------------------ shadow
+// Same persistent schedule as k_trace; the walk is bounded by the target's own t and stops at the first
+// primitive that would have won the reference's nearest-hit comparison (see trace_shadow_visible).
 template <bool SMEM>
 __global__ void __launch_bounds__(WF_THREADS) k_shadow(WfArgs a, int depth) {
     const TrNode* nodes; const TrLeaf* leaves;
     bvh_view<SMEM>(a, nodes, leaves);
-    const int n = a.ctr->nshadow[depth];
+    const int n = a.ctr->nshadow[depth], nnodes = a.nnodes;
     int* cursor = &a.ctr->wf_shadow[depth];
     const int lane = threadIdx.x & 31;
+    WarpFeed feed = make_feed(n);
+    unsigned idle = 0xffffffffu;
+    bool anypar = false, visible = false, found = false; int q = 0, idx = nnodes, pend = -1, tleaf = 0;
+    float tt = TR_INF; unsigned slot = 0;
+    RayPre r = make_ray(mk3(0.f, 0.f, 0.f), mk3(1.f, 1.f, 1.f));
+#ifdef TR_COUNTERS
+    unsigned long long cnt_nodes = 0, cnt_leaves = 0;
+#endif
     while (true) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(cursor, 32);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        int q = base + lane;
-        if (q < n) {
-            float4 A = a.sa[q], B = a.sb[q];
-            int target = __float_as_int(B.z);
-            RayPre r = make_ray(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y));
-            bool vis = trace_shadow_visible(nodes, leaves, a.nnodes, r, target, __ldg(a.leaf_of_prim + target), a.ctr->visits + 2);
-            if (vis) {
-                float4 C = a.sc[q]; unsigned slot = __float_as_uint(B.w);
+        if ((__popc(idle) >= WF_REFILL_MIN || idle == 0xffffffffu) && (feed.more || feed.cb < feed.ce)) {
+            int nq = feed_lanes(feed, cursor, n, idle, lane);
+            if (nq >= 0) {
+                float4 A = a.sa[nq], B = a.sb[nq];
+                r = make_ray(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y));
+                anypar = r.px || r.py || r.pz;
+                tleaf = __ldg(a.leaf_of_prim + __float_as_int(B.z)); slot = __float_as_uint(B.w);
+                const TrLeaf* lf = leaves + tleaf;
+                float u, v; tt = intersect_leaf(r, lf->a, lf->b, lf->c, u, v);
+#ifdef TR_COUNTERS
+                ++cnt_leaves;
+#endif
+                visible = (tt > 0.0f && tt < TR_INF); found = false;
+                q = nq; idx = visible ? 0 : nnodes; pend = -1;
+            }
+        }
+        if (idle == 0xffffffffu) { if (!feed.more && feed.cb >= feed.ce) break; else continue; }
+        const bool has = !((idle >> lane) & 1u);
+#pragma unroll
+        for (int step = 0; step < WF_NODE_STEPS; ++step) {
+            if (has && pend < 0 && idx < nnodes) {
+                float4 lo = nodes[idx].lo, hi = nodes[idx].hi;
+                int link = __float_as_int(hi.w);
+                float tmin;
+                bool hit = (anypar ? slabs(r, lo, hi, tmin) : slabs_fast(r, lo, hi, tmin)) && !(tmin > tt * TR_PRUNE_GUARD);
+                if (link < 0) { int k = -link - 1; if (k == tleaf) found = true; else if (hit) pend = k; }
+#ifdef TR_COUNTERS
+                else ++cnt_nodes;
+#endif
+                idx = (hit && link >= 0) ? idx + 1 : __float_as_int(lo.w);
+            }
+        }
+        const unsigned parked = __ballot_sync(0xffffffffu, has && pend >= 0);
+        unsigned finm = __ballot_sync(0xffffffffu, has && pend < 0 && idx >= nnodes);
+        const unsigned walking = ~idle & ~parked & ~finm;
+        if (__popc(parked) >= TR_LEAF_BATCH || (walking == 0u && parked != 0u)) {
+            if (has && pend >= 0) {
+#ifdef TR_COUNTERS
+                ++cnt_leaves;
+#endif
+                const TrLeaf* l2 = leaves + pend;
+                float u, v, t = intersect_leaf(r, l2->a, l2->b, l2->c, u, v);
+                if (t > 0.0f && t < TR_INF && (t < tt || (t == tt && pend > tleaf))) { visible = false; idx = nnodes; }
+                pend = -1;
+            }
+        }
+        if ((finm >> lane) & 1u) {
+            if (visible && found) {
+                float4 C = a.sc[q];
                 float4 Lv = a.L[slot]; Lv.x += C.x; Lv.y += C.y; Lv.z += C.z; a.L[slot] = Lv;
             }
         }
+        idle |= finm;
     }
+#ifdef TR_COUNTERS
+    atomicAdd(a.ctr->visits + 2, cnt_nodes); atomicAdd(a.ctr->visits + 3, cnt_leaves);
+#endif
 }
 
 // ------------------------------------------------------------------ accumulate (PT_RGB.py:134-136)
@@ -378,11 +538,13 @@ __global__ void k_tonemap(const float* __restrict__ hdr, float* __restrict__ rgb
 // integrator/Debug.py:44-66; one thread per pixel, frame-0 rays (no jitter)
 __global__ void k_debug(WfArgs a, float* __restrict__ fh) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= a.W * a.H) return;
+    const bool active = p < a.W * a.H;
+    if (!active) p = 0;                       // whole warps stay in the (warp-synchronous) traversal
     int i = p / a.H, j = p - i * a.H;
     V3 o = mk3(a.cam.eye[0], a.cam.eye[1], a.cam.eye[2]), d = camera_dir(a.cam, i, j, 0.0f, 0.0f);
     RayPre r = make_ray(o, d);
-    HitRec h = trace_closest(a.nodes, a.leaves, a.nnodes, r, a.ctr->visits);
+    HitRec h = trace_closest(a.nodes, a.leaves, a.nnodes, r, active, a.ctr->visits);
+    if (!active) return;
     float* f = fh + (size_t)p * 16;
     V3 col = mk3(0, 0, 0), pos = mk3(0, 0, 0), gn = mk3(0, 0, 0), nn = mk3(0, 0, 0);
     if (h.prim >= 0) {
@@ -531,7 +693,7 @@ extern "C" int tr_render_pt_rgb(tr_ctx* ctx, int frame_begin, int n_frames, int 
     if (a.npix == 0) { ctx->stats.frames = n_frames; return TR_OK; }    // this rank owns no tile
     // frames per batch: enough paths in flight to fill the chip a few times, bounded by max_paths
     int F = ctx->opt_batch_frames;
-    if (F <= 0) { F = (int)(((size_t)4 << 20) / (size_t)a.npix); if (F < 1) F = 1; }
+    if (F <= 0) { F = (int)(ctx->opt_max_paths / (size_t)a.npix); if (F < 1) F = 1; }     // auto: as many frames per batch as the path budget allows
     while (F > 1 && (size_t)F * a.npix > ctx->opt_max_paths) --F;
     if (F > n_frames) F = n_frames;
     if ((rc = ensure_wavefront(ctx, (size_t)F * a.npix))) return rc;
@@ -641,14 +803,17 @@ extern "C" int tr_tonemap(tr_ctx* ctx, float exposure) {
 __global__ void k_test_trace(WfArgs a, int n, const float* __restrict__ o, const float* __restrict__ d, int shadow,
                              float* __restrict__ t, int* __restrict__ prim, float* __restrict__ uv) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    const bool active = k < n;
+    if (!active) k = 0;
     RayPre r = make_ray(mk3(o[k * 3], o[k * 3 + 1], o[k * 3 + 2]), mk3(d[k * 3], d[k * 3 + 1], d[k * 3 + 2]));
-    HitRec h = trace_closest(a.nodes, a.leaves, a.nnodes, r, nullptr);
-    if (shadow && h.prim >= 0) {
+    HitRec h = trace_closest(a.nodes, a.leaves, a.nnodes, r, active, nullptr);
+    if (shadow) {
         // cross-check the early-exit shadow query against the closest-hit answer it must reproduce
-        bool vis = trace_shadow_visible(a.nodes, a.leaves, a.nnodes, r, h.prim, a.leaf_of_prim[h.prim], nullptr);
-        if (!vis) h.prim = -2;
+        bool has = active && h.prim >= 0;
+        bool vis = trace_shadow_visible(a.nodes, a.leaves, a.nnodes, r, has, has ? a.leaf_of_prim[h.prim] : 0, nullptr);
+        if (has && !vis) h.prim = -2;
     }
+    if (!active) return;
     t[k] = h.t; prim[k] = h.prim;
     if (uv) { uv[k * 2] = h.u; uv[k * 2 + 1] = h.v; }
 }
