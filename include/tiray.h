@@ -47,6 +47,8 @@ typedef struct tr_stats {
     int32_t  paths_in_flight;  /* path slots per batch */
     uint64_t node_visits_shadow; /* shadow-query visits (only with -DTR_COUNTERS) */
     uint64_t leaf_tests_shadow;
+    int32_t  chains;           /* independent wavefront chains per batch */
+    int32_t  pad_;
 } tr_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -116,7 +118,8 @@ int tr_first_hit_download(tr_ctx* ctx, float* t, int32_t* prim, float* uv /*2*/,
 /* replaces UF.tone_map (UtilsFunc.py:583-586): rgb = srgb(ACES(hdr * exposure)) */
 int tr_tonemap(tr_ctx* ctx, float exposure);
 int tr_stats_get(tr_ctx* ctx, tr_stats* out);
-/* tuning: frames per wavefront batch (0 = auto), stage timing on/off, CUDA-graph replay on/off */
+/* tuning: "batch_frames" (0 = auto), "max_paths", "chains" (parallel wavefront chains per batch),
+ * "stage_timing", "graph" (CUDA-graph replay), "smem_bvh" (TMA staging of small BVHs) */
 int tr_set_option(tr_ctx* ctx, const char* name, int value);
 
 /* ---- unit hooks: the device functions of the shading/traversal kernels run on arrays, for parity

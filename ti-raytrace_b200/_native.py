@@ -20,7 +20,8 @@ class Stats(C.Structure):
                 ("leaf_tests", C.c_uint64), ("kernel_launches", C.c_uint64), ("ms_total", C.c_float),
                 ("ms_trace", C.c_float), ("ms_shade", C.c_float), ("ms_shadow", C.c_float), ("ms_build", C.c_float),
                 ("frames", C.c_int32), ("paths_in_flight", C.c_int32),
-                ("node_visits_shadow", C.c_uint64), ("leaf_tests_shadow", C.c_uint64)]
+                ("node_visits_shadow", C.c_uint64), ("leaf_tests_shadow", C.c_uint64),
+                ("chains", C.c_int32), ("pad_", C.c_int32)]
 
 
 # every symbol include/tiray.h declares: name -> (restype, argtypes)

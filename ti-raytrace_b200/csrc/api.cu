@@ -45,7 +45,7 @@ int tr_ctx_create(int device, tr_ctx** out) {
     ctx->own_stream = ctx->stream;
     TR_CUDA(ctx, cudaEventCreate(&ctx->ev0));
     TR_CUDA(ctx, cudaEventCreate(&ctx->ev1));
-    TR_CUDA(ctx, cudaMalloc((void**)&ctx->d_ctr, sizeof(TrCounters)));
+    TR_CUDA(ctx, cudaMalloc((void**)&ctx->d_ctr, sizeof(TrCounters) * TR_MAX_CHAINS));
     TR_CUDA(ctx, cudaMalloc((void**)&ctx->d_build_status, 16 * sizeof(int)));
     TR_CUDA(ctx, cudaMalloc((void**)&ctx->d_batch_params, 64));
     memset(&ctx->stats, 0, sizeof(ctx->stats));
@@ -65,11 +65,13 @@ void tr_ctx_destroy(tr_ctx* ctx) {
                     ctx->d_build_status, ctx->d_nodes, ctx->d_leaves, ctx->d_leaf_of_prim, ctx->d_shade, ctx->d_hist, ctx->d_hdr, ctx->d_rgb,
                     ctx->d_fh, ctx->d_tiles, ctx->d_path[0][0], ctx->d_path[0][1], ctx->d_path[0][2], ctx->d_path[1][0],
                     ctx->d_path[1][1], ctx->d_path[1][2], ctx->d_hit, ctx->d_cls, ctx->d_shq[0], ctx->d_shq[1],
-                    ctx->d_shq[2], ctx->d_L, ctx->d_ctr, ctx->d_batch_params};
+                    ctx->d_shq[2], ctx->d_L, ctx->d_ctr, ctx->d_batch_params, ctx->d_matlin};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (auto e : ctx->stage_ev) cudaEventDestroy(e);
+    for (int j = 1; j < TR_MAX_CHAINS; ++j) { if (ctx->sub_stream[j]) cudaStreamDestroy(ctx->sub_stream[j]); if (ctx->ev_join[j]) cudaEventDestroy(ctx->ev_join[j]); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -112,7 +114,7 @@ int tr_scene_upload(tr_ctx* ctx, const float* vertex, int nv, const int32_t* pri
     else TR_CUDA(ctx, cudaMemsetAsync(ctx->d_shape, 0, 10 * 4, s));
     if (nl > 0 && light) TR_CUDA(ctx, cudaMemcpyAsync(ctx->d_light, light, (size_t)nl * 4, cudaMemcpyHostToDevice, s));
     TR_CUDA(ctx, cudaStreamSynchronize(s));   // host arrays are only borrowed for the call
-    ctx->bvh_ready = false; ctx->shade_ready = false; ctx->fh_ready = false; ctx->gen++;
+    ctx->bvh_ready = false; ctx->shade_ready = false; ctx->fh_ready = false; ctx->matlin_ready = false; ctx->gen++;
     return TR_OK;
 }
 
@@ -121,6 +123,7 @@ int tr_material_upload(tr_ctx* ctx, const float* material, int nm) {
     TR_CUDA(ctx, cudaSetDevice(ctx->device));
     TR_CUDA(ctx, cudaMemcpyAsync(ctx->d_material, material, (size_t)nm * 10 * 4, cudaMemcpyHostToDevice, ctx->stream));
     TR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->matlin_ready = false;
     return TR_OK;
 }
 
@@ -203,6 +206,7 @@ int tr_set_option(tr_ctx* ctx, const char* name, int value) {
     else if (!strcmp(name, "stage_timing")) ctx->opt_stage_timing = value;
     else if (!strcmp(name, "graph")) ctx->opt_graph = value;
     else if (!strcmp(name, "smem_bvh")) ctx->opt_smem_bvh = value;
+    else if (!strcmp(name, "chains")) ctx->opt_chains = value;
     else if (!strcmp(name, "max_paths")) ctx->opt_max_paths = (size_t)value;
     else return tr_fail(ctx, TR_ERR_INVALID, "tr_set_option: unknown option '%s'", name);
     ctx->gen++;

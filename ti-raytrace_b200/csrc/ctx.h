@@ -8,6 +8,7 @@
 #include "../../include/tiray.h"
 
 #define TR_MAX_DEPTH_CAP 64       // counters are sized for this many wavefront stages
+#define TR_MAX_CHAINS 8           // independent wavefront chains per batch (parallel graph branches)
 #define TR_TILE 32                // framebuffer tile edge used for sharding and ray coherence
 
 // Traversal node, 32 B, left-first pre-order (left child = idx+1), threaded with an escape index.
@@ -85,18 +86,21 @@ struct tr_ctx {
     int*    d_cls = nullptr;        // 3 x cap indices (material-sorted shade queues)
     float4* d_shq[3] = {nullptr, nullptr, nullptr};
     float4* d_L = nullptr;          // per-sample radiance
-    TrCounters* d_ctr = nullptr;
-    TrCounters h_ctr;
+    TrCounters* d_ctr = nullptr;          // TR_MAX_CHAINS entries
+    TrCounters h_ctr[TR_MAX_CHAINS];
+    float4* d_matlin = nullptr; bool matlin_ready = false;
+    cudaStream_t sub_stream[TR_MAX_CHAINS] = {}; cudaEvent_t ev_join[TR_MAX_CHAINS] = {}; cudaEvent_t ev_fork = nullptr;
 
     // options
     int opt_batch_frames = 0;       // 0 = auto
     int opt_stage_timing = 0;
     int opt_graph = 1;
     int opt_smem_bvh = 1;
+    int opt_chains = 4;
     size_t opt_max_paths = (size_t)20 << 20;   // path slots per batch (188 B each): more paths in flight amortise the per-stage tails
 
     // cuda graph cache for the batch pipeline
-    cudaGraphExec_t graph_exec = nullptr; int graph_launches = 0, graph_depth = 0;
+    cudaGraphExec_t graph_exec = nullptr; int graph_launches = 0, graph_depth = 0, graph_chains = 0;
     unsigned long long gen = 0, graph_gen = 0;   // any state change bumps gen; a captured graph is valid for one gen
     void* d_batch_params = nullptr;
 

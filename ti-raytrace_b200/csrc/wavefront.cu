@@ -24,7 +24,7 @@ struct BatchParams { int frame_begin; int n_frames; unsigned long long seed; int
 struct WfArgs {
     // scene
     const TrNode* nodes; const TrLeaf* leaves; int nnodes; int nleaves;
-    const TrShade* shade; const float* material; const int* light; int nl; const int* leaf_of_prim;
+    const TrShade* shade; const float* material; const float4* matlin; const int* light; int nl; const int* leaf_of_prim;
     const int* env; int env_w, env_h; float env_power;
     TrCamera cam;
     // film / tiles
@@ -37,6 +37,7 @@ struct WfArgs {
     float4* L;
     TrCounters* ctr;
     const BatchParams* bp;
+    int frame_off, sub_frames;                     // this chain renders local frames [frame_off, frame_off + sub_frames) of the batch
     unsigned smem_nodes_bytes, smem_leaves_bytes;
 };
 
@@ -72,13 +73,16 @@ __device__ __forceinline__ int warp_append(int* counter, bool pred) {
 // ------------------------------------------------------------------ generate
 __global__ void __launch_bounds__(WF_THREADS) k_generate(WfArgs a) {
     const BatchParams bp = *a.bp;
-    const int total = bp.n_frames * a.npix;
+    const int nf = max(0, min(a.sub_frames, bp.n_frames - a.frame_off));
+    const int total = nf * a.npix;
     const int stride = gridDim.x * blockDim.x;
     const int total_r = (total + 31) & ~31;
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < total_r; s += stride) {
-        bool valid = false; int x = 0, y = 0, frame = 0;
-        if (s < total) {
-            int f = s / a.npix, p = s - f * a.npix;
+    for (int sl = blockIdx.x * blockDim.x + threadIdx.x; sl < total_r; sl += stride) {
+        bool valid = false; int x = 0, y = 0, frame = 0, s = 0;
+        if (sl < total) {
+            int f = sl / a.npix, p = sl - f * a.npix;
+            f += a.frame_off;
+            s = f * a.npix + p;                                   // sample slot within the whole batch
             frame = bp.frame_begin + f;
             valid = slot_to_pixel(a, p, x, y);
             a.L[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -329,7 +333,10 @@ __device__ __forceinline__ LightSample sample_li(const WfArgs& a, V3 p, float u_
 
 // ------------------------------------------------------------------ shade
 // One launch covers the three material-sorted queues back to back: [terminal | disney | glass].
-__global__ void __launch_bounds__(WF_THREADS) k_shade(WfArgs a, int depth) {
+#ifndef WF_SHADE_MIN_BLOCKS
+#define WF_SHADE_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(WF_THREADS, WF_SHADE_MIN_BLOCKS) k_shade(WfArgs a, int depth) {
     const BatchParams bp = *a.bp;
     const int n0 = a.ctr->ncls[depth][0], n1 = a.ctr->ncls[depth][1], n2 = a.ctr->ncls[depth][2];
     const int n = n0 + n1 + n2;
@@ -376,7 +383,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_shade(WfArgs a, int depth) {
                     }
                     float4 Lv = a.L[slot]; Lv.x += e.x; Lv.y += e.y; Lv.z += e.z; a.L[slot] = Lv;
                 } else {
-                    V3 rc = srgb_to_lrgb(mcol);
+                    V3 rc = f4xyz(__ldg(a.matlin + s.mat));            // srgb_to_lrgb(Kd), PT_RGB.py:86, precomputed per material
                     unsigned frame = (unsigned)bp.frame_begin + slot / (unsigned)a.npix;
                     float4 R0 = rng4(bp.seed, pix, frame, 1u + 2u * (unsigned)depth);
                     float4 R1 = rng4(bp.seed, pix, frame, 2u + 2u * (unsigned)depth);
@@ -603,6 +610,14 @@ int tr_build_shade_table(tr_ctx* ctx) {
     return TR_OK;
 }
 
+// linear albedo per material: UF.srgb_to_lrgb(material colour) (integrator/PT_RGB.py:86), same device function
+__global__ void k_matlin(const float* __restrict__ material, int nm, float4* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nm) return;
+    V3 c = srgb_to_lrgb(mk3(material[i * 10 + 2], material[i * 10 + 3], material[i * 10 + 4]));
+    out[i] = make_float4(c.x, c.y, c.z, 0.0f);
+}
+
 static int fill_args(tr_ctx* ctx, WfArgs& a) {
     if (!ctx->bvh_ready) return tr_fail(ctx, TR_ERR_INVALID, "render: BVH not built (call tr_bvh_build)");
     if (!ctx->cam_set) return tr_fail(ctx, TR_ERR_INVALID, "render: camera not set");
@@ -610,9 +625,15 @@ static int fill_args(tr_ctx* ctx, WfArgs& a) {
     int rc;
     if ((rc = tr_build_shade_table(ctx))) return rc;
     if ((rc = tr_build_tiles(ctx))) return rc;
+    if (!ctx->matlin_ready) {
+        if ((rc = tr_realloc(ctx, &ctx->d_matlin, (size_t)ctx->nm))) return rc;
+        k_matlin<<<cdiv(ctx->nm, 64), 64, 0, ctx->stream>>>(ctx->d_material, ctx->nm, ctx->d_matlin);
+        TR_CHECK_LAUNCH(ctx);
+        ctx->matlin_ready = true; ctx->gen++;
+    }
     memset(&a, 0, sizeof(a));
     a.nodes = ctx->d_nodes; a.leaves = ctx->d_leaves; a.nnodes = 2 * ctx->np - 1; a.nleaves = ctx->np;
-    a.shade = ctx->d_shade; a.material = ctx->d_material; a.light = ctx->d_light; a.nl = ctx->nl; a.leaf_of_prim = ctx->d_leaf_of_prim;
+    a.shade = ctx->d_shade; a.material = ctx->d_material; a.matlin = ctx->d_matlin; a.light = ctx->d_light; a.nl = ctx->nl; a.leaf_of_prim = ctx->d_leaf_of_prim;
     a.env = ctx->d_env; a.env_w = ctx->d_env ? ctx->env_w : 0; a.env_h = ctx->env_h; a.env_power = ctx->env_power;
     a.cam = ctx->cam; a.W = ctx->W; a.H = ctx->H; a.tiles = ctx->d_tiles; a.npix = ctx->n_local_tiles * TR_TILE * TR_TILE;
     a.hdr = ctx->d_hdr;
@@ -620,6 +641,7 @@ static int fill_args(tr_ctx* ctx, WfArgs& a) {
     a.hit = ctx->d_hit; a.cls = ctx->d_cls; a.cap = ctx->wf_cap;
     a.sa = ctx->d_shq[0]; a.sb = ctx->d_shq[1]; a.sc = ctx->d_shq[2]; a.L = ctx->d_L;
     a.ctr = ctx->d_ctr; a.bp = (const BatchParams*)ctx->d_batch_params;
+    a.frame_off = 0; a.sub_frames = 1 << 20;
     a.smem_nodes_bytes = (unsigned)((size_t)a.nnodes * sizeof(TrNode));
     a.smem_leaves_bytes = (unsigned)((size_t)a.nleaves * sizeof(TrLeaf));
     return TR_OK;
@@ -659,10 +681,21 @@ static int launch_cfg(tr_ctx* ctx, const WfArgs& a, LaunchCfg& c) {
     return TR_OK;
 }
 
-// the fixed launch sequence of one batch (captured into a CUDA graph when opt_graph is on).
-// ev != nullptr (stage timing, non-graph mode): 4 events per depth bracket trace / shade / shadow.
-static int enqueue_batch(tr_ctx* ctx, const WfArgs& a, const LaunchCfg& c, int max_depth, cudaStream_t s, uint64_t* launches, cudaEvent_t* ev) {
-    TR_CUDA(ctx, cudaMemsetAsync(ctx->d_ctr, 0, sizeof(TrCounters), s));
+// per-chain view of the queues: chain j of K renders local frames [j*fs, (j+1)*fs) with its own queue region + counters
+static WfArgs chain_args(const WfArgs& a, int j, int fs) {
+    WfArgs c = a;
+    size_t off = (size_t)j * fs * a.npix;
+    for (int k = 0; k < 2; ++k) { c.pa[k] = a.pa[k] + off; c.pb[k] = a.pb[k] + off; c.pc[k] = a.pc[k] + off; }
+    c.hit = a.hit + off; c.cls = a.cls + 3 * off; c.cap = (size_t)fs * a.npix;
+    c.sa = a.sa + off; c.sb = a.sb + off; c.sc = a.sc + off;
+    c.ctr = a.ctr + j; c.frame_off = j * fs; c.sub_frames = fs;
+    return c;
+}
+
+// one chain: generate, then max_depth x (trace, shade, shadow).
+// ev != nullptr (stage timing, single chain, non-graph mode): 4 events per depth bracket trace / shade / shadow.
+static int enqueue_chain(tr_ctx* ctx, const WfArgs& a, const LaunchCfg& c, int max_depth, cudaStream_t s, uint64_t* launches, cudaEvent_t* ev) {
+    TR_CUDA(ctx, cudaMemsetAsync(a.ctr, 0, sizeof(TrCounters), s));
     k_generate<<<c.grid_simple, WF_THREADS, 0, s>>>(a); ++*launches;
     for (int d = 0; d < max_depth; ++d) {
         if (ev) cudaEventRecord(ev[4 * d + 0], s);
@@ -678,6 +711,28 @@ static int enqueue_batch(tr_ctx* ctx, const WfArgs& a, const LaunchCfg& c, int m
         }
         if (ev) cudaEventRecord(ev[4 * d + 3], s);
         *launches += 2;
+    }
+    TR_CHECK_LAUNCH(ctx);
+    return TR_OK;
+}
+
+// The launch sequence of one batch (captured into a CUDA graph when opt_graph is on): K independent chains over
+// disjoint frame ranges run as parallel branches, so the tail of one chain's stage (a few slow rays) overlaps the
+// next stage of another chain; the frame-ordered running mean (k_accumulate) joins them.
+static int enqueue_batch(tr_ctx* ctx, const WfArgs& a, const LaunchCfg& c, int max_depth, int K, int fs, cudaStream_t s,
+                         uint64_t* launches, cudaEvent_t* ev) {
+    int rc;
+    if (K > 1) {
+        TR_CUDA(ctx, cudaEventRecord(ctx->ev_fork, s));
+        for (int j = 1; j < K; ++j) TR_CUDA(ctx, cudaStreamWaitEvent(ctx->sub_stream[j], ctx->ev_fork, 0));
+    }
+    for (int j = 0; j < K; ++j) {
+        WfArgs cj = chain_args(a, j, fs);
+        if ((rc = enqueue_chain(ctx, cj, c, max_depth, j == 0 ? s : ctx->sub_stream[j], launches, K == 1 ? ev : nullptr))) return rc;
+    }
+    for (int j = 1; j < K; ++j) {
+        TR_CUDA(ctx, cudaEventRecord(ctx->ev_join[j], ctx->sub_stream[j]));
+        TR_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join[j], 0));
     }
     k_accumulate<<<c.grid_simple, WF_THREADS, 0, s>>>(a); ++*launches;
     TR_CHECK_LAUNCH(ctx);
@@ -696,11 +751,21 @@ extern "C" int tr_render_pt_rgb(tr_ctx* ctx, int frame_begin, int n_frames, int 
     if (F <= 0) { F = (int)(ctx->opt_max_paths / (size_t)a.npix); if (F < 1) F = 1; }     // auto: as many frames per batch as the path budget allows
     while (F > 1 && (size_t)F * a.npix > ctx->opt_max_paths) --F;
     if (F > n_frames) F = n_frames;
-    if ((rc = ensure_wavefront(ctx, (size_t)F * a.npix))) return rc;
+    const bool timing = ctx->opt_stage_timing != 0;
+    int K = timing ? 1 : ctx->opt_chains;
+    if (K < 1) K = 1; if (K > TR_MAX_CHAINS) K = TR_MAX_CHAINS; if (K > F) K = F;
+    const int fs = (F + K - 1) / K;                                   // frames per chain
+    if ((rc = ensure_wavefront(ctx, (size_t)fs * K * a.npix))) return rc;
     if ((rc = fill_args(ctx, a))) return rc;
     LaunchCfg cfg; if ((rc = launch_cfg(ctx, a, cfg))) return rc;
     cudaStream_t s = ctx->stream;
-    const bool timing = ctx->opt_stage_timing != 0;
+    if (K > 1 && !ctx->sub_stream[1]) {
+        for (int j = 1; j < TR_MAX_CHAINS; ++j) {
+            TR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->sub_stream[j], cudaStreamNonBlocking));
+            TR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join[j], cudaEventDisableTiming));
+        }
+        TR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    }
     if (timing && ctx->stage_ev.empty()) {
         ctx->stage_ev.resize(4 * TR_MAX_DEPTH_CAP);
         for (auto& e : ctx->stage_ev) TR_CUDA(ctx, cudaEventCreate(&e));
@@ -713,28 +778,30 @@ extern "C" int tr_render_pt_rgb(tr_ctx* ctx, int frame_begin, int n_frames, int 
         BatchParams bp; bp.frame_begin = frame_begin + f0; bp.n_frames = nf; bp.seed = seed; bp.max_depth = max_depth; bp.pad = 0;
         TR_CUDA(ctx, cudaMemcpyAsync(ctx->d_batch_params, &bp, sizeof(bp), cudaMemcpyHostToDevice, s));
         if (ctx->opt_graph && !timing) {
-            if (!ctx->graph_exec || ctx->graph_depth != max_depth || ctx->graph_gen != ctx->gen) {
+            if (!ctx->graph_exec || ctx->graph_depth != max_depth || ctx->graph_gen != ctx->gen || ctx->graph_chains != K) {
                 if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
                 cudaGraph_t g; uint64_t l2 = 0;
                 TR_CUDA(ctx, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-                rc = enqueue_batch(ctx, a, cfg, max_depth, s, &l2, nullptr);
+                rc = enqueue_batch(ctx, a, cfg, max_depth, K, fs, s, &l2, nullptr);
                 cudaError_t e = cudaStreamEndCapture(s, &g);
                 if (rc) return rc;
                 if (e != cudaSuccess) return tr_fail(ctx, TR_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
                 TR_CUDA(ctx, cudaGraphInstantiate(&ctx->graph_exec, g, 0));
                 cudaGraphDestroy(g);
-                ctx->graph_depth = max_depth; ctx->graph_launches = (int)l2; ctx->graph_gen = ctx->gen;
+                ctx->graph_depth = max_depth; ctx->graph_launches = (int)l2; ctx->graph_gen = ctx->gen; ctx->graph_chains = K;
             }
             TR_CUDA(ctx, cudaGraphLaunch(ctx->graph_exec, s));
             launches += (uint64_t)ctx->graph_launches;
         } else {
-            if ((rc = enqueue_batch(ctx, a, cfg, max_depth, s, &launches, timing ? ctx->stage_ev.data() : nullptr))) return rc;
+            if ((rc = enqueue_batch(ctx, a, cfg, max_depth, K, fs, s, &launches, timing ? ctx->stage_ev.data() : nullptr))) return rc;
         }
         // ray counters of this batch = queue sizes (device counters)
-        TR_CUDA(ctx, cudaMemcpyAsync(&ctx->h_ctr, ctx->d_ctr, sizeof(TrCounters), cudaMemcpyDeviceToHost, s));
+        TR_CUDA(ctx, cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(TrCounters) * K, cudaMemcpyDeviceToHost, s));
         TR_CUDA(ctx, cudaStreamSynchronize(s));
-        for (int d = 0; d < max_depth; ++d) { rays_c += (uint64_t)ctx->h_ctr.nq[d]; rays_s += (uint64_t)ctx->h_ctr.nshadow[d]; }
-        for (int k = 0; k < 4; ++k) vis[k] += ctx->h_ctr.visits[k];
+        for (int j = 0; j < K; ++j) {
+            for (int d = 0; d < max_depth; ++d) { rays_c += (uint64_t)ctx->h_ctr[j].nq[d]; rays_s += (uint64_t)ctx->h_ctr[j].nshadow[d]; }
+            for (int k = 0; k < 4; ++k) vis[k] += ctx->h_ctr[j].visits[k];
+        }
         if (timing) for (int d = 0; d < max_depth; ++d) {
             float t0 = 0, t1 = 0, t2 = 0; cudaEvent_t* e = ctx->stage_ev.data() + 4 * d;
             cudaEventElapsedTime(&t0, e[0], e[1]); cudaEventElapsedTime(&t1, e[1], e[2]); cudaEventElapsedTime(&t2, e[2], e[3]);
@@ -746,7 +813,7 @@ extern "C" int tr_render_pt_rgb(tr_ctx* ctx, int frame_begin, int n_frames, int 
     float ms = 0.0f; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->stats.rays_closest = rays_c; ctx->stats.rays_shadow = rays_s;
     ctx->stats.node_visits = vis[0]; ctx->stats.leaf_tests = vis[1]; ctx->stats.node_visits_shadow = vis[2]; ctx->stats.leaf_tests_shadow = vis[3];
-    ctx->stats.kernel_launches = launches; ctx->stats.ms_total = ms; ctx->stats.frames = n_frames; ctx->stats.paths_in_flight = (int)((size_t)F * a.npix);
+    ctx->stats.kernel_launches = launches; ctx->stats.ms_total = ms; ctx->stats.frames = n_frames; ctx->stats.paths_in_flight = (int)((size_t)F * a.npix); ctx->stats.chains = K;
     ctx->stats.ms_trace = ms_trace; ctx->stats.ms_shade = ms_shade; ctx->stats.ms_shadow = ms_shadow;
     return TR_OK;
 }
@@ -759,10 +826,10 @@ extern "C" int tr_render_debug(tr_ctx* ctx) {
     TR_CUDA(ctx, cudaMemsetAsync(ctx->d_ctr, 0, sizeof(TrCounters), ctx->stream));
     k_debug<<<cdiv(ctx->W * ctx->H, 128), 128, 0, ctx->stream>>>(a, ctx->d_fh);
     TR_CHECK_LAUNCH(ctx);
-    TR_CUDA(ctx, cudaMemcpyAsync(&ctx->h_ctr, ctx->d_ctr, sizeof(TrCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    TR_CUDA(ctx, cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(TrCounters), cudaMemcpyDeviceToHost, ctx->stream));
     TR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stats.rays_closest = (uint64_t)ctx->W * ctx->H; ctx->stats.rays_shadow = 0;
-    ctx->stats.node_visits = ctx->h_ctr.visits[0]; ctx->stats.leaf_tests = ctx->h_ctr.visits[1];
+    ctx->stats.node_visits = ctx->h_ctr[0].visits[0]; ctx->stats.leaf_tests = ctx->h_ctr[0].visits[1];
     ctx->fh_ready = true;
     return TR_OK;
 }
