@@ -65,7 +65,7 @@ void tr_ctx_destroy(tr_ctx* ctx) {
                     ctx->d_build_status, ctx->d_nodes, ctx->d_leaves, ctx->d_leaf_of_prim, ctx->d_shade, ctx->d_hist, ctx->d_hdr, ctx->d_rgb,
                     ctx->d_fh, ctx->d_tiles, ctx->d_path[0][0], ctx->d_path[0][1], ctx->d_path[0][2], ctx->d_path[1][0],
                     ctx->d_path[1][1], ctx->d_path[1][2], ctx->d_hit, ctx->d_cls, ctx->d_shq[0], ctx->d_shq[1],
-                    ctx->d_shq[2], ctx->d_L, ctx->d_ctr, ctx->d_batch_params, ctx->d_matlin};
+                    ctx->d_shq[2], ctx->d_L, ctx->d_ctr, ctx->d_batch_params, ctx->d_matlin, ctx->d_axis, ctx->d_next8};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);

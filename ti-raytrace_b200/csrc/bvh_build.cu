@@ -164,7 +164,8 @@ __device__ __forceinline__ int find_split(const int* __restrict__ code, int firs
     return split;
 }
 
-__global__ void k_karras(const int* __restrict__ code, int n, int* __restrict__ left, int* __restrict__ right, int* __restrict__ parent) {
+__global__ void k_karras(const int* __restrict__ code, int n, int* __restrict__ left, int* __restrict__ right, int* __restrict__ parent,
+                         int* __restrict__ axis) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     int r0, r1; determine_range(code, n, i, r0, r1);
@@ -174,6 +175,10 @@ __global__ void k_karras(const int* __restrict__ code, int n, int* __restrict__ 
     if (max(r0, r1) == split + 1) r += n - 1;
     left[i] = l; right[i] = r;
     parent[l] = i; parent[r] = i;
+    // split axis of this node = axis of the highest Morton bit in which its range differs (bit 0 = x, 1 = y, 2 = z;
+    // the left child holds the smaller coordinate). 3 = no axis (run of identical codes). Only used to ORDER the walk.
+    int x = code[min(r0, r1)] ^ code[max(r0, r1)];
+    axis[i] = (x > 0) ? ((31 - __clz(x)) % 3) : 3;
 }
 
 // ------------------------------------------------------------------ leaf boxes + atomic bottom-up refit
@@ -231,7 +236,7 @@ __global__ void k_flatten(const float* __restrict__ vertex, const int* __restric
                           const int* __restrict__ sorted_prim, int n, const int* __restrict__ left, const int* __restrict__ right,
                           const int* __restrict__ parent, const float* __restrict__ boxes, const int* __restrict__ leafcount,
                           int* __restrict__ pre_out, TrNode* __restrict__ nodes, TrLeaf* __restrict__ leaves,
-                          int* __restrict__ leaf_of_prim, float leaf_guard) {
+                          int* __restrict__ leaf_of_prim, float leaf_guard, const int* __restrict__ axis) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int nn = 2 * n - 1;
     if (x >= nn) return;
@@ -245,7 +250,7 @@ __global__ void k_flatten(const float* __restrict__ vertex, const int* __restric
     const float* b = boxes + (size_t)x * 6;
     int lc = leafcount[x];
     bool leaf = x >= n - 1;
-    int link = leaf ? -((x - (n - 1)) + 1) : pre + 2 * leafcount[left[x]];
+    int link = leaf ? -((x - (n - 1)) + 1) : ((pre + 2 * leafcount[left[x]]) | (axis[x] << 29));
     // traversal copy of the box: leaf boxes are grown by a guard band (the reference never tests a leaf's
     // own box; the band keeps the cull strictly weaker than the triangle test).  The reference-layout
     // views (tr_bvh_download) come from `boxes`, untouched.
@@ -275,6 +280,26 @@ __global__ void k_flatten(const float* __restrict__ vertex, const int* __restric
         }
         leaves[k] = lf;
     }
+}
+
+// ------------------------------------------------------------------ ordered threading
+// next8[pre(x)*8 + o] = node to visit after the sub-tree of x when the walk enters, at every internal node, the child
+// on the near side of a ray with direction-sign octant o (bit a set <=> d[a] < 0) first.  Stackless front-to-back
+// order: 8 escape links per node instead of one.
+__global__ void k_next8(int n, const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ parent,
+                        const int* __restrict__ axis, const int* __restrict__ pre, int* __restrict__ next8) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int nn = 2 * n - 1;
+    if (t >= nn * 8) return;
+    int x = t >> 3, o = t & 7;
+    int c = x, p, res = nn;
+    while ((p = parent[c]) >= 0) {
+        int l = left[p], r = right[p];
+        int first = ((o >> axis[p]) & 1) ? r : l;          // axis 3: bit 3 of o is 0 -> left first
+        if (c == first) { res = pre[first == l ? r : l]; break; }
+        c = p;
+    }
+    next8[pre[x] * 8 + o] = res;
 }
 
 // ------------------------------------------------------------------ reference-layout views
@@ -325,6 +350,8 @@ extern "C" int tr_bvh_build(tr_ctx* ctx) {
     if ((rc = tr_realloc(ctx, &ctx->d_nodes, (size_t)nn))) return rc;
     if ((rc = tr_realloc(ctx, &ctx->d_leaves, (size_t)n))) return rc;
     if ((rc = tr_realloc(ctx, &ctx->d_leaf_of_prim, (size_t)n))) return rc;
+    if ((rc = tr_realloc(ctx, &ctx->d_axis, (size_t)nn))) return rc;
+    if ((rc = tr_realloc(ctx, &ctx->d_next8, (size_t)nn * 8))) return rc;
     const int nblocks = cdiv(n, SORT_CHUNK);
     if ((rc = tr_realloc(ctx, &ctx->d_hist, (size_t)RADIX * nblocks))) return rc;
 
@@ -354,7 +381,7 @@ extern "C" int tr_bvh_build(tr_ctx* ctx) {
             TR_CHECK_LAUNCH(ctx);
             cur ^= 1;
         }
-        k_karras<<<cdiv(n - 1, 256), 256, 0, s>>>(ctx->d_keys[cur], n, ctx->d_left, ctx->d_right, ctx->d_parent);
+        k_karras<<<cdiv(n - 1, 256), 256, 0, s>>>(ctx->d_keys[cur], n, ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_axis);
         TR_CHECK_LAUNCH(ctx);
     }
     ctx->sorted_buf = cur;
@@ -363,7 +390,9 @@ extern "C" int tr_bvh_build(tr_ctx* ctx) {
     TR_CHECK_LAUNCH(ctx);
     k_flatten<<<cdiv(nn, 256), 256, 0, s>>>(ctx->d_vertex, ctx->d_prim, ctx->d_shape, ctx->d_vals[cur], n, ctx->d_left, ctx->d_right,
                                            ctx->d_parent, ctx->d_boxes, ctx->d_leafcount, ctx->d_pre, ctx->d_nodes, ctx->d_leaves,
-                                           ctx->d_leaf_of_prim, leaf_guard);
+                                           ctx->d_leaf_of_prim, leaf_guard, ctx->d_axis);
+    TR_CHECK_LAUNCH(ctx);
+    k_next8<<<cdiv(nn * 8, 256), 256, 0, s>>>(n, ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_axis, ctx->d_pre, ctx->d_next8);
     TR_CHECK_LAUNCH(ctx);
     TR_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
     int status[16];

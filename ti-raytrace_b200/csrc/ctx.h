@@ -13,7 +13,7 @@
 
 // Traversal node, 32 B, left-first pre-order (left child = idx+1), threaded with an escape index.
 //   lo = (min.x, min.y, min.z, as_float(escape))      escape = idx + subtree size
-//   hi = (max.x, max.y, max.z, as_float(link))        link >= 0: pre-order index of the right child
+//   hi = (max.x, max.y, max.z, as_float(link))        link >= 0: pre-order index of the right child | split axis << 29
 //                                                     link <  0: leaf, sorted position k = -link-1
 struct TrNode { float4 lo, hi; };
 // Leaf record, 48 B, in sorted (Morton) order:
@@ -64,6 +64,7 @@ struct tr_ctx {
     int*   d_leafcount = nullptr; int* d_flag = nullptr; int* d_pre = nullptr;
     int*   d_build_status = nullptr;     // [0] = refit-completed internal nodes
     TrNode* d_nodes = nullptr; TrLeaf* d_leaves = nullptr; int* d_leaf_of_prim = nullptr;
+    int* d_axis = nullptr; int* d_next8 = nullptr;    // split axis per internal node; 8 octant-ordered escape links per node
     TrShade* d_shade = nullptr; bool shade_ready = false;
     int*   d_hist = nullptr; size_t hist_cap = 0;
 

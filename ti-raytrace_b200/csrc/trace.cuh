@@ -13,6 +13,7 @@
 #define TR_PRUNE_GUARD 1.0001f
 
 struct RayPre {
+    int oct;               // direction-sign octant: bit a set <=> d[a] < 0 (selects the front-to-back threading)
     V3 o, d;
     float ix, iy, iz;      // 1/d per axis (UtilsFunc.py:510), unused when the axis is "parallel"
     bool px, py, pz;       // |d| < 1e-6 (UtilsFunc.py:506)
@@ -20,6 +21,7 @@ struct RayPre {
 
 __device__ __forceinline__ RayPre make_ray(V3 o, V3 d) {
     RayPre r; r.o = o; r.d = d;
+    r.oct = (d.x < 0.0f ? 1 : 0) | (d.y < 0.0f ? 2 : 0) | (d.z < 0.0f ? 4 : 0);
     r.px = fabsf(d.x) < 0.000001f; r.py = fabsf(d.y) < 0.000001f; r.pz = fabsf(d.z) < 0.000001f;
     r.ix = 1.0f / d.x; r.iy = 1.0f / d.y; r.iz = 1.0f / d.z;
     return r;
@@ -85,7 +87,22 @@ __device__ __forceinline__ float intersect_leaf(const RayPre& r, float4 la, floa
     return t;
 }
 
-struct HitRec { float t, u, v; int prim; int mat; };
+struct HitRec { float t, u, v; int prim; int mat; int leaf; };
+
+// next node of the walk. ORDERED (trees read from global memory): near child first on a box hit, octant escape link
+// (next8) otherwise = stackless front-to-back order, which halves the node visits on the 130 k-triangle scene.
+// Unordered (small trees staged in shared memory, where every box overlaps every ray and order buys nothing):
+// left child first, single escape link stored in the node.
+template <bool ORDERED>
+__device__ __forceinline__ int next_node(int idx, int link, bool hit, int esc, int oct) {
+    int first = idx + 1;
+    if (ORDERED) first = ((oct >> (link >> 29)) & 1) ? (link & 0x1fffffff) : idx + 1;
+    return (hit && link >= 0) ? first : esc;
+}
+// the reference pops the right child first and accepts strict t < best: among equal-t hits the LARGEST sorted leaf wins
+__device__ __forceinline__ bool closer(float t, int k, float best_t, int best_k) {
+    return t > 0.0f && t < TR_INF && (t < best_t || (t == best_t && k > best_k));
+}
 
 #ifdef TR_COUNTERS
 #define TR_COUNT_NODE() (++cnt_nodes)
@@ -121,9 +138,10 @@ __device__ __forceinline__ bool slabs_fast(const RayPre& r, float4 lo, float4 hi
 
 // Closest hit (Scene.py:702-744 semantics).  nodes/leaves may point to shared or global memory.
 // Warp-synchronous: all 32 lanes must call it together; lanes without a ray pass active = false.
-__device__ __forceinline__ HitRec trace_closest(const TrNode* __restrict__ nodes, const TrLeaf* __restrict__ leaves, int nnodes,
+__device__ __forceinline__ HitRec trace_closest(const TrNode* __restrict__ nodes, const TrLeaf* __restrict__ leaves,
+                                                 const int* __restrict__ next8, int nnodes,
                                                  const RayPre& r, bool active, unsigned long long* cnt) {
-    HitRec h; h.t = TR_INF; h.u = 0.0f; h.v = 0.0f; h.prim = -1; h.mat = 0;
+    HitRec h; h.t = TR_INF; h.u = 0.0f; h.v = 0.0f; h.prim = -1; h.mat = 0; h.leaf = -1;
 #ifdef TR_COUNTERS
     unsigned cnt_nodes = 0, cnt_leaves = 0;
 #endif
@@ -132,11 +150,12 @@ __device__ __forceinline__ HitRec trace_closest(const TrNode* __restrict__ nodes
     while (true) {
         if (pend < 0 && idx < nnodes) {
             float4 lo = nodes[idx].lo, hi = nodes[idx].hi;
+            int esc = next8[idx * 8 + r.oct];
             int link = __float_as_int(hi.w);
             float tmin;
             bool hit = (anypar ? slabs(r, lo, hi, tmin) : slabs_fast(r, lo, hi, tmin)) && !(tmin > h.t * TR_PRUNE_GUARD);
             if (link < 0) { if (hit) pend = -link - 1; } else { TR_COUNT_NODE(); }
-            idx = (hit && link >= 0) ? idx + 1 : __float_as_int(lo.w);      // leaf: escape == idx + 1
+            idx = next_node<true>(idx, link, hit, esc, r.oct);
         }
         const unsigned parked = __ballot_sync(0xffffffffu, pend >= 0);
         const unsigned walking = __ballot_sync(0xffffffffu, pend < 0 && idx < nnodes);
@@ -147,7 +166,7 @@ __device__ __forceinline__ HitRec trace_closest(const TrNode* __restrict__ nodes
                 const TrLeaf* lf = leaves + pend;
                 float4 la = lf->a, lb = lf->b, lc = lf->c;
                 float u, v, t = intersect_leaf(r, la, lb, lc, u, v);
-                if (t <= h.t && t > 0.0f && t < TR_INF) { h.t = t; h.u = u; h.v = v; h.prim = __float_as_int(la.w); h.mat = __float_as_int(lc.w); }
+                if (closer(t, pend, h.t, h.leaf)) { h.t = t; h.u = u; h.v = v; h.prim = __float_as_int(la.w); h.mat = __float_as_int(lc.w); h.leaf = pend; }
                 pend = -1;
             }
         }
@@ -164,7 +183,8 @@ __device__ __forceinline__ HitRec trace_closest(const TrNode* __restrict__ nodes
 // primitive that would have won the reference's comparison (t < t_t, or t == t_t at a later leaf
 // position); the target only counts if the walk reaches its leaf (every ancestor passes the slab test).
 // Warp-synchronous like trace_closest.
-__device__ __forceinline__ bool trace_shadow_visible(const TrNode* __restrict__ nodes, const TrLeaf* __restrict__ leaves, int nnodes,
+__device__ __forceinline__ bool trace_shadow_visible(const TrNode* __restrict__ nodes, const TrLeaf* __restrict__ leaves,
+                                                     const int* __restrict__ next8, int nnodes,
                                                      const RayPre& r, bool active, int target_leaf, unsigned long long* cnt) {
 #ifdef TR_COUNTERS
     unsigned cnt_nodes = 0, cnt_leaves = 0;
@@ -182,6 +202,7 @@ __device__ __forceinline__ bool trace_shadow_visible(const TrNode* __restrict__ 
     while (true) {
         if (pend < 0 && idx < nnodes) {
             float4 lo = nodes[idx].lo, hi = nodes[idx].hi;
+            int esc = next8[idx * 8 + r.oct];
             int link = __float_as_int(hi.w);
             float tmin;
             bool hit = (anypar ? slabs(r, lo, hi, tmin) : slabs_fast(r, lo, hi, tmin)) && !(tmin > tt * TR_PRUNE_GUARD);
@@ -189,7 +210,7 @@ __device__ __forceinline__ bool trace_shadow_visible(const TrNode* __restrict__ 
                 int k = -link - 1;
                 if (k == target_leaf) found = true; else if (hit) pend = k;
             } else { TR_COUNT_NODE(); }
-            idx = (hit && link >= 0) ? idx + 1 : __float_as_int(lo.w);
+            idx = next_node<true>(idx, link, hit, esc, r.oct);
         }
         const unsigned parked = __ballot_sync(0xffffffffu, pend >= 0);
         const unsigned walking = __ballot_sync(0xffffffffu, pend < 0 && idx < nnodes);

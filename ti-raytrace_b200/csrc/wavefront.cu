@@ -23,7 +23,7 @@ struct BatchParams { int frame_begin; int n_frames; unsigned long long seed; int
 
 struct WfArgs {
     // scene
-    const TrNode* nodes; const TrLeaf* leaves; int nnodes; int nleaves;
+    const TrNode* nodes; const TrLeaf* leaves; const int* next8; int nnodes; int nleaves;
     const TrShade* shade; const float* material; const float4* matlin; const int* light; int nl; const int* leaf_of_prim;
     const int* env; int env_w, env_h; float env_power;
     TrCamera cam;
@@ -38,7 +38,7 @@ struct WfArgs {
     TrCounters* ctr;
     const BatchParams* bp;
     int frame_off, sub_frames;                     // this chain renders local frames [frame_off, frame_off + sub_frames) of the batch
-    unsigned smem_nodes_bytes, smem_leaves_bytes;
+    unsigned smem_nodes_bytes, smem_leaves_bytes, smem_next_bytes;
 };
 
 // local pixel slot p -> pixel coordinates.  32x32 tiles, inside a tile 4(x) x 8(y) pixel blocks per warp
@@ -104,13 +104,13 @@ __global__ void __launch_bounds__(WF_THREADS) k_generate(WfArgs a) {
 extern __shared__ __align__(128) unsigned char wf_smem[];
 
 template <bool SMEM>
-__device__ __forceinline__ void bvh_view(const WfArgs& a, const TrNode*& nodes, const TrLeaf*& leaves) {
+__device__ __forceinline__ void bvh_view(const WfArgs& a, const TrNode*& nodes, const TrLeaf*& leaves, const int*& next8) {
     if (SMEM) {
         __shared__ unsigned long long bar;
         TrNode* sn = (TrNode*)wf_smem; TrLeaf* sl = (TrLeaf*)(wf_smem + a.smem_nodes_bytes);
         tma_stage_to_smem(sn, a.nodes, a.smem_nodes_bytes, sl, a.leaves, a.smem_leaves_bytes, &bar);
-        nodes = sn; leaves = sl;
-    } else { nodes = a.nodes; leaves = a.leaves; }
+        nodes = sn; leaves = sl; next8 = nullptr;       // small trees: single-link (left-first) threading, see next_step
+    } else { nodes = a.nodes; leaves = a.leaves; next8 = a.next8; }
 }
 
 // ------------------------------------------------------------------ trace (closest hit)
@@ -172,8 +172,8 @@ __device__ __forceinline__ void flush_retired(const WfArgs& a, int depth, const 
 
 template <bool SMEM>
 __global__ void __launch_bounds__(WF_THREADS) k_trace(WfArgs a, int depth) {
-    const TrNode* nodes; const TrLeaf* leaves;
-    bvh_view<SMEM>(a, nodes, leaves);
+    const TrNode* nodes; const TrLeaf* leaves; const int* next8;
+    bvh_view<SMEM>(a, nodes, leaves, next8);
     __shared__ int retire_buf[WF_THREADS / 32][64];      // finished (queue index | class << 30), flushed 32 at a time
     const int n = a.ctr->nq[depth], nnodes = a.nnodes;
     const int pp = depth & 1;
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_trace(WfArgs a, int depth) {
     unsigned idle = 0xffffffffu;                        // warp-uniform: lanes without a ray
     bool anypar = false; int q = 0, idx = nnodes, pend = -1;
     RayPre r = make_ray(mk3(0.f, 0.f, 0.f), mk3(1.f, 1.f, 1.f));
-    HitRec h; h.t = TR_INF; h.u = h.v = 0.0f; h.prim = -1; h.mat = 0;
+    HitRec h; h.t = TR_INF; h.u = h.v = 0.0f; h.prim = -1; h.mat = 0; h.leaf = -1;
 #ifdef TR_COUNTERS
     unsigned long long cnt_nodes = 0, cnt_leaves = 0;
 #endif
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_trace(WfArgs a, int depth) {
                 float4 A = pa[nq], B = pb[nq];
                 r = make_ray(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y));
                 anypar = r.px || r.py || r.pz;
-                h.t = TR_INF; h.u = h.v = 0.0f; h.prim = -1; h.mat = 0;
+                h.t = TR_INF; h.u = h.v = 0.0f; h.prim = -1; h.mat = 0; h.leaf = -1;
                 q = nq; idx = 0; pend = -1;
             }
         }
@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_trace(WfArgs a, int depth) {
         for (int step = 0; step < WF_NODE_STEPS; ++step) {
             if (has && pend < 0 && idx < nnodes) {
                 float4 lo = nodes[idx].lo, hi = nodes[idx].hi;
+                int esc = SMEM ? __float_as_int(lo.w) : next8[idx * 8 + r.oct];
                 int link = __float_as_int(hi.w);
                 float tmin;
                 bool hit = (anypar ? slabs(r, lo, hi, tmin) : slabs_fast(r, lo, hi, tmin)) && !(tmin > h.t * TR_PRUNE_GUARD);
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_trace(WfArgs a, int depth) {
 #ifdef TR_COUNTERS
                 else ++cnt_nodes;
 #endif
-                idx = (hit && link >= 0) ? idx + 1 : __float_as_int(lo.w);
+                idx = next_node<!SMEM>(idx, link, hit, esc, r.oct);
             }
         }
         // ---- batched leaf step
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_trace(WfArgs a, int depth) {
                 const TrLeaf* lf = leaves + pend;
                 float4 la = lf->a, lb = lf->b, lc = lf->c;
                 float u, v, t = intersect_leaf(r, la, lb, lc, u, v);
-                if (t <= h.t && t > 0.0f && t < TR_INF) { h.t = t; h.u = u; h.v = v; h.prim = __float_as_int(la.w); h.mat = __float_as_int(lc.w); }
+                if (closer(t, pend, h.t, h.leaf)) { h.t = t; h.u = u; h.v = v; h.prim = __float_as_int(la.w); h.mat = __float_as_int(lc.w); h.leaf = pend; }
                 pend = -1;
             }
         }
@@ -442,8 +443,8 @@ __global__ void __launch_bounds__(WF_THREADS, WF_SHADE_MIN_BLOCKS) k_shade(WfArg
 // primitive that would have won the reference's nearest-hit comparison (see trace_shadow_visible).
 template <bool SMEM>
 __global__ void __launch_bounds__(WF_THREADS) k_shadow(WfArgs a, int depth) {
-    const TrNode* nodes; const TrLeaf* leaves;
-    bvh_view<SMEM>(a, nodes, leaves);
+    const TrNode* nodes; const TrLeaf* leaves; const int* next8;
+    bvh_view<SMEM>(a, nodes, leaves, next8);
     const int n = a.ctr->nshadow[depth], nnodes = a.nnodes;
     int* cursor = &a.ctr->wf_shadow[depth];
     const int lane = threadIdx.x & 31;
@@ -478,6 +479,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_shadow(WfArgs a, int depth) {
         for (int step = 0; step < WF_NODE_STEPS; ++step) {
             if (has && pend < 0 && idx < nnodes) {
                 float4 lo = nodes[idx].lo, hi = nodes[idx].hi;
+                int esc = SMEM ? __float_as_int(lo.w) : next8[idx * 8 + r.oct];
                 int link = __float_as_int(hi.w);
                 float tmin;
                 bool hit = (anypar ? slabs(r, lo, hi, tmin) : slabs_fast(r, lo, hi, tmin)) && !(tmin > tt * TR_PRUNE_GUARD);
@@ -485,7 +487,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_shadow(WfArgs a, int depth) {
 #ifdef TR_COUNTERS
                 else ++cnt_nodes;
 #endif
-                idx = (hit && link >= 0) ? idx + 1 : __float_as_int(lo.w);
+                idx = next_node<!SMEM>(idx, link, hit, esc, r.oct);
             }
         }
         const unsigned parked = __ballot_sync(0xffffffffu, has && pend >= 0);
@@ -550,7 +552,7 @@ __global__ void k_debug(WfArgs a, float* __restrict__ fh) {
     int i = p / a.H, j = p - i * a.H;
     V3 o = mk3(a.cam.eye[0], a.cam.eye[1], a.cam.eye[2]), d = camera_dir(a.cam, i, j, 0.0f, 0.0f);
     RayPre r = make_ray(o, d);
-    HitRec h = trace_closest(a.nodes, a.leaves, a.nnodes, r, active, a.ctr->visits);
+    HitRec h = trace_closest(a.nodes, a.leaves, a.next8, a.nnodes, r, active, a.ctr->visits);
     if (!active) return;
     float* f = fh + (size_t)p * 16;
     V3 col = mk3(0, 0, 0), pos = mk3(0, 0, 0), gn = mk3(0, 0, 0), nn = mk3(0, 0, 0);
@@ -632,7 +634,7 @@ static int fill_args(tr_ctx* ctx, WfArgs& a) {
         ctx->matlin_ready = true; ctx->gen++;
     }
     memset(&a, 0, sizeof(a));
-    a.nodes = ctx->d_nodes; a.leaves = ctx->d_leaves; a.nnodes = 2 * ctx->np - 1; a.nleaves = ctx->np;
+    a.nodes = ctx->d_nodes; a.leaves = ctx->d_leaves; a.next8 = ctx->d_next8; a.nnodes = 2 * ctx->np - 1; a.nleaves = ctx->np;
     a.shade = ctx->d_shade; a.material = ctx->d_material; a.matlin = ctx->d_matlin; a.light = ctx->d_light; a.nl = ctx->nl; a.leaf_of_prim = ctx->d_leaf_of_prim;
     a.env = ctx->d_env; a.env_w = ctx->d_env ? ctx->env_w : 0; a.env_h = ctx->env_h; a.env_power = ctx->env_power;
     a.cam = ctx->cam; a.W = ctx->W; a.H = ctx->H; a.tiles = ctx->d_tiles; a.npix = ctx->n_local_tiles * TR_TILE * TR_TILE;
@@ -644,6 +646,7 @@ static int fill_args(tr_ctx* ctx, WfArgs& a) {
     a.frame_off = 0; a.sub_frames = 1 << 20;
     a.smem_nodes_bytes = (unsigned)((size_t)a.nnodes * sizeof(TrNode));
     a.smem_leaves_bytes = (unsigned)((size_t)a.nleaves * sizeof(TrLeaf));
+    a.smem_next_bytes = (unsigned)((size_t)a.nnodes * 8 * sizeof(int));
     return TR_OK;
 }
 
@@ -873,11 +876,11 @@ __global__ void k_test_trace(WfArgs a, int n, const float* __restrict__ o, const
     const bool active = k < n;
     if (!active) k = 0;
     RayPre r = make_ray(mk3(o[k * 3], o[k * 3 + 1], o[k * 3 + 2]), mk3(d[k * 3], d[k * 3 + 1], d[k * 3 + 2]));
-    HitRec h = trace_closest(a.nodes, a.leaves, a.nnodes, r, active, nullptr);
+    HitRec h = trace_closest(a.nodes, a.leaves, a.next8, a.nnodes, r, active, nullptr);
     if (shadow) {
         // cross-check the early-exit shadow query against the closest-hit answer it must reproduce
         bool has = active && h.prim >= 0;
-        bool vis = trace_shadow_visible(a.nodes, a.leaves, a.nnodes, r, has, has ? a.leaf_of_prim[h.prim] : 0, nullptr);
+        bool vis = trace_shadow_visible(a.nodes, a.leaves, a.next8, a.nnodes, r, has, has ? a.leaf_of_prim[h.prim] : 0, nullptr);
         if (has && !vis) h.prim = -2;
     }
     if (!active) return;
@@ -891,7 +894,7 @@ extern "C" int tr_test_trace(tr_ctx* ctx, int n, const float* o, const float* d,
     if (!ctx->bvh_ready) return tr_fail(ctx, TR_ERR_INVALID, "tr_test_trace: BVH not built");
     int rc; if ((rc = tr_build_shade_table(ctx))) return rc;
     WfArgs a; memset(&a, 0, sizeof(a));
-    a.nodes = ctx->d_nodes; a.leaves = ctx->d_leaves; a.nnodes = 2 * ctx->np - 1; a.leaf_of_prim = ctx->d_leaf_of_prim;
+    a.nodes = ctx->d_nodes; a.leaves = ctx->d_leaves; a.next8 = ctx->d_next8; a.nnodes = 2 * ctx->np - 1; a.leaf_of_prim = ctx->d_leaf_of_prim;
     float *d_o, *d_d, *d_t, *d_uv; int* d_p;
     TR_CUDA(ctx, cudaMalloc((void**)&d_o, (size_t)n * 12)); TR_CUDA(ctx, cudaMalloc((void**)&d_d, (size_t)n * 12));
     TR_CUDA(ctx, cudaMalloc((void**)&d_t, (size_t)n * 4)); TR_CUDA(ctx, cudaMalloc((void**)&d_p, (size_t)n * 4));
