@@ -2,10 +2,11 @@
 //
 // Replaces Scene.closet_hit / closet_hit_shadow (Scene.py:671-744), which walk the same pre-order
 // node array with an explicit per-pixel stack in global memory, unordered and unpruned.  Here the
-// walk follows escape links (no stack), prunes sub-trees whose slab entry lies beyond the best hit
-// (with a relative guard band so exact/near ties are still tested) and keeps the reference's result:
-// the reference pops the right child first and accepts strict t < best, so among equal-t hits the
-// leaf with the LARGEST sorted position wins; a left-first walk reproduces that with t <= best.
+// walk follows escape links (no stack; one link per node for small trees in shared memory, eight
+// direction-octant links per node for a front-to-back walk of large trees), prunes sub-trees whose slab
+// entry lies beyond the best hit (with a relative guard band so exact/near ties are still tested) and keeps
+// the reference's result: the reference pops the right child first and accepts strict t < best, so among
+// equal-t hits the leaf with the LARGEST sorted position wins; closer() applies exactly that rule.
 #pragma once
 #include "ctx.h"
 #include "common.cuh"
@@ -124,14 +125,14 @@ __device__ __forceinline__ bool slabs_fast(const RayPre& r, float4 lo, float4 hi
     return !(tmin > tmax);
 }
 
-// Warp-cooperative traversal schedule ("postponed leaves").
+// Warp-cooperative traversal schedule.
 // Every node visit is the same instruction stream for internal nodes and leaves: one slab test on the
 // node's box (leaf nodes carry their triangle's box, grown by a guard band at build time so that a
-// Moller-Trumbore hit can never be culled by it).  A lane that reaches a leaf whose box is hit parks the
-// leaf in `pend` and waits; the Moller-Trumbore block runs for the whole warp only when at least
-// TR_LEAF_BATCH lanes have a parked leaf (or nobody can advance), so both blocks execute with most lanes
-// active instead of serialising leaf and box work on every step.  Per-lane leaf order is unchanged, so the
-// reference's tie rule (t <= best: the later sorted leaf wins) still holds.
+// Moller-Trumbore hit can never be culled by it; the reference tests every leaf under a hit parent).  A lane
+// that reaches a leaf whose box is hit parks the leaf in `pend`; the Moller-Trumbore block then runs for the
+// parked lanes once per round of node steps.  TR_LEAF_BATCH > 1 would delay it until that many lanes are
+// parked; measured on B200 (sweep 1..24, one and two parked slots per lane): 1 is fastest on both scenes.
+// Hits are compared with closer(): the reference's tie rule made explicit, so the visiting order is free.
 #ifndef TR_LEAF_BATCH
 #define TR_LEAF_BATCH 1
 #endif
