@@ -212,11 +212,14 @@ def run_native(args, wl):
             dist.barrier()
         t0 = time.perf_counter()
         scene.setup_data_gpu()                   # tables H2D (pageable numpy) + env + LBVH build
+        ta = time.perf_counter()
         if wl["normals"]:
             scene.process_normal()
         cam.dirty = True
         ctx.film_clear(); cam.frame = 0; cam.frame_cpu[0] = 0
+        tb = time.perf_counter()
         st2 = integ.render_frames(spp)
+        tc = time.perf_counter()
         if world > 1:
             with torch.cuda.stream(stream):
                 parallel.reduce_film(parallel.film_tensor(ctx), dst=0)
@@ -224,6 +227,9 @@ def run_native(args, wl):
         hdr_host, rgb_host = ctx.film_download(True, True)
         torch.cuda.synchronize(local)
         dt = time.perf_counter() - t0
+        if args.verbose and rank == 0:
+            print("e2e pass %d: upload+build %.2f ms, normals %.2f, render %.2f (device %.2f), reduce+tonemap+download %.2f" %
+                  (k, (ta - t0) * 1e3, (tb - ta) * 1e3, (tc - tb) * 1e3, st2["ms_total"], (time.perf_counter() - tc) * 1e3), file=sys.stderr)
         if k > 0:                                # first pass is warm-up (graph re-capture after the rebuild)
             e2e_t += dt; e2e_rays += int(st2["rays_closest"]) + int(st2["rays_shadow"])
     if world > 1:
@@ -294,6 +300,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="cornell", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

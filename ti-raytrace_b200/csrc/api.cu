@@ -64,12 +64,14 @@ void tr_ctx_destroy(tr_ctx* ctx) {
                     ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_boxes, ctx->d_leafcount, ctx->d_flag, ctx->d_pre,
                     ctx->d_build_status, ctx->d_nodes, ctx->d_leaves, ctx->d_leaf_of_prim, ctx->d_shade, ctx->d_hist, ctx->d_hdr, ctx->d_rgb,
                     ctx->d_fh, ctx->d_tiles, ctx->d_path[0][0], ctx->d_path[0][1], ctx->d_path[0][2], ctx->d_path[1][0],
-                    ctx->d_path[1][1], ctx->d_path[1][2], ctx->d_hit, ctx->d_cls, ctx->d_shq[0], ctx->d_shq[1],
-                    ctx->d_shq[2], ctx->d_L, ctx->d_ctr, ctx->d_batch_params, ctx->d_matlin, ctx->d_axis, ctx->d_next8};
+                    ctx->d_path[1][1], ctx->d_path[1][2], ctx->d_hit, ctx->d_cls, ctx->d_shq[0][0], ctx->d_shq[0][1],
+                    ctx->d_shq[0][2], ctx->d_shq[1][0], ctx->d_shq[1][1], ctx->d_shq[1][2], ctx->d_Lnee, ctx->d_L, ctx->d_ctr, ctx->d_batch_params, ctx->d_matlin, ctx->d_axis, ctx->d_nodesx, ctx->d_smooth};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (auto e : ctx->stage_ev) cudaEventDestroy(e);
+    for (auto e : ctx->dep_ev) cudaEventDestroy(e);
+    for (int j = 0; j < TR_MAX_CHAINS; ++j) if (ctx->shadow_stream[j]) cudaStreamDestroy(ctx->shadow_stream[j]);
     for (int j = 1; j < TR_MAX_CHAINS; ++j) { if (ctx->sub_stream[j]) cudaStreamDestroy(ctx->sub_stream[j]); if (ctx->ev_join[j]) cudaEventDestroy(ctx->ev_join[j]); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -207,9 +209,12 @@ int tr_set_option(tr_ctx* ctx, const char* name, int value) {
     else if (!strcmp(name, "graph")) ctx->opt_graph = value;
     else if (!strcmp(name, "smem_bvh")) ctx->opt_smem_bvh = value;
     else if (!strcmp(name, "chains")) ctx->opt_chains = value;
+    else if (!strcmp(name, "shadow_overlap")) ctx->opt_shadow_overlap = value;
+    else if (!strcmp(name, "tail_max")) ctx->opt_tail_max = value;
     else if (!strcmp(name, "max_paths")) ctx->opt_max_paths = (size_t)value;
     else return tr_fail(ctx, TR_ERR_INVALID, "tr_set_option: unknown option '%s'", name);
     ctx->gen++;
+    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }   // options are baked into the captured graph
     return TR_OK;
 }
 

@@ -283,11 +283,12 @@ __global__ void k_flatten(const float* __restrict__ vertex, const int* __restric
 }
 
 // ------------------------------------------------------------------ ordered threading
-// next8[pre(x)*8 + o] = node to visit after the sub-tree of x when the walk enters, at every internal node, the child
+// nodesx[pre(x)].next[o] = node to visit after the sub-tree of x when the walk enters, at every internal node, the child
 // on the near side of a ray with direction-sign octant o (bit a set <=> d[a] < 0) first.  Stackless front-to-back
 // order: 8 escape links per node instead of one.
 __global__ void k_next8(int n, const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ parent,
-                        const int* __restrict__ axis, const int* __restrict__ pre, int* __restrict__ next8) {
+                        const int* __restrict__ axis, const int* __restrict__ pre, const TrNode* __restrict__ nodes,
+                        TrNodeX* __restrict__ nodesx) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int nn = 2 * n - 1;
     if (t >= nn * 8) return;
@@ -299,7 +300,9 @@ __global__ void k_next8(int n, const int* __restrict__ left, const int* __restri
         if (c == first) { res = pre[first == l ? r : l]; break; }
         c = p;
     }
-    next8[pre[x] * 8 + o] = res;
+    const int px = pre[x];
+    nodesx[px].next[o] = res;
+    if (o == 0) { nodesx[px].lo = nodes[px].lo; nodesx[px].hi = nodes[px].hi; }
 }
 
 // ------------------------------------------------------------------ reference-layout views
@@ -351,7 +354,7 @@ extern "C" int tr_bvh_build(tr_ctx* ctx) {
     if ((rc = tr_realloc(ctx, &ctx->d_leaves, (size_t)n))) return rc;
     if ((rc = tr_realloc(ctx, &ctx->d_leaf_of_prim, (size_t)n))) return rc;
     if ((rc = tr_realloc(ctx, &ctx->d_axis, (size_t)nn))) return rc;
-    if ((rc = tr_realloc(ctx, &ctx->d_next8, (size_t)nn * 8))) return rc;
+    if ((rc = tr_realloc(ctx, &ctx->d_nodesx, (size_t)nn))) return rc;
     const int nblocks = cdiv(n, SORT_CHUNK);
     if ((rc = tr_realloc(ctx, &ctx->d_hist, (size_t)RADIX * nblocks))) return rc;
 
@@ -392,7 +395,7 @@ extern "C" int tr_bvh_build(tr_ctx* ctx) {
                                            ctx->d_parent, ctx->d_boxes, ctx->d_leafcount, ctx->d_pre, ctx->d_nodes, ctx->d_leaves,
                                            ctx->d_leaf_of_prim, leaf_guard, ctx->d_axis);
     TR_CHECK_LAUNCH(ctx);
-    k_next8<<<cdiv(nn * 8, 256), 256, 0, s>>>(n, ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_axis, ctx->d_pre, ctx->d_next8);
+    k_next8<<<cdiv(nn * 8, 256), 256, 0, s>>>(n, ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_axis, ctx->d_pre, ctx->d_nodes, ctx->d_nodesx);
     TR_CHECK_LAUNCH(ctx);
     TR_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
     int status[16];

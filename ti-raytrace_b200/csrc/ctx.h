@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string>
 #include <vector>
+#include <unordered_map>
 #include "../../include/tiray.h"
 
 #define TR_MAX_DEPTH_CAP 64       // counters are sized for this many wavefront stages
@@ -16,6 +17,9 @@
 //   hi = (max.x, max.y, max.z, as_float(link))        link >= 0: pre-order index of the right child | split axis << 29
 //                                                     link <  0: leaf, sorted position k = -link-1
 struct TrNode { float4 lo, hi; };
+// Node of the ordered (front-to-back) walk used for trees that live in global memory: the same box words plus the 8
+// direction-octant escape links, 64 B = one half cache line per visit.
+struct TrNodeX { float4 lo, hi; int next[8]; };
 // Leaf record, 48 B, in sorted (Morton) order:
 //   a = (v0.xyz, as_float(prim id)), b = (E1.xyz, as_float(kind)), c = (E2.xyz, as_float(material id))   kind 0: triangle
 //   a = (centre.xyz, prim id),       b = (radius, 0, 0, kind)                         kind 1: sphere
@@ -35,6 +39,10 @@ struct TrCounters {
     int ncls[TR_MAX_DEPTH_CAP + 1][4];   // material-sorted shade queue sizes: terminal, disney, glass
     int wf_trace[TR_MAX_DEPTH_CAP + 1];  // work-fetch cursors of the persistent trace kernels
     int wf_shadow[TR_MAX_DEPTH_CAP + 1];
+    int shade_done[TR_MAX_DEPTH_CAP + 1]; // blocks of k_shade(d) that finished (last one decides the hand-over)
+    int tail_from;                        // depth (>= 1) from which k_tail owns the chain's paths; 0: wavefront all the way
+    int pad_;
+    unsigned long long tail_rays[2];      // closest / shadow traversals executed by k_tail
     unsigned long long visits[4];        // closest: nodes, leaves; shadow: nodes, leaves (only with -DTR_COUNTERS)
 };
 
@@ -64,7 +72,7 @@ struct tr_ctx {
     int*   d_leafcount = nullptr; int* d_flag = nullptr; int* d_pre = nullptr;
     int*   d_build_status = nullptr;     // [0] = refit-completed internal nodes
     TrNode* d_nodes = nullptr; TrLeaf* d_leaves = nullptr; int* d_leaf_of_prim = nullptr;
-    int* d_axis = nullptr; int* d_next8 = nullptr;    // split axis per internal node; 8 octant-ordered escape links per node
+    int* d_axis = nullptr; TrNodeX* d_nodesx = nullptr;    // split axis per internal node; 64-byte nodes with 8 octant-ordered escape links
     TrShade* d_shade = nullptr; bool shade_ready = false;
     int*   d_hist = nullptr; size_t hist_cap = 0;
 
@@ -85,8 +93,8 @@ struct tr_ctx {
     float4* d_path[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     float4* d_hit = nullptr;
     int*    d_cls = nullptr;        // 3 x cap indices (material-sorted shade queues)
-    float4* d_shq[3] = {nullptr, nullptr, nullptr};
-    float4* d_L = nullptr;          // per-sample radiance
+    float4* d_shq[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    float4* d_L = nullptr; float4* d_Lnee = nullptr;          // per-sample radiance: terminal term, NEE sum
     TrCounters* d_ctr = nullptr;          // TR_MAX_CHAINS entries
     TrCounters h_ctr[TR_MAX_CHAINS];
     float4* d_matlin = nullptr; bool matlin_ready = false;
@@ -98,16 +106,23 @@ struct tr_ctx {
     int opt_graph = 1;
     int opt_smem_bvh = 1;
     int opt_chains = 4;
+    int opt_shadow_overlap = 1;
+    int opt_tail_max = 16384;
     size_t opt_max_paths = (size_t)20 << 20;   // path slots per batch (188 B each): more paths in flight amortise the per-stage tails
 
     // cuda graph cache for the batch pipeline
-    cudaGraphExec_t graph_exec = nullptr; int graph_launches = 0, graph_depth = 0, graph_chains = 0;
+    cudaGraphExec_t graph_exec = nullptr; int graph_launches = 0, graph_depth = 0, graph_chains = 0, graph_fs = 0;
+    std::vector<char> graph_args;
     unsigned long long gen = 0, graph_gen = 0;   // any state change bumps gen; a captured graph is valid for one gen
     void* d_batch_params = nullptr;
 
     tr_stats stats;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> stage_ev;
+    std::vector<cudaEvent_t> dep_ev;               // [chain][depth][shade done, shadow done]
+    cudaStream_t shadow_stream[TR_MAX_CHAINS] = {};
+    std::unordered_map<void*, size_t> capacity;   // bytes behind every buffer handed out by tr_realloc (re-used when large enough)
+    float* d_smooth = nullptr;                    // process_normal scratch
     cudaStream_t own_stream = nullptr;   // ctx->stream may be redirected to a caller's stream (tr_stream_set)
 };
 
@@ -116,10 +131,19 @@ int tr_fail(tr_ctx* ctx, int code, const char* fmt, ...);
     return tr_fail(ctx, TR_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
 #define TR_CHECK_LAUNCH(ctx) TR_CUDA(ctx, cudaGetLastError())
 
+// (Re)allocate a context-owned device buffer. An existing buffer is kept when it is large enough: cudaFree /
+// cudaMalloc synchronise the device and cost milliseconds, which would dominate a scene re-upload.
 template <typename T> static inline int tr_realloc(tr_ctx* ctx, T** p, size_t count) {
-    if (*p) { cudaFree(*p); *p = nullptr; }
     if (count == 0) count = 1;
-    TR_CUDA(ctx, cudaMalloc((void**)p, count * sizeof(T)));
+    const size_t bytes = count * sizeof(T);
+    if (*p) {
+        auto it = ctx->capacity.find((void*)*p);
+        if (it != ctx->capacity.end() && it->second >= bytes) return TR_OK;
+        if (it != ctx->capacity.end()) ctx->capacity.erase(it);
+        cudaFree(*p); *p = nullptr;
+    }
+    TR_CUDA(ctx, cudaMalloc((void**)p, bytes));
+    ctx->capacity[(void*)*p] = bytes;
     return TR_OK;
 }
 

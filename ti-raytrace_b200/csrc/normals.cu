@@ -94,13 +94,12 @@ extern "C" int tr_process_normal(tr_ctx* ctx) {
     if (!ctx || !ctx->bvh_ready) return tr_fail(ctx, TR_ERR_INVALID, "tr_process_normal: BVH not built");
     TR_CUDA(ctx, cudaSetDevice(ctx->device));
     // the vertex soup must be 3 consecutive vertices per triangle primitive (Scene.py:94-141)
-    float* d_smooth = nullptr;
-    TR_CUDA(ctx, cudaMalloc((void**)&d_smooth, (size_t)ctx->nv * 12));
+    int rc; if ((rc = tr_realloc(ctx, &ctx->d_smooth, (size_t)ctx->nv * 3))) return rc;
+    float* d_smooth = ctx->d_smooth;
     int g = (ctx->nv + 127) / 128;
     k_smooth_normals<<<g, 128, 0, ctx->stream>>>(ctx->d_vertex, ctx->d_prim, ctx->nv, ctx->d_nodes, ctx->d_leaves, d_smooth);
     k_write_normals<<<g, 128, 0, ctx->stream>>>(ctx->d_vertex, d_smooth, ctx->nv);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_smooth);
     if (e != cudaSuccess) return tr_fail(ctx, TR_ERR_CUDA, "tr_process_normal: %s", cudaGetErrorString(e));
     TR_CHECK_LAUNCH(ctx);
     ctx->shade_ready = false; ctx->fh_ready = false; ctx->gen++;    // shading records hold normals
@@ -118,11 +117,10 @@ extern "C" int tr_vertex_download(tr_ctx* ctx, float* vertex) {
 extern "C" int tr_total_area(tr_ctx* ctx, float* area) {
     if (!ctx || !ctx->d_vertex || !area) return tr_fail(ctx, TR_ERR_INVALID, "tr_total_area: no scene");
     TR_CUDA(ctx, cudaSetDevice(ctx->device));
-    float* d = nullptr; TR_CUDA(ctx, cudaMalloc((void**)&d, 4));
+    float* d = (float*)(ctx->d_build_status + 8);      // scratch word of the status block
     k_total_area<<<1, 1, 0, ctx->stream>>>(ctx->d_vertex, ctx->d_prim, ctx->d_shape, ctx->d_light, ctx->nl, d);
     cudaMemcpyAsync(area, d, 4, cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d);
     if (e != cudaSuccess) return tr_fail(ctx, TR_ERR_CUDA, "tr_total_area: %s", cudaGetErrorString(e));
     return TR_OK;
 }

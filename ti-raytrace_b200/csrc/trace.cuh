@@ -88,10 +88,13 @@ __device__ __forceinline__ float intersect_leaf(const RayPre& r, float4 la, floa
     return t;
 }
 
+// hint the next node's line into L1 while the slab test of the current node is still in flight
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 struct HitRec { float t, u, v; int prim; int mat; int leaf; };
 
 // next node of the walk. ORDERED (trees read from global memory): near child first on a box hit, octant escape link
-// (next8) otherwise = stackless front-to-back order, which halves the node visits on the 130 k-triangle scene.
+// (TrNodeX::next) otherwise = stackless front-to-back order, which halves the node visits on the 130 k-triangle scene.
 // Unordered (small trees staged in shared memory, where every box overlaps every ray and order buys nothing):
 // left child first, single escape link stored in the node.
 template <bool ORDERED>
@@ -139,8 +142,9 @@ __device__ __forceinline__ bool slabs_fast(const RayPre& r, float4 lo, float4 hi
 
 // Closest hit (Scene.py:702-744 semantics).  nodes/leaves may point to shared or global memory.
 // Warp-synchronous: all 32 lanes must call it together; lanes without a ray pass active = false.
+template <bool SMEM>
 __device__ __forceinline__ HitRec trace_closest(const TrNode* __restrict__ nodes, const TrLeaf* __restrict__ leaves,
-                                                 const int* __restrict__ next8, int nnodes,
+                                                 const TrNodeX* __restrict__ nodesx, int nnodes,
                                                  const RayPre& r, bool active, unsigned long long* cnt) {
     HitRec h; h.t = TR_INF; h.u = 0.0f; h.v = 0.0f; h.prim = -1; h.mat = 0; h.leaf = -1;
 #ifdef TR_COUNTERS
@@ -150,13 +154,14 @@ __device__ __forceinline__ HitRec trace_closest(const TrNode* __restrict__ nodes
     int idx = active ? 0 : nnodes, pend = -1;
     while (true) {
         if (pend < 0 && idx < nnodes) {
-            float4 lo = nodes[idx].lo, hi = nodes[idx].hi;
-            int esc = next8[idx * 8 + r.oct];
+            float4 lo, hi; int esc;
+            if (SMEM) { lo = nodes[idx].lo; hi = nodes[idx].hi; esc = __float_as_int(lo.w); }
+            else { lo = nodesx[idx].lo; hi = nodesx[idx].hi; esc = nodesx[idx].next[r.oct]; }
             int link = __float_as_int(hi.w);
             float tmin;
             bool hit = (anypar ? slabs(r, lo, hi, tmin) : slabs_fast(r, lo, hi, tmin)) && !(tmin > h.t * TR_PRUNE_GUARD);
             if (link < 0) { if (hit) pend = -link - 1; } else { TR_COUNT_NODE(); }
-            idx = next_node<true>(idx, link, hit, esc, r.oct);
+            idx = next_node<!SMEM>(idx, link, hit, esc, r.oct);
         }
         const unsigned parked = __ballot_sync(0xffffffffu, pend >= 0);
         const unsigned walking = __ballot_sync(0xffffffffu, pend < 0 && idx < nnodes);
@@ -184,8 +189,9 @@ __device__ __forceinline__ HitRec trace_closest(const TrNode* __restrict__ nodes
 // primitive that would have won the reference's comparison (t < t_t, or t == t_t at a later leaf
 // position); the target only counts if the walk reaches its leaf (every ancestor passes the slab test).
 // Warp-synchronous like trace_closest.
+template <bool SMEM>
 __device__ __forceinline__ bool trace_shadow_visible(const TrNode* __restrict__ nodes, const TrLeaf* __restrict__ leaves,
-                                                     const int* __restrict__ next8, int nnodes,
+                                                     const TrNodeX* __restrict__ nodesx, int nnodes,
                                                      const RayPre& r, bool active, int target_leaf, unsigned long long* cnt) {
 #ifdef TR_COUNTERS
     unsigned cnt_nodes = 0, cnt_leaves = 0;
@@ -202,8 +208,9 @@ __device__ __forceinline__ bool trace_shadow_visible(const TrNode* __restrict__ 
     int idx = visible ? 0 : nnodes, pend = -1;
     while (true) {
         if (pend < 0 && idx < nnodes) {
-            float4 lo = nodes[idx].lo, hi = nodes[idx].hi;
-            int esc = next8[idx * 8 + r.oct];
+            float4 lo, hi; int esc;
+            if (SMEM) { lo = nodes[idx].lo; hi = nodes[idx].hi; esc = __float_as_int(lo.w); }
+            else { lo = nodesx[idx].lo; hi = nodesx[idx].hi; esc = nodesx[idx].next[r.oct]; }
             int link = __float_as_int(hi.w);
             float tmin;
             bool hit = (anypar ? slabs(r, lo, hi, tmin) : slabs_fast(r, lo, hi, tmin)) && !(tmin > tt * TR_PRUNE_GUARD);
@@ -211,7 +218,7 @@ __device__ __forceinline__ bool trace_shadow_visible(const TrNode* __restrict__ 
                 int k = -link - 1;
                 if (k == target_leaf) found = true; else if (hit) pend = k;
             } else { TR_COUNT_NODE(); }
-            idx = next_node<true>(idx, link, hit, esc, r.oct);
+            idx = next_node<!SMEM>(idx, link, hit, esc, r.oct);
         }
         const unsigned parked = __ballot_sync(0xffffffffu, pend >= 0);
         const unsigned walking = __ballot_sync(0xffffffffu, pend < 0 && idx < nnodes);

@@ -23,7 +23,7 @@ struct BatchParams { int frame_begin; int n_frames; unsigned long long seed; int
 
 struct WfArgs {
     // scene
-    const TrNode* nodes; const TrLeaf* leaves; const int* next8; int nnodes; int nleaves;
+    const TrNode* nodes; const TrLeaf* leaves; const TrNodeX* nodesx; int nnodes; int nleaves;
     const TrShade* shade; const float* material; const float4* matlin; const int* light; int nl; const int* leaf_of_prim;
     const int* env; int env_w, env_h; float env_power;
     TrCamera cam;
@@ -33,10 +33,12 @@ struct WfArgs {
     // queues
     float4* pa[2]; float4* pb[2]; float4* pc[2];
     float4* hit; int* cls; size_t cap;
-    float4* sa; float4* sb; float4* sc;
-    float4* L;
+    float4* sa[2]; float4* sb[2]; float4* sc[2];   // shadow queue, ping-pong by depth parity (shadow(d) overlaps trace/shade(d+1))
+    float4* L;                                     // terminal term (emitter / environment) per sample
+    float4* Lnee;                                  // sum of the NEE terms per sample, in depth order
     TrCounters* ctr;
     const BatchParams* bp;
+    int tail_max;                                  // hand the chain to k_tail once its live paths drop to this (0 = never)
     int frame_off, sub_frames;                     // this chain renders local frames [frame_off, frame_off + sub_frames) of the batch
     unsigned smem_nodes_bytes, smem_leaves_bytes, smem_next_bytes;
 };
@@ -70,6 +72,13 @@ __device__ __forceinline__ int warp_append(int* counter, bool pred) {
     return pred ? base + __popc(m & ((1u << lane) - 1u)) : -1;
 }
 
+// true when an earlier stage handed the remaining paths of this chain to the tail kernel (tail_from: 0 = no hand-over,
+// d >= 1 = k_tail owns the paths from depth d on)
+__device__ __forceinline__ bool tail_took_over(const WfArgs& a, int depth) {
+    const int tf = a.ctr->tail_from;
+    return tf > 0 && depth >= tf;
+}
+
 // ------------------------------------------------------------------ generate
 __global__ void __launch_bounds__(WF_THREADS) k_generate(WfArgs a) {
     const BatchParams bp = *a.bp;
@@ -85,7 +94,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_generate(WfArgs a) {
             s = f * a.npix + p;                                   // sample slot within the whole batch
             frame = bp.frame_begin + f;
             valid = slot_to_pixel(a, p, x, y);
-            a.L[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            a.L[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); a.Lnee[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
         int q = warp_append(&a.ctr->nq[0], valid);
         if (valid) {
@@ -104,13 +113,13 @@ __global__ void __launch_bounds__(WF_THREADS) k_generate(WfArgs a) {
 extern __shared__ __align__(128) unsigned char wf_smem[];
 
 template <bool SMEM>
-__device__ __forceinline__ void bvh_view(const WfArgs& a, const TrNode*& nodes, const TrLeaf*& leaves, const int*& next8) {
+__device__ __forceinline__ void bvh_view(const WfArgs& a, const TrNode*& nodes, const TrLeaf*& leaves, const TrNodeX*& nodesx) {
     if (SMEM) {
         __shared__ unsigned long long bar;
         TrNode* sn = (TrNode*)wf_smem; TrLeaf* sl = (TrLeaf*)(wf_smem + a.smem_nodes_bytes);
         tma_stage_to_smem(sn, a.nodes, a.smem_nodes_bytes, sl, a.leaves, a.smem_leaves_bytes, &bar);
-        nodes = sn; leaves = sl; next8 = nullptr;       // small trees: single-link (left-first) threading, see next_step
-    } else { nodes = a.nodes; leaves = a.leaves; next8 = a.next8; }
+        nodes = sn; leaves = sl; nodesx = nullptr;      // small trees: single-link (left-first) threading, see next_node
+    } else { nodes = a.nodes; leaves = a.leaves; nodesx = a.nodesx; }
 }
 
 // ------------------------------------------------------------------ trace (closest hit)
@@ -172,8 +181,9 @@ __device__ __forceinline__ void flush_retired(const WfArgs& a, int depth, const 
 
 template <bool SMEM>
 __global__ void __launch_bounds__(WF_THREADS) k_trace(WfArgs a, int depth) {
-    const TrNode* nodes; const TrLeaf* leaves; const int* next8;
-    bvh_view<SMEM>(a, nodes, leaves, next8);
+    if (tail_took_over(a, depth)) return;
+    const TrNode* nodes; const TrLeaf* leaves; const TrNodeX* nodesx;
+    bvh_view<SMEM>(a, nodes, leaves, nodesx);
     __shared__ int retire_buf[WF_THREADS / 32][64];      // finished (queue index | class << 30), flushed 32 at a time
     const int n = a.ctr->nq[depth], nnodes = a.nnodes;
     const int pp = depth & 1;
@@ -209,9 +219,13 @@ __global__ void __launch_bounds__(WF_THREADS) k_trace(WfArgs a, int depth) {
 #pragma unroll
         for (int step = 0; step < WF_NODE_STEPS; ++step) {
             if (has && pend < 0 && idx < nnodes) {
-                float4 lo = nodes[idx].lo, hi = nodes[idx].hi;
-                int esc = SMEM ? __float_as_int(lo.w) : next8[idx * 8 + r.oct];
+                float4 lo, hi; int esc;
+                if (SMEM) { lo = nodes[idx].lo; hi = nodes[idx].hi; esc = __float_as_int(lo.w); }
+                else { const TrNodeX* nd = nodesx + idx; lo = nd->lo; hi = nd->hi; esc = nd->next[r.oct]; }
                 int link = __float_as_int(hi.w);
+#ifdef WF_PREFETCH
+                if (!SMEM && link >= 0) prefetch_l1(nodesx + (link & 0x1fffffff));      // right child (the left one shares this line or the next)
+#endif
                 float tmin;
                 bool hit = (anypar ? slabs(r, lo, hi, tmin) : slabs_fast(r, lo, hi, tmin)) && !(tmin > h.t * TR_PRUNE_GUARD);
                 if (link < 0) { if (hit) pend = -link - 1; }
@@ -334,108 +348,182 @@ __device__ __forceinline__ LightSample sample_li(const WfArgs& a, V3 p, float u_
 
 // ------------------------------------------------------------------ shade
 // One launch covers the three material-sorted queues back to back: [terminal | disney | glass].
+// One path vertex of PathTrace.render (integrator/PT_RGB.py:66-132): emitter / environment terminal terms go
+// straight to L[slot]; a surviving path comes back as its next queue record, a NEE sample as a shadow record.
+// cl: 0 terminal (miss or emitter), 1 Disney, 2 glass.  Used by the wavefront shade kernel and by the tail kernel.
+struct ShadeOut { bool cont, shadow; float4 nA, nB, nC, sA, sB, sC; };
+
+__device__ __forceinline__ void shade_path(const WfArgs& a, const BatchParams& bp, int depth, int cl,
+                                           float4 A, float4 B, float4 C, float4 Hh, ShadeOut& out) {
+    out.cont = false; out.shadow = false;
+    const bool last = depth + 1 >= bp.max_depth;
+    V3 o = mk3(A.x, A.y, A.z), d = mk3(A.w, B.x, B.y);
+    float brdf_pdf = B.z;
+    unsigned sw = __float_as_uint(B.w); unsigned slot = sw & ~SPEC_BIT; bool perfect_spec = (sw & SPEC_BIT) != 0;
+    V3 T = mk3(C.x, C.y, C.z); unsigned pix = __float_as_uint(C.w);
+    float t = Hh.x; int prim = __float_as_int(Hh.y);
+    if (prim < 0) {
+        // miss: equirect environment lookup (integrator/PT_RGB.py:127-132)
+        if (a.env_w > 0) {
+            float dis = sqrtf(d.x * d.x + d.z * d.z);
+            float tx = (atan2f(d.z, d.x) + TR_PI_ENV) / TR_PI_ENV / 2.0f;
+            float ty = atan2f(d.y, dis) / TR_PI_ENV + 0.5f;
+            V3 e = (srgb_to_lrgb(env_texture2d(a, tx, ty)) * T) * a.env_power;
+            float4 Lv = a.L[slot]; Lv.x += e.x; Lv.y += e.y; Lv.z += e.z; a.L[slot] = Lv;
+        }
+        return;
+    }
+    Surf s = surface_at(a, prim, Hh.z, Hh.w, o, d, t);
+    V3 fn = signf_(dot3(-d, s.gn)) * s.n;                 // UF.faceforward(normal, -direction, gnormal)
+    const float* m = a.material + (size_t)s.mat * 10;
+    V3 mcol = mk3(__ldg(m + 2), __ldg(m + 3), __ldg(m + 4));
+    float p0 = __ldg(m + 5), p1 = __ldg(m + 6);
+    if (cl == 0) {
+        // emitter (integrator/PT_RGB.py:72-81)
+        V3 e;
+        if (perfect_spec) e = T * mcol;
+        else {
+            float fCos = fabsf(dot3(d, s.gn));
+            float area = s.area * (float)a.nl;
+            float light_pdf = (t * t) / (area * fCos);
+            e = power_heuristic(brdf_pdf, light_pdf) * T * mcol;
+        }
+        float4 Lv = a.L[slot]; Lv.x += e.x; Lv.y += e.y; Lv.z += e.z; a.L[slot] = Lv;
+        return;
+    }
+    V3 rc = f4xyz(__ldg(a.matlin + s.mat));            // srgb_to_lrgb(Kd), PT_RGB.py:86, precomputed per material
+    unsigned frame = (unsigned)bp.frame_begin + slot / (unsigned)a.npix;
+    float4 R0 = rng4(bp.seed, pix, frame, 1u + 2u * (unsigned)depth);
+    float4 R1 = rng4(bp.seed, pix, frame, 2u + 2u * (unsigned)depth);
+    V3 next_d; float f_or_b = 1.0f, brdf, pdf; bool spec;
+    if (cl == 2) {
+        spec = true;
+        next_d = glass_sample(d, s.n, p0, R0.w, f_or_b);      // brdf/Glass.py:9-34
+        brdf = 1.0f; pdf = 1.0f;
+    } else {
+        spec = false;
+        if (a.nl > 0) {
+            LightSample ls = sample_li(a, s.pos, R0.x, R0.y, R0.z);
+            float NdotL_s = dot3(fn, ls.dir), NdotL_l = dot3(ls.normal, ls.dir);
+            if (NdotL_s < 0.0f && NdotL_l > 0.0f) {
+                float b2, p2; disney_evaluate_pdf(fn, -d, -ls.dir, p0, p1, b2, p2);
+                V3 c = mk3(0.0f, 0.0f, 0.0f);
+                if (p2 > 0.0f) {
+                    float light_pdf = ls.dist * ls.dist * ls.choice_pdf / NdotL_l;
+                    float wgt = power_heuristic(light_pdf, p2) / fmaxf(0.0001f, light_pdf);
+                    c = ((((wgt * ls.emission) * T) * rc) * b2) * fabsf(NdotL_s);
+                }
+                out.shadow = true;
+                out.sA = make_float4(ls.pos.x, ls.pos.y, ls.pos.z, ls.dir.x);
+                out.sB = make_float4(ls.dir.y, ls.dir.z, __int_as_float(prim), __uint_as_float(slot));
+                out.sC = make_float4(c.x, c.y, c.z, 0.0f);
+            }
+        }
+        next_d = disney_sample(d, fn, p0, p1, R0.w, R1.x, R1.y);
+        disney_evaluate_pdf(fn, -d, next_d, p0, p1, brdf, pdf);
+        brdf *= fabsf(dot3(s.n, next_d));
+    }
+    V3 next_o = offset_ray(s.pos, signf_(f_or_b) * fn);
+    if (pdf > 0.0f) {
+        bool alive = true;
+        if (f_or_b < 0.0f) { float Rr = expf(-t / p1); if (R1.z >= Rr) alive = false; }   // PT_RGB.py:118-122
+        if (alive && !last) {
+            T = T * ((brdf / pdf) * rc);
+            out.cont = true;
+            out.nA = make_float4(next_o.x, next_o.y, next_o.z, next_d.x);
+            out.nB = make_float4(next_d.y, next_d.z, pdf, __uint_as_float(slot | (spec ? SPEC_BIT : 0u)));
+            out.nC = make_float4(T.x, T.y, T.z, __uint_as_float(pix));
+        }
+    }
+}
+
 #ifndef WF_SHADE_MIN_BLOCKS
 #define WF_SHADE_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(WF_THREADS, WF_SHADE_MIN_BLOCKS) k_shade(WfArgs a, int depth) {
+    if (tail_took_over(a, depth)) return;
     const BatchParams bp = *a.bp;
     const int n0 = a.ctr->ncls[depth][0], n1 = a.ctr->ncls[depth][1], n2 = a.ctr->ncls[depth][2];
     const int n = n0 + n1 + n2;
     const int pp = depth & 1, np_ = pp ^ 1;
     const int stride = gridDim.x * blockDim.x;
     const int n_r = (n + 31) & ~31;
-    const bool last = depth + 1 >= bp.max_depth;
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_r; w += stride) {
-        bool cont = false, shadow = false;
-        float4 nA, nB, nC, sA, sB, sC;
+        ShadeOut o; o.cont = false; o.shadow = false;
         if (w < n) {
             int cl = (w < n0) ? 0 : (w < n0 + n1 ? 1 : 2);
             int q = a.cls[(size_t)cl * a.cap + (w - (cl == 0 ? 0 : (cl == 1 ? n0 : n0 + n1)))];
-            float4 A = a.pa[pp][q], B = a.pb[pp][q], C = a.pc[pp][q], Hh = a.hit[q];
-            V3 o = mk3(A.x, A.y, A.z), d = mk3(A.w, B.x, B.y);
-            float brdf_pdf = B.z;
-            unsigned sw = __float_as_uint(B.w); unsigned slot = sw & ~SPEC_BIT; bool perfect_spec = (sw & SPEC_BIT) != 0;
-            V3 T = mk3(C.x, C.y, C.z); unsigned pix = __float_as_uint(C.w);
-            float t = Hh.x; int prim = __float_as_int(Hh.y);
-            if (prim < 0) {
-                // miss: equirect environment lookup (integrator/PT_RGB.py:127-132)
-                if (a.env_w > 0) {
-                    float dis = sqrtf(d.x * d.x + d.z * d.z);
-                    float tx = (atan2f(d.z, d.x) + TR_PI_ENV) / TR_PI_ENV / 2.0f;
-                    float ty = atan2f(d.y, dis) / TR_PI_ENV + 0.5f;
-                    V3 e = (srgb_to_lrgb(env_texture2d(a, tx, ty)) * T) * a.env_power;
-                    float4 Lv = a.L[slot]; Lv.x += e.x; Lv.y += e.y; Lv.z += e.z; a.L[slot] = Lv;
+            shade_path(a, bp, depth, cl, a.pa[pp][q], a.pb[pp][q], a.pc[pp][q], a.hit[q], o);
+        }
+        int qn = warp_append(&a.ctr->nq[depth + 1], o.cont);
+        if (o.cont) { a.pa[np_][qn] = o.nA; a.pb[np_][qn] = o.nB; a.pc[np_][qn] = o.nC; }
+        int qs = warp_append(&a.ctr->nshadow[depth], o.shadow);
+        if (o.shadow) { a.sa[pp][qs] = o.sA; a.sb[pp][qs] = o.sB; a.sc[pp][qs] = o.sC; }
+    }
+    // last block out decides whether the next depth is small enough for the tail kernel (queue size is final now)
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&a.ctr->shade_done[depth], 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        int nn = *((volatile int*)&a.ctr->nq[depth + 1]);
+        if (a.tail_max > 0 && depth + 1 < bp.max_depth && nn > 0 && nn <= a.tail_max) a.ctr->tail_from = depth + 1;
+    }
+}
+
+// ------------------------------------------------------------------ tail (megakernel for the last few paths)
+// Deep bounces carry a tiny fraction of the rays (C3: 1.7 % beyond depth 2) but every wavefront stage pays the latency
+// of its slowest ray (~0.1-0.2 ms for a 1000-node walk), 3 stages x 13 depths.  Once a chain's live-path count drops to
+// tail_max, this kernel takes the remaining paths and runs them to completion, one path per lane: closest hit, shade,
+// shadow ray, next bounce, all in registers.  Same device functions, same per-path operation order (NEE terms are added
+// to Lnee in depth order, after shadow(depth-1) of the wavefront: the kernel is enqueued behind it), so the film is
+// bit-identical with or without the hand-over.
+template <bool SMEM>
+__global__ void __launch_bounds__(WF_THREADS) k_tail(WfArgs a, int depth) {
+    if (a.ctr->tail_from != depth) return;
+    const TrNode* nodes; const TrLeaf* leaves; const TrNodeX* nodesx;
+    bvh_view<SMEM>(a, nodes, leaves, nodesx);
+    const BatchParams bp = *a.bp;
+    const int n = a.ctr->nq[depth], pp = depth & 1;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    unsigned long long n_closest = 0, n_shadow = 0;
+    for (int base = warp * 32; base < n; base += nwarps * 32) {
+        const int q = base + lane;
+        bool alive = q < n;
+        float4 A = make_float4(0.f, 0.f, 0.f, 1.f), B = make_float4(1.f, 1.f, 1.f, 0.f), C = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (alive) { A = a.pa[pp][q]; B = a.pb[pp][q]; C = a.pc[pp][q]; }
+        for (int d = depth; d < bp.max_depth; ++d) {
+            if (__ballot_sync(0xffffffffu, alive) == 0u) break;
+            RayPre r = make_ray(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y));
+            HitRec h = trace_closest<SMEM>(nodes, leaves, nodesx, a.nnodes, r, alive, a.ctr->visits);
+            ShadeOut o; o.cont = false; o.shadow = false;
+            if (alive) {
+                ++n_closest;
+                int cl = 0;
+                if (h.prim >= 0) {
+                    int mt = (int)__ldg(a.material + (size_t)h.mat * 10);
+                    cl = (mt == TR_MAT_LIGHT) ? 0 : (mt == TR_MAT_GLASS ? 2 : 1);
                 }
-            } else {
-                Surf s = surface_at(a, prim, Hh.z, Hh.w, o, d, t);
-                V3 fn = signf_(dot3(-d, s.gn)) * s.n;                 // UF.faceforward(normal, -direction, gnormal)
-                const float* m = a.material + (size_t)s.mat * 10;
-                V3 mcol = mk3(__ldg(m + 2), __ldg(m + 3), __ldg(m + 4));
-                float p0 = __ldg(m + 5), p1 = __ldg(m + 6);
-                if (cl == 0) {
-                    // emitter (integrator/PT_RGB.py:72-81)
-                    V3 e;
-                    if (perfect_spec) e = T * mcol;
-                    else {
-                        float fCos = fabsf(dot3(d, s.gn));
-                        float area = s.area * (float)a.nl;
-                        float light_pdf = (t * t) / (area * fCos);
-                        e = power_heuristic(brdf_pdf, light_pdf) * T * mcol;
-                    }
-                    float4 Lv = a.L[slot]; Lv.x += e.x; Lv.y += e.y; Lv.z += e.z; a.L[slot] = Lv;
-                } else {
-                    V3 rc = f4xyz(__ldg(a.matlin + s.mat));            // srgb_to_lrgb(Kd), PT_RGB.py:86, precomputed per material
-                    unsigned frame = (unsigned)bp.frame_begin + slot / (unsigned)a.npix;
-                    float4 R0 = rng4(bp.seed, pix, frame, 1u + 2u * (unsigned)depth);
-                    float4 R1 = rng4(bp.seed, pix, frame, 2u + 2u * (unsigned)depth);
-                    V3 next_d; float f_or_b = 1.0f, brdf, pdf; bool spec;
-                    if (cl == 2) {
-                        spec = true;
-                        next_d = glass_sample(d, s.n, p0, R0.w, f_or_b);      // brdf/Glass.py:9-34
-                        brdf = 1.0f; pdf = 1.0f;
-                    } else {
-                        spec = false;
-                        if (a.nl > 0) {
-                            LightSample ls = sample_li(a, s.pos, R0.x, R0.y, R0.z);
-                            float NdotL_s = dot3(fn, ls.dir), NdotL_l = dot3(ls.normal, ls.dir);
-                            if (NdotL_s < 0.0f && NdotL_l > 0.0f) {
-                                float b2, p2; disney_evaluate_pdf(fn, -d, -ls.dir, p0, p1, b2, p2);
-                                V3 c = mk3(0.0f, 0.0f, 0.0f);
-                                if (p2 > 0.0f) {
-                                    float light_pdf = ls.dist * ls.dist * ls.choice_pdf / NdotL_l;
-                                    float wgt = power_heuristic(light_pdf, p2) / fmaxf(0.0001f, light_pdf);
-                                    c = ((((wgt * ls.emission) * T) * rc) * b2) * fabsf(NdotL_s);
-                                }
-                                shadow = true;
-                                sA = make_float4(ls.pos.x, ls.pos.y, ls.pos.z, ls.dir.x);
-                                sB = make_float4(ls.dir.y, ls.dir.z, __int_as_float(prim), __uint_as_float(slot));
-                                sC = make_float4(c.x, c.y, c.z, 0.0f);
-                            }
-                        }
-                        next_d = disney_sample(d, fn, p0, p1, R0.w, R1.x, R1.y);
-                        disney_evaluate_pdf(fn, -d, next_d, p0, p1, brdf, pdf);
-                        brdf *= fabsf(dot3(s.n, next_d));
-                    }
-                    V3 next_o = offset_ray(s.pos, signf_(f_or_b) * fn);
-                    if (pdf > 0.0f) {
-                        bool alive = true;
-                        if (f_or_b < 0.0f) { float Rr = expf(-t / p1); if (R1.z >= Rr) alive = false; }   // PT_RGB.py:118-122
-                        if (alive && !last) {
-                            T = T * ((brdf / pdf) * rc);
-                            cont = true;
-                            nA = make_float4(next_o.x, next_o.y, next_o.z, next_d.x);
-                            nB = make_float4(next_d.y, next_d.z, pdf, __uint_as_float(slot | (spec ? SPEC_BIT : 0u)));
-                            nC = make_float4(T.x, T.y, T.z, __uint_as_float(pix));
-                        }
-                    }
+                shade_path(a, bp, d, cl, A, B, C, make_float4(h.t, __int_as_float(h.prim), h.u, h.v), o);
+            }
+            const bool sh = alive && o.shadow;
+            if (__ballot_sync(0xffffffffu, sh) != 0u) {
+                RayPre rs = make_ray(mk3(o.sA.x, o.sA.y, o.sA.z), mk3(o.sA.w, o.sB.x, o.sB.y));
+                int tleaf = sh ? __ldg(a.leaf_of_prim + __float_as_int(o.sB.z)) : 0;
+                bool vis = trace_shadow_visible<SMEM>(nodes, leaves, nodesx, a.nnodes, rs, sh, tleaf, a.ctr->visits + 2);
+                if (sh) {
+                    ++n_shadow;
+                    if (vis) { unsigned slot = __float_as_uint(o.sB.w); float4 Lv = a.Lnee[slot]; Lv.x += o.sC.x; Lv.y += o.sC.y; Lv.z += o.sC.z; a.Lnee[slot] = Lv; }
                 }
             }
+            alive = alive && o.cont;
+            if (alive) { A = o.nA; B = o.nB; C = o.nC; }
         }
-        int qn = warp_append(&a.ctr->nq[depth + 1], cont);
-        if (cont) { a.pa[np_][qn] = nA; a.pb[np_][qn] = nB; a.pc[np_][qn] = nC; }
-        int qs = warp_append(&a.ctr->nshadow[depth], shadow);
-        if (shadow) { a.sa[qs] = sA; a.sb[qs] = sB; a.sc[qs] = sC; }
     }
+    if (n_closest) atomicAdd(&a.ctr->tail_rays[0], n_closest);
+    if (n_shadow) atomicAdd(&a.ctr->tail_rays[1], n_shadow);
 }
 
 // ------------------------------------------------------------------ shadow
@@ -443,8 +531,9 @@ __global__ void __launch_bounds__(WF_THREADS, WF_SHADE_MIN_BLOCKS) k_shade(WfArg
 // primitive that would have won the reference's nearest-hit comparison (see trace_shadow_visible).
 template <bool SMEM>
 __global__ void __launch_bounds__(WF_THREADS) k_shadow(WfArgs a, int depth) {
-    const TrNode* nodes; const TrLeaf* leaves; const int* next8;
-    bvh_view<SMEM>(a, nodes, leaves, next8);
+    if (tail_took_over(a, depth)) return;
+    const TrNode* nodes; const TrLeaf* leaves; const TrNodeX* nodesx;
+    bvh_view<SMEM>(a, nodes, leaves, nodesx);
     const int n = a.ctr->nshadow[depth], nnodes = a.nnodes;
     int* cursor = &a.ctr->wf_shadow[depth];
     const int lane = threadIdx.x & 31;
@@ -460,7 +549,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_shadow(WfArgs a, int depth) {
         if ((__popc(idle) >= WF_REFILL_MIN || idle == 0xffffffffu) && (feed.more || feed.cb < feed.ce)) {
             int nq = feed_lanes(feed, cursor, n, idle, lane);
             if (nq >= 0) {
-                float4 A = a.sa[nq], B = a.sb[nq];
+                float4 A = a.sa[depth & 1][nq], B = a.sb[depth & 1][nq];
                 r = make_ray(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y));
                 anypar = r.px || r.py || r.pz;
                 tleaf = __ldg(a.leaf_of_prim + __float_as_int(B.z)); slot = __float_as_uint(B.w);
@@ -478,9 +567,13 @@ __global__ void __launch_bounds__(WF_THREADS) k_shadow(WfArgs a, int depth) {
 #pragma unroll
         for (int step = 0; step < WF_NODE_STEPS; ++step) {
             if (has && pend < 0 && idx < nnodes) {
-                float4 lo = nodes[idx].lo, hi = nodes[idx].hi;
-                int esc = SMEM ? __float_as_int(lo.w) : next8[idx * 8 + r.oct];
+                float4 lo, hi; int esc;
+                if (SMEM) { lo = nodes[idx].lo; hi = nodes[idx].hi; esc = __float_as_int(lo.w); }
+                else { const TrNodeX* nd = nodesx + idx; lo = nd->lo; hi = nd->hi; esc = nd->next[r.oct]; }
                 int link = __float_as_int(hi.w);
+#ifdef WF_PREFETCH
+                if (!SMEM && link >= 0) prefetch_l1(nodesx + (link & 0x1fffffff));      // right child (the left one shares this line or the next)
+#endif
                 float tmin;
                 bool hit = (anypar ? slabs(r, lo, hi, tmin) : slabs_fast(r, lo, hi, tmin)) && !(tmin > tt * TR_PRUNE_GUARD);
                 if (link < 0) { int k = -link - 1; if (k == tleaf) found = true; else if (hit) pend = k; }
@@ -506,8 +599,8 @@ __global__ void __launch_bounds__(WF_THREADS) k_shadow(WfArgs a, int depth) {
         }
         if ((finm >> lane) & 1u) {
             if (visible && found) {
-                float4 C = a.sc[q];
-                float4 Lv = a.L[slot]; Lv.x += C.x; Lv.y += C.y; Lv.z += C.z; a.L[slot] = Lv;
+                float4 C = a.sc[depth & 1][q];
+                float4 Lv = a.Lnee[slot]; Lv.x += C.x; Lv.y += C.y; Lv.z += C.z; a.Lnee[slot] = Lv;
             }
         }
         idle |= finm;
@@ -527,7 +620,9 @@ __global__ void __launch_bounds__(WF_THREADS) k_accumulate(WfArgs a) {
         float* o = a.hdr + ((size_t)x * a.H + y) * 3;
         float r = o[0], g = o[1], b = o[2];
         for (int f = 0; f < bp.n_frames; ++f) {
-            float4 Lv = a.L[(size_t)f * a.npix + p];
+            // radiance = (NEE terms in depth order) + terminal term: the reference's summation order (PT_RGB.py:76-109,131)
+            float4 Lt = a.L[(size_t)f * a.npix + p], Lv = a.Lnee[(size_t)f * a.npix + p];
+            Lv.x += Lt.x; Lv.y += Lt.y; Lv.z += Lt.z;
             float coff = 1.0f / ((float)(bp.frame_begin + f) + 1.0f);
             r = Lv.x * coff + r * (1.0f - coff);
             g = Lv.y * coff + g * (1.0f - coff);
@@ -552,7 +647,7 @@ __global__ void k_debug(WfArgs a, float* __restrict__ fh) {
     int i = p / a.H, j = p - i * a.H;
     V3 o = mk3(a.cam.eye[0], a.cam.eye[1], a.cam.eye[2]), d = camera_dir(a.cam, i, j, 0.0f, 0.0f);
     RayPre r = make_ray(o, d);
-    HitRec h = trace_closest(a.nodes, a.leaves, a.next8, a.nnodes, r, active, a.ctr->visits);
+    HitRec h = trace_closest<false>(a.nodes, a.leaves, a.nodesx, a.nnodes, r, active, a.ctr->visits);
     if (!active) return;
     float* f = fh + (size_t)p * 16;
     V3 col = mk3(0, 0, 0), pos = mk3(0, 0, 0), gn = mk3(0, 0, 0), nn = mk3(0, 0, 0);
@@ -634,16 +729,17 @@ static int fill_args(tr_ctx* ctx, WfArgs& a) {
         ctx->matlin_ready = true; ctx->gen++;
     }
     memset(&a, 0, sizeof(a));
-    a.nodes = ctx->d_nodes; a.leaves = ctx->d_leaves; a.next8 = ctx->d_next8; a.nnodes = 2 * ctx->np - 1; a.nleaves = ctx->np;
+    a.nodes = ctx->d_nodes; a.leaves = ctx->d_leaves; a.nodesx = ctx->d_nodesx; a.nnodes = 2 * ctx->np - 1; a.nleaves = ctx->np;
     a.shade = ctx->d_shade; a.material = ctx->d_material; a.matlin = ctx->d_matlin; a.light = ctx->d_light; a.nl = ctx->nl; a.leaf_of_prim = ctx->d_leaf_of_prim;
     a.env = ctx->d_env; a.env_w = ctx->d_env ? ctx->env_w : 0; a.env_h = ctx->env_h; a.env_power = ctx->env_power;
     a.cam = ctx->cam; a.W = ctx->W; a.H = ctx->H; a.tiles = ctx->d_tiles; a.npix = ctx->n_local_tiles * TR_TILE * TR_TILE;
     a.hdr = ctx->d_hdr;
     for (int k = 0; k < 2; ++k) { a.pa[k] = ctx->d_path[k][0]; a.pb[k] = ctx->d_path[k][1]; a.pc[k] = ctx->d_path[k][2]; }
     a.hit = ctx->d_hit; a.cls = ctx->d_cls; a.cap = ctx->wf_cap;
-    a.sa = ctx->d_shq[0]; a.sb = ctx->d_shq[1]; a.sc = ctx->d_shq[2]; a.L = ctx->d_L;
+    for (int k = 0; k < 2; ++k) { a.sa[k] = ctx->d_shq[k][0]; a.sb[k] = ctx->d_shq[k][1]; a.sc[k] = ctx->d_shq[k][2]; }
+    a.L = ctx->d_L; a.Lnee = ctx->d_Lnee;
     a.ctr = ctx->d_ctr; a.bp = (const BatchParams*)ctx->d_batch_params;
-    a.frame_off = 0; a.sub_frames = 1 << 20;
+    a.frame_off = 0; a.sub_frames = 1 << 20; a.tail_max = ctx->opt_tail_max;
     a.smem_nodes_bytes = (unsigned)((size_t)a.nnodes * sizeof(TrNode));
     a.smem_leaves_bytes = (unsigned)((size_t)a.nleaves * sizeof(TrLeaf));
     a.smem_next_bytes = (unsigned)((size_t)a.nnodes * 8 * sizeof(int));
@@ -656,13 +752,14 @@ static int ensure_wavefront(tr_ctx* ctx, size_t slots) {
     for (int k = 0; k < 2; ++k) for (int j = 0; j < 3; ++j) if ((rc = tr_realloc(ctx, &ctx->d_path[k][j], slots))) return rc;
     if ((rc = tr_realloc(ctx, &ctx->d_hit, slots))) return rc;
     if ((rc = tr_realloc(ctx, &ctx->d_cls, slots * 3))) return rc;
-    for (int j = 0; j < 3; ++j) if ((rc = tr_realloc(ctx, &ctx->d_shq[j], slots))) return rc;
+    for (int k = 0; k < 2; ++k) for (int j = 0; j < 3; ++j) if ((rc = tr_realloc(ctx, &ctx->d_shq[k][j], slots))) return rc;
     if ((rc = tr_realloc(ctx, &ctx->d_L, slots))) return rc;
+    if ((rc = tr_realloc(ctx, &ctx->d_Lnee, slots))) return rc;
     ctx->wf_cap = slots; ctx->gen++;
     return TR_OK;
 }
 
-struct LaunchCfg { int grid_trace, grid_shadow, grid_simple; size_t smem; bool use_smem; };
+struct LaunchCfg { int grid_trace, grid_shadow, grid_simple; size_t smem; bool use_smem; };   // memset before use (compared bytewise)
 
 static int launch_cfg(tr_ctx* ctx, const WfArgs& a, LaunchCfg& c) {
     size_t bytes = (size_t)a.smem_nodes_bytes + a.smem_leaves_bytes;
@@ -690,14 +787,19 @@ static WfArgs chain_args(const WfArgs& a, int j, int fs) {
     size_t off = (size_t)j * fs * a.npix;
     for (int k = 0; k < 2; ++k) { c.pa[k] = a.pa[k] + off; c.pb[k] = a.pb[k] + off; c.pc[k] = a.pc[k] + off; }
     c.hit = a.hit + off; c.cls = a.cls + 3 * off; c.cap = (size_t)fs * a.npix;
-    c.sa = a.sa + off; c.sb = a.sb + off; c.sc = a.sc + off;
+    for (int k = 0; k < 2; ++k) { c.sa[k] = a.sa[k] + off; c.sb[k] = a.sb[k] + off; c.sc[k] = a.sc[k] + off; }
     c.ctr = a.ctr + j; c.frame_off = j * fs; c.sub_frames = fs;
     return c;
 }
 
-// one chain: generate, then max_depth x (trace, shade, shadow).
+// one chain: generate, then max_depth x (trace, shade) on stream s, with shadow(d) on stream ss:
+//   shadow(d) needs shade(d) (its queue) and shadow(d-1) (it sums the NEE terms in depth order);
+//   shade(d+2) needs shadow(d) (the shadow queue is a ping-pong pair).
+// So the long tail of a trace stage overlaps the previous depth's shadow rays.  ss == s serialises everything.
 // ev != nullptr (stage timing, single chain, non-graph mode): 4 events per depth bracket trace / shade / shadow.
-static int enqueue_chain(tr_ctx* ctx, const WfArgs& a, const LaunchCfg& c, int max_depth, cudaStream_t s, uint64_t* launches, cudaEvent_t* ev) {
+static int enqueue_chain(tr_ctx* ctx, const WfArgs& a, const LaunchCfg& c, int max_depth, cudaStream_t s, cudaStream_t ss,
+                         cudaEvent_t* dep, uint64_t* launches, cudaEvent_t* ev) {
+    const bool split = (ss != s);
     TR_CUDA(ctx, cudaMemsetAsync(a.ctr, 0, sizeof(TrCounters), s));
     k_generate<<<c.grid_simple, WF_THREADS, 0, s>>>(a); ++*launches;
     for (int d = 0; d < max_depth; ++d) {
@@ -705,15 +807,29 @@ static int enqueue_chain(tr_ctx* ctx, const WfArgs& a, const LaunchCfg& c, int m
         if (c.use_smem) k_trace<true><<<c.grid_trace, WF_THREADS, c.smem, s>>>(a, d);
         else k_trace<false><<<c.grid_trace, WF_THREADS, 0, s>>>(a, d);
         if (ev) cudaEventRecord(ev[4 * d + 1], s);
+        if (split && d >= 2) TR_CUDA(ctx, cudaStreamWaitEvent(s, dep[2 * (d - 2) + 1], 0));
         k_shade<<<c.grid_simple, WF_THREADS, 0, s>>>(a, d);
         if (ev) cudaEventRecord(ev[4 * d + 2], s);
         if (a.nl > 0) {
-            if (c.use_smem) k_shadow<true><<<c.grid_shadow, WF_THREADS, c.smem, s>>>(a, d);
-            else k_shadow<false><<<c.grid_shadow, WF_THREADS, 0, s>>>(a, d);
+            if (split) { TR_CUDA(ctx, cudaEventRecord(dep[2 * d], s)); TR_CUDA(ctx, cudaStreamWaitEvent(ss, dep[2 * d], 0)); }
+            if (c.use_smem) k_shadow<true><<<c.grid_shadow, WF_THREADS, c.smem, ss>>>(a, d);
+            else k_shadow<false><<<c.grid_shadow, WF_THREADS, 0, ss>>>(a, d);
+            if (split) TR_CUDA(ctx, cudaEventRecord(dep[2 * d + 1], ss));
+            ++*launches;
+        }
+        if (a.tail_max > 0 && d + 1 < max_depth) {
+            // behind shadow(d) on the same stream: NEE terms stay in depth order; shade(d) (the hand-over decision) is done
+            if (split && a.nl == 0) { TR_CUDA(ctx, cudaEventRecord(dep[2 * d], s)); TR_CUDA(ctx, cudaStreamWaitEvent(ss, dep[2 * d], 0)); }
+            if (c.use_smem) k_tail<true><<<c.grid_trace, WF_THREADS, c.smem, ss>>>(a, d + 1);
+            else k_tail<false><<<c.grid_trace, WF_THREADS, 0, ss>>>(a, d + 1);
             ++*launches;
         }
         if (ev) cudaEventRecord(ev[4 * d + 3], s);
         *launches += 2;
+    }
+    if (split) {                                                                           // join: everything enqueued on ss
+        TR_CUDA(ctx, cudaEventRecord(dep[2 * max_depth], ss));
+        TR_CUDA(ctx, cudaStreamWaitEvent(s, dep[2 * max_depth], 0));
     }
     TR_CHECK_LAUNCH(ctx);
     return TR_OK;
@@ -731,7 +847,9 @@ static int enqueue_batch(tr_ctx* ctx, const WfArgs& a, const LaunchCfg& c, int m
     }
     for (int j = 0; j < K; ++j) {
         WfArgs cj = chain_args(a, j, fs);
-        if ((rc = enqueue_chain(ctx, cj, c, max_depth, j == 0 ? s : ctx->sub_stream[j], launches, K == 1 ? ev : nullptr))) return rc;
+        cudaStream_t sj = (j == 0) ? s : ctx->sub_stream[j];
+        cudaStream_t ssj = (ev || !ctx->opt_shadow_overlap) ? sj : ctx->shadow_stream[j];
+        if ((rc = enqueue_chain(ctx, cj, c, max_depth, sj, ssj, ctx->dep_ev.data() + (size_t)j * 2 * (TR_MAX_DEPTH_CAP + 1), launches, K == 1 ? ev : nullptr))) return rc;
     }
     for (int j = 1; j < K; ++j) {
         TR_CUDA(ctx, cudaEventRecord(ctx->ev_join[j], ctx->sub_stream[j]));
@@ -760,8 +878,13 @@ extern "C" int tr_render_pt_rgb(tr_ctx* ctx, int frame_begin, int n_frames, int 
     const int fs = (F + K - 1) / K;                                   // frames per chain
     if ((rc = ensure_wavefront(ctx, (size_t)fs * K * a.npix))) return rc;
     if ((rc = fill_args(ctx, a))) return rc;
-    LaunchCfg cfg; if ((rc = launch_cfg(ctx, a, cfg))) return rc;
+    LaunchCfg cfg; memset(&cfg, 0, sizeof(cfg)); if ((rc = launch_cfg(ctx, a, cfg))) return rc;
     cudaStream_t s = ctx->stream;
+    if (ctx->dep_ev.empty()) {
+        ctx->dep_ev.resize((size_t)TR_MAX_CHAINS * 2 * (TR_MAX_DEPTH_CAP + 1));
+        for (auto& e : ctx->dep_ev) TR_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (int j = 0; j < TR_MAX_CHAINS; ++j) TR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->shadow_stream[j], cudaStreamNonBlocking));
+    }
     if (K > 1 && !ctx->sub_stream[1]) {
         for (int j = 1; j < TR_MAX_CHAINS; ++j) {
             TR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->sub_stream[j], cudaStreamNonBlocking));
@@ -781,7 +904,10 @@ extern "C" int tr_render_pt_rgb(tr_ctx* ctx, int frame_begin, int n_frames, int 
         BatchParams bp; bp.frame_begin = frame_begin + f0; bp.n_frames = nf; bp.seed = seed; bp.max_depth = max_depth; bp.pad = 0;
         TR_CUDA(ctx, cudaMemcpyAsync(ctx->d_batch_params, &bp, sizeof(bp), cudaMemcpyHostToDevice, s));
         if (ctx->opt_graph && !timing) {
-            if (!ctx->graph_exec || ctx->graph_depth != max_depth || ctx->graph_gen != ctx->gen || ctx->graph_chains != K) {
+            // a captured graph stays valid as long as the kernel arguments it baked in are unchanged
+            if (!ctx->graph_exec || ctx->graph_depth != max_depth || ctx->graph_chains != K || ctx->graph_fs != fs ||
+                ctx->graph_args.size() != sizeof(WfArgs) + sizeof(LaunchCfg) || memcmp(ctx->graph_args.data(), &a, sizeof(WfArgs)) != 0 ||
+                memcmp(ctx->graph_args.data() + sizeof(WfArgs), &cfg, sizeof(LaunchCfg)) != 0) {
                 if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
                 cudaGraph_t g; uint64_t l2 = 0;
                 TR_CUDA(ctx, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
@@ -791,7 +917,9 @@ extern "C" int tr_render_pt_rgb(tr_ctx* ctx, int frame_begin, int n_frames, int 
                 if (e != cudaSuccess) return tr_fail(ctx, TR_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
                 TR_CUDA(ctx, cudaGraphInstantiate(&ctx->graph_exec, g, 0));
                 cudaGraphDestroy(g);
-                ctx->graph_depth = max_depth; ctx->graph_launches = (int)l2; ctx->graph_gen = ctx->gen; ctx->graph_chains = K;
+                ctx->graph_depth = max_depth; ctx->graph_launches = (int)l2; ctx->graph_gen = ctx->gen; ctx->graph_chains = K; ctx->graph_fs = fs;
+                ctx->graph_args.resize(sizeof(WfArgs) + sizeof(LaunchCfg));
+                memcpy(ctx->graph_args.data(), &a, sizeof(WfArgs)); memcpy(ctx->graph_args.data() + sizeof(WfArgs), &cfg, sizeof(LaunchCfg));
             }
             TR_CUDA(ctx, cudaGraphLaunch(ctx->graph_exec, s));
             launches += (uint64_t)ctx->graph_launches;
@@ -802,7 +930,9 @@ extern "C" int tr_render_pt_rgb(tr_ctx* ctx, int frame_begin, int n_frames, int 
         TR_CUDA(ctx, cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(TrCounters) * K, cudaMemcpyDeviceToHost, s));
         TR_CUDA(ctx, cudaStreamSynchronize(s));
         for (int j = 0; j < K; ++j) {
-            for (int d = 0; d < max_depth; ++d) { rays_c += (uint64_t)ctx->h_ctr[j].nq[d]; rays_s += (uint64_t)ctx->h_ctr[j].nshadow[d]; }
+            const int tf = ctx->h_ctr[j].tail_from;
+            for (int d = 0; d < max_depth; ++d) { if (tf == 0 || d != tf) rays_c += (uint64_t)ctx->h_ctr[j].nq[d]; rays_s += (uint64_t)ctx->h_ctr[j].nshadow[d]; }
+            rays_c += ctx->h_ctr[j].tail_rays[0]; rays_s += ctx->h_ctr[j].tail_rays[1];
             for (int k = 0; k < 4; ++k) vis[k] += ctx->h_ctr[j].visits[k];
         }
         if (timing) for (int d = 0; d < max_depth; ++d) {
@@ -876,11 +1006,11 @@ __global__ void k_test_trace(WfArgs a, int n, const float* __restrict__ o, const
     const bool active = k < n;
     if (!active) k = 0;
     RayPre r = make_ray(mk3(o[k * 3], o[k * 3 + 1], o[k * 3 + 2]), mk3(d[k * 3], d[k * 3 + 1], d[k * 3 + 2]));
-    HitRec h = trace_closest(a.nodes, a.leaves, a.next8, a.nnodes, r, active, nullptr);
+    HitRec h = trace_closest<false>(a.nodes, a.leaves, a.nodesx, a.nnodes, r, active, nullptr);
     if (shadow) {
         // cross-check the early-exit shadow query against the closest-hit answer it must reproduce
         bool has = active && h.prim >= 0;
-        bool vis = trace_shadow_visible(a.nodes, a.leaves, a.next8, a.nnodes, r, has, has ? a.leaf_of_prim[h.prim] : 0, nullptr);
+        bool vis = trace_shadow_visible<false>(a.nodes, a.leaves, a.nodesx, a.nnodes, r, has, has ? a.leaf_of_prim[h.prim] : 0, nullptr);
         if (has && !vis) h.prim = -2;
     }
     if (!active) return;
@@ -894,7 +1024,7 @@ extern "C" int tr_test_trace(tr_ctx* ctx, int n, const float* o, const float* d,
     if (!ctx->bvh_ready) return tr_fail(ctx, TR_ERR_INVALID, "tr_test_trace: BVH not built");
     int rc; if ((rc = tr_build_shade_table(ctx))) return rc;
     WfArgs a; memset(&a, 0, sizeof(a));
-    a.nodes = ctx->d_nodes; a.leaves = ctx->d_leaves; a.next8 = ctx->d_next8; a.nnodes = 2 * ctx->np - 1; a.leaf_of_prim = ctx->d_leaf_of_prim;
+    a.nodes = ctx->d_nodes; a.leaves = ctx->d_leaves; a.nodesx = ctx->d_nodesx; a.nnodes = 2 * ctx->np - 1; a.leaf_of_prim = ctx->d_leaf_of_prim;
     float *d_o, *d_d, *d_t, *d_uv; int* d_p;
     TR_CUDA(ctx, cudaMalloc((void**)&d_o, (size_t)n * 12)); TR_CUDA(ctx, cudaMalloc((void**)&d_d, (size_t)n * 12));
     TR_CUDA(ctx, cudaMalloc((void**)&d_t, (size_t)n * 4)); TR_CUDA(ctx, cudaMalloc((void**)&d_p, (size_t)n * 4));

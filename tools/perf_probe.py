@@ -19,6 +19,9 @@ ap.add_argument("--batch", default="0")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--opts", default="", help="name=value,... passed to tr_set_option")
 ap.add_argument("--counters", action="store_true")
+ap.add_argument("--max-depth", type=int, default=15)
+ap.add_argument("--shard", default="", help="rank,nranks: emulate one rank of a tile-sharded run")
+ap.add_argument("--e2e", action="store_true", help="time the pieces of the host-buffer path")
 args = ap.parse_args()
 os.environ["TIRAY_LIB"] = args.lib
 
@@ -31,6 +34,27 @@ ctx = _native.context()
 for kv in filter(None, args.opts.split(",")):
     k, v = kv.split("="); ctx.set_option(k, int(v))
 integ, cam = ex.integrator, ex.cam
+integ.max_depth = args.max_depth
+if args.shard:
+    r_, n_ = (int(x) for x in args.shard.split(",")); ctx.set_shard(r_, n_)
+if args.e2e:
+    import time
+    sc = ex.scene
+    for rep in range(3):
+        t = [time.perf_counter()]
+        ctx.scene_upload(sc.vertex_np, sc.primitive_np, sc.material_np, sc.shape_np if sc.shape_count else None,
+                         sc.light_np if sc.light_count else None, sc.minboundarynp, sc.maxboundarynp); t.append(time.perf_counter())
+        sc.env.setup_data_gpu(sc.env_power); t.append(time.perf_counter())
+        ctx.bvh_build(); t.append(time.perf_counter())
+        build_ms = ctx.stats()["ms_build"]
+        if wl["normals"]:
+            ctx.process_normal()
+        ctx.synchronize(); t.append(time.perf_counter())
+        cam.dirty = True; ctx.film_clear(); cam.frame = 0; cam.frame_cpu[0] = 0
+        integ.render_frames(wl["spp"]); ctx.synchronize(); t.append(time.perf_counter())
+        ctx.tonemap(0.5); ctx.film_download(True, True); t.append(time.perf_counter())
+        names = ["scene_upload", "env_upload", "bvh_build(host wall)", "process_normal", "render", "tonemap+download"]
+        print("e2e pieces ms:", ", ".join("%s %.2f" % (n, (b - a) * 1e3) for n, a, b in zip(names, t[:-1], t[1:])), "| bvh device ms %.3f" % build_ms, flush=True)
 for b in [int(x) for x in args.batch.split(",")]:
     ctx.set_option("batch_frames", b)
     best = None
