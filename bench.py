@@ -281,7 +281,7 @@ def run_native(args, wl):
                            "stage_ms_per_step": {"trace": stt["ms_trace"], "shade": stt["ms_shade"], "shadow": stt["ms_shadow"], "total": stt["ms_total"]},
                            "note": "effective bandwidth: the BVH is SMEM/L2 resident, compulsory DRAM traffic is the 48 B/ray queue stream"}
         if not args.no_cpu:
-            sample_spp = 64 if args.workload == "cornell" else 4      # ~10-20 s of CPU work
+            sample_spp = 64 if args.workload == "cornell" else 16     # the full step: a few seconds on 16 threads, ~15 s on 4
             cpu_reference_run(wl, 1)                                   # warm the pages / OpenMP pool
             v, r, dt, cores, _ = cpu_reference_run(wl, sample_spp)
             out["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port",
