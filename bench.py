@@ -4,7 +4,7 @@
   python bench.py --gpus N --steps K --warmup W [--workload cornell|teapot_mc] [--impl native|reference]
 
 A step = one full pass of the hot path over one batch: clear the film, render `spp` samples per pixel
-(cornell: 512x512, 64 spp = BASELINE configs[1]; teapot_mc: 1024x1024, 16 spp = configs[2]) with the
+(cornell: 512x512, 64 spp = BASELINE configs[1]; teapot_mc: 1024x1024, 64 spp = configs[2]; teapot_mc16: 16 spp) with the
 scene, BVH and camera resident in HBM, and (N > 1) one NCCL sum-reduce of the film.  rays = closest-hit
 traversals + shadow traversals actually executed (device queue counters).
 
@@ -34,8 +34,10 @@ for p in (PKG, os.path.join(PKG, "integrator"), os.path.join(PKG, "example"), RO
 WORKLOADS = {
     "cornell": dict(module="cornell_box", W=512, H=512, spp=64, files=["cornell_box.obj"], sphere_light=False, env_power=0.0,
                     desc="cornell_box.py PT_RGB 512x512 64spp max_depth 15 (BASELINE configs[1])", normals=False),
-    "teapot_mc": dict(module="teapot_mc", W=1024, H=1024, spp=16, files=["mc.obj", "Teapot.obj"], sphere_light=True, env_power=5.0,
-                      desc="single_model.py mc.obj+Teapot.obj (130720 tris) PT_RGB 1024x1024 16spp (BASELINE configs[2])", normals=True),
+    "teapot_mc": dict(module="teapot_mc", W=1024, H=1024, spp=64, files=["mc.obj", "Teapot.obj"], sphere_light=True, env_power=5.0,
+                      desc="single_model.py mc.obj+Teapot.obj (130720 tris) PT_RGB 1024x1024 64spp (BASELINE configs[2])", normals=True),
+    "teapot_mc16": dict(module="teapot_mc", W=1024, H=1024, spp=16, files=["mc.obj", "Teapot.obj"], sphere_light=True, env_power=5.0,
+                        desc="single_model.py mc.obj+Teapot.obj (130720 tris) PT_RGB 1024x1024 16spp (SURVEY 8d C3)", normals=True),
 }
 MAX_DEPTH = 15
 
@@ -281,7 +283,7 @@ def run_native(args, wl):
                            "stage_ms_per_step": {"trace": stt["ms_trace"], "shade": stt["ms_shade"], "shadow": stt["ms_shadow"], "total": stt["ms_total"]},
                            "note": "effective bandwidth: the BVH is SMEM/L2 resident, compulsory DRAM traffic is the 48 B/ray queue stream"}
         if not args.no_cpu:
-            sample_spp = 64 if args.workload == "cornell" else 16     # the full step: a few seconds on 16 threads, ~15 s on 4
+            sample_spp = 64 if args.workload == "cornell" else 16     # a few seconds on 16 threads, ~15 s on 4
             cpu_reference_run(wl, 1)                                   # warm the pages / OpenMP pool
             v, r, dt, cores, _ = cpu_reference_run(wl, sample_spp)
             out["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port",

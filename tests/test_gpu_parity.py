@@ -312,3 +312,87 @@ def test_full_size_teapot_mc_first_hit(gpu_ctx, oracle_tables):
     o = build_oracle_scene(oracle_tables("teapot_mc", sphere_light=True), res, res)
     f = o.first_hit(res, res)
     assert np.array_equal(g["prim"], f["prim"]) and np.array_equal(g["t"], f["t"])
+
+
+# ---------------------------------------------------------------------------------- edge cases
+def test_ragged_image_sizes_and_single_pixel(gpu_ctx, oracle_tables):
+    """image sizes that are not multiples of the 32x32 tile (partial tiles) and a 1x1 film"""
+    for W, H in [(100, 70), (33, 31), (1, 1)]:
+        scene, cam, integ = build_gpu_scene("cornell", W, H)
+        integ.render_frames(2)
+        g = integ.hdr.to_numpy()
+        o = build_oracle_scene(oracle_tables("cornell"), W, H)
+        ref, cnt = o.render_pt_rgb(W, H, 0, 2)
+        frac_bad, _ = _compare_radiance(g, ref)
+        assert g.shape == (W, H, 3) and frac_bad <= max(1e-3, 1.5 / (W * H)), (W, H, frac_bad)
+
+
+def test_scene_without_lights_and_env_only(gpu_ctx, oracle_tables):
+    """no emitter at all: NEE is skipped (light_count = 0); with an environment map the only light is the miss term"""
+    W = H = 96
+    for power in (0.0, 5.0):
+        scene, cam, integ = build_gpu_scene("teapot", W, H, env_power=power)
+        integ.render_frames(2)
+        g = integ.hdr.to_numpy()
+        o = build_oracle_scene(oracle_tables("teapot"), W, H, env_power=power)
+        ref, cnt = o.render_pt_rgb(W, H, 0, 2)
+        frac_bad, mean_err = _compare_radiance(g, ref, rel=2e-3)
+        assert frac_bad < 5e-3, (power, frac_bad)
+        assert cnt["shadow"] == 0 and integ_stats_shadow(gpu_ctx) == 0
+        if power == 0.0:
+            assert not g.any()
+
+
+def integ_stats_shadow(ctx):
+    return int(ctx.stats()["rays_shadow"])
+
+
+def test_depth_limits_and_seed(gpu_ctx, oracle_tables):
+    """max_depth 1 and 3 (the tail kernel / last-stage paths), another seed"""
+    W = H = 96
+    o = build_oracle_scene(oracle_tables("cornell"), W, H)
+    for depth, seed in [(1, 0), (3, 7), (15, 123456789012)]:
+        scene, cam, integ = build_gpu_scene("cornell", W, H)
+        integ.max_depth, integ.seed = depth, seed
+        integ.render_frames(3)
+        ref, cnt = o.render_pt_rgb(W, H, 0, 3, max_depth=depth, seed=seed)
+        frac_bad, _ = _compare_radiance(integ.hdr.to_numpy(), ref)
+        assert frac_bad < 2e-3, (depth, seed, frac_bad)
+
+
+def test_options_do_not_change_the_film(gpu_ctx):
+    """chains, shadow overlap, tail hand-over, graph replay, batch size: bit-identical film"""
+    W = H = 160
+    scene, cam, integ = build_gpu_scene("sphere", W, H, sphere_light=True, glass0=True, env_power=5.0)
+    ref = None
+    for opts in [dict(chains=1, shadow_overlap=0, tail_max=0, graph=0), dict(chains=4, shadow_overlap=1, tail_max=16384, graph=1),
+                 dict(chains=8, shadow_overlap=1, tail_max=100000000, graph=1, batch_frames=3), dict(chains=2, tail_max=64, batch_frames=1)]:
+        for k, v in opts.items():
+            gpu_ctx.set_option(k, v)
+        gpu_ctx.film_clear(); cam.frame = 0; cam.frame_cpu[0] = 0
+        integ.render_frames(5)
+        img = integ.hdr.to_numpy()
+        if ref is None:
+            ref = img
+        assert np.array_equal(img, ref), opts
+
+
+def test_error_paths(gpu_ctx):
+    """call-order and argument errors come back as RuntimeError with the library's text, never a crash"""
+    import _native
+    with pytest.raises(RuntimeError, match="BVH not built"):
+        gpu_ctx.bvh_download()
+    with pytest.raises(RuntimeError):
+        gpu_ctx.render_pt_rgb(0, 1)
+    with pytest.raises(RuntimeError, match="bad size"):
+        gpu_ctx.film_create(0, 5)
+    with pytest.raises(RuntimeError, match="unknown option"):
+        gpu_ctx.set_option("no_such_option", 1)
+    scene = make_product_scene("cornell"); scene.setup_data_cpu(); scene.setup_data_gpu()
+    gpu_ctx.film_create(8, 8)
+    with pytest.raises(RuntimeError, match="camera not set"):
+        gpu_ctx.render_pt_rgb(0, 1)
+    with pytest.raises(RuntimeError, match="bad arguments"):
+        gpu_ctx.render_pt_rgb(0, 0)
+    with pytest.raises(RuntimeError, match="device"):
+        _native.Context(1000)
