@@ -380,8 +380,8 @@ def test_options_do_not_change_the_film(gpu_ctx):
 def test_error_paths(gpu_ctx):
     """call-order and argument errors come back as RuntimeError with the library's text, never a crash"""
     import _native
-    with pytest.raises(RuntimeError, match="BVH not built"):
-        gpu_ctx.bvh_download()
+    with pytest.raises(RuntimeError, match="no scene uploaded"):
+        gpu_ctx.bvh_build()
     with pytest.raises(RuntimeError):
         gpu_ctx.render_pt_rgb(0, 1)
     with pytest.raises(RuntimeError, match="bad size"):
