@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """bench.py — headline metric of BASELINE.json: Mrays/s (and ms/spp) of PT_RGB.
 
-  python bench.py --gpus N --steps K --warmup W [--workload cornell|teapot_mc] [--impl native|reference]
+  python bench.py --gpus N --steps K --warmup W [--workload cornell|teapot_mc|teapot_mc16|spectral_box] [--impl native|reference]
 
 A step = one full pass of the hot path over one batch: clear the film, render `spp` samples per pixel
-(cornell: 512x512, 64 spp = BASELINE configs[1]; teapot_mc: 1024x1024, 64 spp = configs[2]; teapot_mc16: 16 spp) with the
+(cornell: 512x512, 64 spp = BASELINE configs[1]; teapot_mc: 1024x1024, 64 spp = configs[2]; teapot_mc16: 16 spp;
+spectral_box: PT_Spec hero-wavelength 512x512, 64 spp = configs[3]) with the
 scene, BVH and camera resident in HBM, and (N > 1) one NCCL sum-reduce of the film.  rays = closest-hit
 traversals + shadow traversals actually executed (device queue counters).
 
@@ -38,6 +39,9 @@ WORKLOADS = {
                       desc="single_model.py mc.obj+Teapot.obj (130720 tris) PT_RGB 1024x1024 64spp (BASELINE configs[2])", normals=True),
     "teapot_mc16": dict(module="teapot_mc", W=1024, H=1024, spp=16, files=["mc.obj", "Teapot.obj"], sphere_light=True, env_power=5.0,
                         desc="single_model.py mc.obj+Teapot.obj (130720 tris) PT_RGB 1024x1024 16spp (SURVEY 8d C3)", normals=True),
+    "spectral_box": dict(module="spectral_box", W=512, H=512, spp=64, files=["cornell_box.obj"], sphere_light=False, env_power=0.0,
+                         desc="spectral_box.py PT_Spec hero-wavelength 512x512 64spp max_depth 10 (BASELINE configs[3])", normals=True,
+                         spectral=True, max_depth=10),
 }
 MAX_DEPTH = 15
 
@@ -98,6 +102,9 @@ def cpu_reference_run(wl, spp, frame_begin=0):
     """the reference algorithm on the host cores (oracle, fast build): returns (Mrays/s, rays, seconds, threads)"""
     from oracle import oracle
     t = oracle_tables(wl)
+    if wl.get("spectral"):
+        for k in range(3):                          # example/spectral_box.py:22-27
+            t.material[k, 0] = 10.0; t.material[k, 1] = float(k)
     s = oracle.OracleScene(t, fast=True).build()
     cam = oracle.fit_camera(t, wl["W"], wl["H"])
     s.set_camera(cam[1], cam[2], *cam[3:])
@@ -105,8 +112,14 @@ def cpu_reference_run(wl, spp, frame_begin=0):
     s.set_env(packed, w, h, wl["env_power"])
     if wl["normals"]:
         s.process_normal()
-    t0 = time.perf_counter()
-    _, cnt = s.render_pt_rgb(wl["W"], wl["H"], frame_begin, spp, MAX_DEPTH, 0)
+    if wl.get("spectral"):
+        from oracle import spectral
+        spectral.attach(s, PKG)
+        t0 = time.perf_counter()
+        _, cnt = spectral.render_pt_spec(s, wl["W"], wl["H"], frame_begin, spp, wl["max_depth"], 0)
+    else:
+        t0 = time.perf_counter()
+        _, cnt = s.render_pt_rgb(wl["W"], wl["H"], frame_begin, spp, MAX_DEPTH, 0)
     dt = time.perf_counter() - t0
     rays = cnt["closest"] + cnt["shadow"]
     return rays / dt / 1e6, rays, dt, int(oracle.lib(True).orc_num_threads()), cnt
@@ -117,7 +130,7 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_spp = 4 if args.workload == "cornell" else 1
+    sample_spp = 4 if args.workload in ("cornell", "spectral_box") else 1
     for _ in range(args.warmup):
         cpu_reference_run(wl, 1)
     rays = 0; secs = 0.0; cores = 1
@@ -206,6 +219,9 @@ def run_native(args, wl):
     import UtilsFunc as UF
     scene = ex.scene
     h2d = scene.vertex_np.nbytes + scene.primitive_np.nbytes + scene.material_np.nbytes + scene.env.np_img.nbytes + 64 + 64 + 12
+    if wl.get("spectral"):                       # sensor, rgb2spec table, four spectra, sky state
+        h2d += integ.data_np.nbytes + integ.rgb2spec.table_data_np.nbytes + integ.rgb2spec.table_scale_np.nbytes + 113 * 4
+        h2d += sum(sp.data_np.nbytes for sp in (integ.d65, integ.white, integ.red, integ.green))
     d2h = 2 * wl["W"] * wl["H"] * 12
     e2e_rays = 0; e2e_t = 0.0
     for k in range(max(1, min(args.steps, 3)) + 1):
@@ -213,6 +229,8 @@ def run_native(args, wl):
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
+        if wl.get("spectral"):
+            integ.setup_data_gpu()               # spectral tables H2D + white-point normalisation
         scene.setup_data_gpu()                   # tables H2D (pageable numpy) + env + LBVH build
         ta = time.perf_counter()
         if wl["normals"]:
@@ -256,19 +274,22 @@ def run_native(args, wl):
         stt = integ.render_frames(spp)
         ctx.set_option("stage_timing", 0)
         n_batches = (spp * wl["W"] * wl["H"] + paths_in_flight - 1) // paths_in_flight
-        n_trace_launches = n_batches * MAX_DEPTH
-        # visit counts of the same traversal policy from the counters flavour of the library
+        n_trace_launches = n_batches * integ.max_depth
+        # visit counts of the same traversal policy from the counters flavour of the library: the same host classes
+        # drive a second context
         cctx = _native.Context(local, "libtiray_counters.so")
-        cctx.scene_upload(scene.vertex_np, scene.primitive_np, scene.material_np, scene.shape_np if scene.shape_count else None,
-                          scene.light_np if scene.light_count else None, scene.minboundarynp, scene.maxboundarynp)
-        cctx.env_upload(scene.env.np_img, scene.env.wid, scene.env.hgt, scene.env_power)
-        cctx.bvh_build()
-        if wl["normals"]:
-            cctx.process_normal()
-        cctx.film_create(wl["W"], wl["H"])
-        cctx.camera_set(cam.view_np[0], cam.view_inv_np[0], cam.eye_np[0], cam.fx, cam.fy, cam.cx, cam.cy)
-        cctx.render_pt_rgb(0, spp, MAX_DEPTH, 0)
-        cs = cctx.stats(); cctx.close()
+        main_ctx, _native._ctx = _native._ctx, cctx
+        try:
+            integ.setup_data_cpu(); integ.setup_data_gpu(); scene.setup_data_gpu()
+            if wl["normals"]:
+                scene.process_normal()
+            cam.dirty = True; cam.frame = 0; cam.frame_cpu[0] = 0
+            integ.render_frames(spp)
+            cs = cctx.stats()
+        finally:
+            _native._ctx = main_ctx
+            cam.dirty = True
+        cctx.close()
         algo_bytes = 48 * cs["rays_closest"] + 32 * cs["node_visits"] + 68 * cs["leaf_tests"]
         trace_s = stt["ms_trace"] * 1e-3
         peak, how = measured_peak_gbs()
@@ -283,7 +304,7 @@ def run_native(args, wl):
                            "stage_ms_per_step": {"trace": stt["ms_trace"], "shade": stt["ms_shade"], "shadow": stt["ms_shadow"], "total": stt["ms_total"]},
                            "note": "effective bandwidth: the BVH is SMEM/L2 resident, compulsory DRAM traffic is the 48 B/ray queue stream"}
         if not args.no_cpu:
-            sample_spp = 64 if args.workload == "cornell" else 16     # a few seconds on 16 threads, ~15 s on 4
+            sample_spp = 64 if args.workload in ("cornell", "spectral_box") else 16     # a few seconds on 16 threads, ~15 s on 4
             cpu_reference_run(wl, 1)                                   # warm the pages / OpenMP pool
             v, r, dt, cores, _ = cpu_reference_run(wl, sample_spp)
             out["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port",

@@ -110,6 +110,12 @@ int tr_set_shard(tr_ctx* ctx, int rank, int nranks);
  * Asynchronous on the context stream. stack_size is accepted for API parity (the traversal is
  * stackless); max_depth is the reference's MAX_DEPTH (15). */
 int tr_render_pt_rgb(tr_ctx* ctx, int frame_begin, int n_frames, int max_depth, uint64_t seed);
+/* replaces PT_Spec.PathTrace.render (integrator/PT_Spec.py:189-280): the same wavefront with four hero wavelengths per
+ * path (spectrum/HeroSample.py), spectral reflectances through the rgb2spec model or measured tables (MAT_SPECTRAL),
+ * the Sellmeier glass of Glass.sample_lambda (brdf/Glass.py:39-65), the sky dome on a miss, and AddSplat
+ * (CIE XYZ -> linear sRGB) as accumulation.  max_depth is the reference's MAX_DEPTH (10).  Requires every
+ * tr_spec_*_upload below. */
+int tr_render_pt_spec(tr_ctx* ctx, int frame_begin, int n_frames, int max_depth, uint64_t seed);
 /* replaces Debug.render (integrator/Debug.py:44-66); also fills the first-hit buffers */
 int tr_render_debug(tr_ctx* ctx);
 /* frame-0 primary rays and first hits, index [x*H+y]; any pointer may be NULL */
@@ -121,6 +127,21 @@ int tr_stats_get(tr_ctx* ctx, tr_stats* out);
 /* tuning: "batch_frames" (0 = auto), "max_paths", "chains" (parallel wavefront chains per batch),
  * "stage_timing", "graph" (CUDA-graph replay), "smem_bvh" (TMA staging of small BVHs) */
 int tr_set_option(tr_ctx* ctx, const char* name, int value);
+
+/* ---- spectral tables: replace the from_numpy calls of PT_Spec.setup_data_gpu (integrator/PT_Spec.py:89-98) ---------
+ * sensor: CIE 1931 colour matching functions, n x 3 f32 on a regular grid lmin..lmax nm (:57-79,90) */
+int tr_spec_sensor_upload(tr_ctx* ctx, const float* xyz, int n, float lmin, float lmax);
+/* one tabulated spectrum (spectrum/Spectrum.py:18-40): which = 0 D65 illuminant, 1 white, 2 red, 3 green reflectance
+ * (the MAT_SPECTRAL tables selected by the material's alebdoTex, integrator/PT_Spec.py:119-135) */
+int tr_spec_spectrum_upload(tr_ctx* ctx, int which, const float* data, int n, float lmin, float lmax);
+int tr_spec_spectrum_download(tr_ctx* ctx, int which, float* data /* n */);
+/* Jakob-Hanika coefficient table (spectrum/Rgb2Spec.py:15-42): scale res f32, data 3*res^3*3 f32 */
+int tr_spec_rgb2spec_upload(tr_ctx* ctx, const float* scale, const float* data, int res);
+/* Hosek-Wilkie sky state after Sky.update (sky/Sky.py:84-96,107-159): configs 11 x 9, radiances 11, sun direction */
+int tr_spec_sky_upload(tr_ctx* ctx, const float* configs, const float* radiances, const float sun_dir[3]);
+/* replaces PT_Spec.normalize_spec (integrator/PT_Spec.py:101-107) = cal_white_point (:174-187) + Spectrum.scale
+ * (spectrum/Spectrum.py:53-56): scales table `which` so that its CIE Y is 1; returns the white point before scaling */
+int tr_spec_normalize(tr_ctx* ctx, int which, float white_point[3]);
 
 /* ---- unit hooks: the device functions of the shading/traversal kernels run on arrays, for parity
  * tests against the oracle (brdf/Disney.py:17-108, brdf/Glass.py:9-34, UtilsFunc.py:440-461,
@@ -136,6 +157,13 @@ int tr_test_rng(tr_ctx* ctx, uint64_t seed, uint32_t pixel, uint32_t frame, uint
 /* arbitrary rays through the traversal kernels; shadow != 0 uses the nearest-hit shadow query */
 int tr_test_trace(tr_ctx* ctx, int n, const float* o, const float* d, int shadow,
                   float* t, int32_t* prim, float* uv /* n x 2 or NULL */);
+
+/* spectral device functions: Hero.srgb_to_spec (spectrum/HeroSample.py:46-57) for n (srgb, hero wavelength) pairs;
+ * Sky.get_solar_radiance (sky/Sky.py:258-265); Spectrum.sample (spectrum/Spectrum.py:43-51) of table `which`, or
+ * PT_Spec.sample of the sensor (which = -1, out n x 3) */
+int tr_test_srgb_to_spec(tr_ctx* ctx, int n, const float* rgb /* n x 3 */, const float* lambda0 /* n */, float* out4 /* n x 4 */);
+int tr_test_sky_radiance(tr_ctx* ctx, int n, const float* theta, const float* gamma, const float* wavelength, float* out);
+int tr_test_spectrum_sample(tr_ctx* ctx, int which, int n, const float* lambda, float* out);
 
 #ifdef __cplusplus
 }

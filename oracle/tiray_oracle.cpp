@@ -92,6 +92,15 @@ inline F4 rng4(uint64_t seed, uint32_t pixel, uint32_t frame, uint32_t block) {
 // ---------------------------------------------------------------- scene container
 struct Counters { uint64_t closest = 0, shadow = 0, node_visits = 0, leaf_tests = 0; };
 
+// spectral tables of PT_Spec (integrator/PT_Spec.py:44-98)
+struct Spectrum1 { std::vector<float> data; float lmin = 0, lmax = 0, lrange = 1; int size = 0; };
+struct SpecData {
+    std::vector<float> sensor; float s_lmin = 0, s_lmax = 0, s_lrange = 1; int s_size = 0;   // CIE 1931 2-deg CMFs, n x 3
+    Spectrum1 sp[4];                                   // 0 d65, 1 white, 2 red, 3 green
+    std::vector<float> rs_scale, rs_data; int rs_res = 0;   // Jakob-Hanika rgb2spec table
+    float sky_cfg[11 * 9] = {0}, sky_rad[11] = {0}, sun_dir[3] = {0, 0, 1}; bool sky_on = false;
+};
+
 struct Scene {
     std::vector<float>   vertex;    // nv x 9
     std::vector<int32_t> prim;      // np x 3
@@ -110,6 +119,7 @@ struct Scene {
     // camera (Camera.py)
     float view_inv[16]; float eye[3]; float fx, fy, cx, cy;
     int stack_size = 64;
+    SpecData spec;
     int max_stack_seen = 0; int overflow = 0;
 };
 
@@ -791,6 +801,8 @@ V3 pt_rgb_pixel(Scene& s, int i, int j, int frame, int max_depth, uint64_t seed,
     return L;
 }
 
+#include "spec_core.inc"
+
 }  // namespace
 
 // =============================================================================== C API
@@ -1022,5 +1034,7 @@ int orc_num_threads() {
 #endif
 }
 int orc_slabs(const float* o, const float* d, const float* mn, const float* mx) { return slabs(v3(o[0], o[1], o[2]), v3(d[0], d[1], d[2]), mn, mx); }
+
+#include "spec_api.inc"
 
 }  // extern "C"

@@ -33,20 +33,23 @@ def oracle_tables():
     from oracle import objload
     cache = {}
 
-    def get(name, sphere_light=False, glass0=False):
-        key = (name, sphere_light, glass0)
+    def get(name, sphere_light=False, glass0=False, spectral_walls=False):
+        key = (name, sphere_light, glass0, spectral_walls)
         if key not in cache:
             shapes = [objload.sphere_light_rows()] if sphere_light else []
 
             def edit(mats):
                 if glass0:
                     mats[0][0] = 1.0; mats[0][5] = 1.3; mats[0][6] = 5.0
+                if spectral_walls:                       # example/spectral_box.py:22-27
+                    for k in range(3):
+                        mats[k][0] = 10.0; mats[k][1] = float(k)
             cache[key] = objload.load_scene([model(f) for f in SCENES[name]["files"]], shapes=shapes, material_edit=edit)
         return cache[key]
     return get
 
 
-def make_product_scene(name, sphere_light=False, glass0=False, env_power=0.0):
+def make_product_scene(name, sphere_light=False, glass0=False, env_power=0.0, spectral_walls=False):
     """product-side Scene (host packing only; no device calls)"""
     import Scene
     import SceneData as SCD
@@ -55,6 +58,9 @@ def make_product_scene(name, sphere_light=False, glass0=False, env_power=0.0):
         s.add_obj("model/" + f)
     if glass0:
         m = s.material_cpu[0]; m.type = SCD.MAT_GLASS; m.setIor(1.3); m.setExtinciton(5.0)
+    if spectral_walls:
+        for k in range(3):
+            s.material_cpu[k].type = SCD.MAT_SPECTRAL; s.material_cpu[k].alebdoTex = k
     if sphere_light:
         sh = SCD.Shape(); sh.type = SCD.SHPAE_SPHERE; sh.pos = [0.0, 20.0, 0.0]; sh.setRadius(5.0)
         mt = SCD.Material(); mt.type = SCD.MAT_LIGHT; mt.setColor([50.0, 50.0, 50.0])

@@ -162,11 +162,11 @@ def test_brdf_hooks_match_oracle(gpu_ctx):
 
 
 # ---------------------------------------------------------------------------------- path tracing
-def _compare_radiance(g, o, rel=1e-3, outlier_budget=1e-3):
+def _compare_radiance(g, o, rel=1e-3, outlier_budget=1e-3, floor=1.0):
     """per-pixel L-inf <= rel * max(1, value); pixels whose path took another branch at a float
     boundary (libm ulp differences) are outliers, bounded by the budget"""
     err = np.abs(g - o).max(axis=2)
-    tol = rel * np.maximum(1.0, np.abs(o).max(axis=2))
+    tol = rel * np.maximum(floor, np.abs(o).max(axis=2))
     bad = err > tol
     return bad.mean(), float(np.abs(g.mean((0, 1)) - o.mean((0, 1))).max() / max(1e-9, o.mean()))
 

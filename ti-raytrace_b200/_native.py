@@ -49,6 +49,7 @@ SIGNATURES = {
     "tr_film_device_ptr": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "tr_set_shard": (C.c_int, [_vp, C.c_int, C.c_int]),
     "tr_render_pt_rgb": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_uint64]),
+    "tr_render_pt_spec": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_uint64]),
     "tr_render_debug": (C.c_int, [_vp]),
     "tr_first_hit_download": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tr_tonemap": (C.c_int, [_vp, C.c_float]),
@@ -60,6 +61,15 @@ SIGNATURES = {
     "tr_test_offset_ray": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
     "tr_test_rng": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _vp]),
     "tr_test_trace": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "tr_spec_sensor_upload": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_float]),
+    "tr_spec_spectrum_upload": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_float, C.c_float]),
+    "tr_spec_spectrum_download": (C.c_int, [_vp, C.c_int, _vp]),
+    "tr_spec_rgb2spec_upload": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "tr_spec_sky_upload": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "tr_spec_normalize": (C.c_int, [_vp, C.c_int, _vp]),
+    "tr_test_srgb_to_spec": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
+    "tr_test_sky_radiance": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp]),
+    "tr_test_spectrum_sample": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
 }
 
 _libs = {}
@@ -197,6 +207,44 @@ class Context:
     # ---- integrators
     def render_pt_rgb(self, frame_begin, n_frames, max_depth=15, seed=0):
         self._ck(self.lib.tr_render_pt_rgb(self.h, int(frame_begin), int(n_frames), int(max_depth), int(seed)), "tr_render_pt_rgb")
+
+    def render_pt_spec(self, frame_begin, n_frames, max_depth=10, seed=0):
+        self._ck(self.lib.tr_render_pt_spec(self.h, int(frame_begin), int(n_frames), int(max_depth), int(seed)), "tr_render_pt_spec")
+
+    # ---- spectral tables (PT_Spec)
+    def spec_sensor_upload(self, xyz, lmin, lmax):
+        a = _f(xyz, (-1, 3)); self._ck(self.lib.tr_spec_sensor_upload(self.h, _ptr(a), a.shape[0], float(lmin), float(lmax)), "tr_spec_sensor_upload")
+
+    def spec_spectrum_upload(self, which, data, lmin, lmax):
+        a = _f(data, (-1,)); self._ck(self.lib.tr_spec_spectrum_upload(self.h, int(which), _ptr(a), a.shape[0], float(lmin), float(lmax)), "tr_spec_spectrum_upload")
+
+    def spec_spectrum_download(self, which, n):
+        out = np.zeros(int(n), np.float32); self._ck(self.lib.tr_spec_spectrum_download(self.h, int(which), _ptr(out)), "tr_spec_spectrum_download"); return out
+
+    def spec_rgb2spec_upload(self, scale, data, res):
+        a, b = _f(scale, (-1,)), _f(data, (-1,))
+        assert a.size == res and b.size == res ** 3 * 9
+        self._ck(self.lib.tr_spec_rgb2spec_upload(self.h, _ptr(a), _ptr(b), int(res)), "tr_spec_rgb2spec_upload")
+
+    def spec_sky_upload(self, configs, radiances, sun_dir):
+        a, b, c = _f(configs, (-1,)), _f(radiances, (-1,)), _f(sun_dir, (-1,))
+        assert a.size == 99 and b.size == 11 and c.size == 3
+        self._ck(self.lib.tr_spec_sky_upload(self.h, _ptr(a), _ptr(b), _ptr(c)), "tr_spec_sky_upload")
+
+    def spec_normalize(self, which):
+        wp = np.zeros(3, np.float32); self._ck(self.lib.tr_spec_normalize(self.h, int(which), _ptr(wp)), "tr_spec_normalize"); return wp
+
+    def test_srgb_to_spec(self, rgb, lambda0):
+        a, b = _f(rgb, (-1, 3)), _f(lambda0, (-1,)); out = np.zeros((a.shape[0], 4), np.float32)
+        self._ck(self.lib.tr_test_srgb_to_spec(self.h, a.shape[0], _ptr(a), _ptr(b), _ptr(out)), "hook"); return out
+
+    def test_sky_radiance(self, theta, gamma, wl):
+        a, b, c = _f(theta, (-1,)), _f(gamma, (-1,)), _f(wl, (-1,)); out = np.zeros(a.shape[0], np.float32)
+        self._ck(self.lib.tr_test_sky_radiance(self.h, a.shape[0], _ptr(a), _ptr(b), _ptr(c), _ptr(out)), "hook"); return out
+
+    def test_spectrum_sample(self, which, lam):
+        a = _f(lam, (-1,)); out = np.zeros((a.shape[0], 3) if which < 0 else a.shape[0], np.float32)
+        self._ck(self.lib.tr_test_spectrum_sample(self.h, int(which), a.shape[0], _ptr(a), _ptr(out)), "hook"); return out
 
     def render_debug(self):
         self._ck(self.lib.tr_render_debug(self.h), "tr_render_debug")

@@ -65,7 +65,9 @@ void tr_ctx_destroy(tr_ctx* ctx) {
                     ctx->d_build_status, ctx->d_nodes, ctx->d_leaves, ctx->d_leaf_of_prim, ctx->d_shade, ctx->d_hist, ctx->d_hdr, ctx->d_rgb,
                     ctx->d_fh, ctx->d_tiles, ctx->d_path[0][0], ctx->d_path[0][1], ctx->d_path[0][2], ctx->d_path[1][0],
                     ctx->d_path[1][1], ctx->d_path[1][2], ctx->d_hit, ctx->d_cls, ctx->d_shq[0][0], ctx->d_shq[0][1],
-                    ctx->d_shq[0][2], ctx->d_shq[1][0], ctx->d_shq[1][1], ctx->d_shq[1][2], ctx->d_Lnee, ctx->d_L, ctx->d_ctr, ctx->d_batch_params, ctx->d_matlin, ctx->d_axis, ctx->d_nodesx, ctx->d_smooth};
+                    ctx->d_shq[0][2], ctx->d_shq[1][0], ctx->d_shq[1][1], ctx->d_shq[1][2], ctx->d_Lnee, ctx->d_L, ctx->d_ctr, ctx->d_batch_params, ctx->d_matlin, ctx->d_axis, ctx->d_nodesx, ctx->d_smooth,
+                    ctx->d_sensor, ctx->d_spectrum[0], ctx->d_spectrum[1], ctx->d_spectrum[2], ctx->d_spectrum[3], ctx->d_rs_scale, ctx->d_rs_data,
+                    ctx->d_sky, ctx->d_matspec, ctx->d_white_point};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -116,7 +118,7 @@ int tr_scene_upload(tr_ctx* ctx, const float* vertex, int nv, const int32_t* pri
     else TR_CUDA(ctx, cudaMemsetAsync(ctx->d_shape, 0, 10 * 4, s));
     if (nl > 0 && light) TR_CUDA(ctx, cudaMemcpyAsync(ctx->d_light, light, (size_t)nl * 4, cudaMemcpyHostToDevice, s));
     TR_CUDA(ctx, cudaStreamSynchronize(s));   // host arrays are only borrowed for the call
-    ctx->bvh_ready = false; ctx->shade_ready = false; ctx->fh_ready = false; ctx->matlin_ready = false; ctx->gen++;
+    ctx->bvh_ready = false; ctx->shade_ready = false; ctx->fh_ready = false; ctx->matlin_ready = false; ctx->matspec_ready = false; ctx->gen++;
     return TR_OK;
 }
 
@@ -125,7 +127,7 @@ int tr_material_upload(tr_ctx* ctx, const float* material, int nm) {
     TR_CUDA(ctx, cudaSetDevice(ctx->device));
     TR_CUDA(ctx, cudaMemcpyAsync(ctx->d_material, material, (size_t)nm * 10 * 4, cudaMemcpyHostToDevice, ctx->stream));
     TR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->matlin_ready = false;
+    ctx->matlin_ready = false; ctx->matspec_ready = false;
     return TR_OK;
 }
 

@@ -7,6 +7,7 @@
 #include <vector>
 #include <unordered_map>
 #include "../../include/tiray.h"
+#include "spectral.cuh"
 
 #define TR_MAX_DEPTH_CAP 64       // counters are sized for this many wavefront stages
 #define TR_MAX_CHAINS 8           // independent wavefront chains per batch (parallel graph branches)
@@ -100,6 +101,13 @@ struct tr_ctx {
     float4* d_matlin = nullptr; bool matlin_ready = false;
     cudaStream_t sub_stream[TR_MAX_CHAINS] = {}; cudaEvent_t ev_join[TR_MAX_CHAINS] = {}; cudaEvent_t ev_fork = nullptr;
 
+    // spectral integrator tables (PT_Spec): device copies + the view handed to the kernels
+    SpecDev spec = {};
+    float4* d_sensor = nullptr; float* d_spectrum[4] = {nullptr, nullptr, nullptr, nullptr};
+    float* d_rs_scale = nullptr; float* d_rs_data = nullptr; int rs_res = 0;
+    float* d_sky = nullptr; float4* d_matspec = nullptr; bool matspec_ready = false;
+    float* d_white_point = nullptr;
+
     // options
     int opt_batch_frames = 0;       // 0 = auto
     int opt_stage_timing = 0;
@@ -111,7 +119,7 @@ struct tr_ctx {
     size_t opt_max_paths = (size_t)20 << 20;   // path slots per batch (188 B each): more paths in flight amortise the per-stage tails
 
     // cuda graph cache for the batch pipeline
-    cudaGraphExec_t graph_exec = nullptr; int graph_launches = 0, graph_depth = 0, graph_chains = 0, graph_fs = 0;
+    cudaGraphExec_t graph_exec = nullptr; int graph_launches = 0, graph_depth = 0, graph_chains = 0, graph_fs = 0, graph_spec = 0;
     std::vector<char> graph_args;
     unsigned long long gen = 0, graph_gen = 0;   // any state change bumps gen; a captured graph is valid for one gen
     void* d_batch_params = nullptr;
@@ -150,3 +158,4 @@ template <typename T> static inline int tr_realloc(tr_ctx* ctx, T** p, size_t co
 // implemented across the .cu files
 int tr_build_shade_table(tr_ctx* ctx);
 int tr_build_tiles(tr_ctx* ctx);
+int tr_spec_prepare(tr_ctx* ctx);      // spectral.cu: checks the PT_Spec tables and builds the per-material coefficient table

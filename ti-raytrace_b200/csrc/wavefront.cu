@@ -15,6 +15,7 @@
 #include "ctx.h"
 #include "common.cuh"
 #include "trace.cuh"
+#include "spectral.cuh"
 
 #define WF_THREADS 256
 #define SPEC_BIT 0x80000000u
@@ -41,6 +42,7 @@ struct WfArgs {
     int tail_max;                                  // hand the chain to k_tail once its live paths drop to this (0 = never)
     int frame_off, sub_frames;                     // this chain renders local frames [frame_off, frame_off + sub_frames) of the batch
     unsigned smem_nodes_bytes, smem_leaves_bytes, smem_next_bytes;
+    SpecDev spec;                                  // tables of the spectral integrator (PT_Spec), zero for PT_RGB
 };
 
 // local pixel slot p -> pixel coordinates.  32x32 tiles, inside a tile 4(x) x 8(y) pixel blocks per warp
@@ -80,6 +82,9 @@ __device__ __forceinline__ bool tail_took_over(const WfArgs& a, int depth) {
 }
 
 // ------------------------------------------------------------------ generate
+// SPEC (PT_Spec): B.z carries the pixel id (brdf_pdf / perfect_spec are unused there: the emitter term is never MIS
+// weighted, integrator/PT_Spec.py:219-231) and C the four hero-wavelength throughputs.
+template <bool SPEC>
 __global__ void __launch_bounds__(WF_THREADS) k_generate(WfArgs a) {
     const BatchParams bp = *a.bp;
     const int nf = max(0, min(a.sub_frames, bp.n_frames - a.frame_off));
@@ -103,8 +108,13 @@ __global__ void __launch_bounds__(WF_THREADS) k_generate(WfArgs a) {
             if (frame != 0) { float4 r = rng4(bp.seed, pix, (unsigned)frame, 0u); jx = r.x - 0.5f; jy = r.y - 0.5f; }
             V3 d = camera_dir(a.cam, x, y, jx, jy);
             a.pa[0][q] = make_float4(a.cam.eye[0], a.cam.eye[1], a.cam.eye[2], d.x);
-            a.pb[0][q] = make_float4(d.y, d.z, 1.0f, __uint_as_float((unsigned)s | SPEC_BIT));
-            a.pc[0][q] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(pix));
+            if (SPEC) {
+                a.pb[0][q] = make_float4(d.y, d.z, __uint_as_float(pix), __uint_as_float((unsigned)s | SPEC_BIT));
+                a.pc[0][q] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+            } else {
+                a.pb[0][q] = make_float4(d.y, d.z, 1.0f, __uint_as_float((unsigned)s | SPEC_BIT));
+                a.pc[0][q] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(pix));
+            }
         }
     }
 }
@@ -437,10 +447,100 @@ __device__ __forceinline__ void shade_path(const WfArgs& a, const BatchParams& b
     }
 }
 
+
+// One path vertex of PT_Spec.PathTrace.render (integrator/PT_Spec.py:203-277), four hero wavelengths per path.
+// Queue record: B.z = pixel id, C = throughput of the four lanes; the hero wavelength is recomputed from the
+// counter-based RNG (block 0, .z) instead of being stored.  RNG blocks: 1+2d = (light index, a, b, lobe / Fresnel
+// coin), 2+2d = (r1, r2, hero index of the glass bounce, -).
+__device__ __forceinline__ void shade_path_spec(const WfArgs& a, const BatchParams& bp, int depth, int cl,
+                                                float4 A, float4 B, float4 C, float4 Hh, ShadeOut& out) {
+    out.cont = false; out.shadow = false;
+    const SpecDev& sd = a.spec;
+    const bool last = depth + 1 >= bp.max_depth;
+    V3 o = mk3(A.x, A.y, A.z), d = mk3(A.w, B.x, B.y);
+    unsigned pix = __float_as_uint(B.z);
+    unsigned slot = __float_as_uint(B.w) & ~SPEC_BIT;
+    V4 T = ld4(C);
+    unsigned frame = (unsigned)bp.frame_begin + slot / (unsigned)a.npix;
+    float Lambda = HERO_LAMBDA_MIN + HERO_STEP * rng4(bp.seed, pix, frame, 0u).z;       // :191
+    V4 light_rad = hero_sample(sd.sp[TR_SPEC_D65], Lambda);                                // :217
+    float t = Hh.x; int prim = __float_as_int(Hh.y);
+    if (prim < 0) {
+        // miss: sky dome (:269-276)
+        float dis = sqrtf(d.x * d.x + d.z * d.z);
+        float beta = atan2f(d.y, dis);
+        float gamma = acosf(dot3(d, mk3(__ldg(sd.sky + 110), __ldg(sd.sky + 111), __ldg(sd.sky + 112))));
+        float theta = clampf(0.5f * TR_PI_ENV - beta, 0.0f, 0.5f * TR_PI_ENV);
+        V4 ibl;
+#pragma unroll
+        for (int k = 0; k < HERO_N; ++k) ibl.v[k] = sky_radiance(sd, theta, gamma, Lambda + (float)k * HERO_STEP);
+        a.L[slot] = st4(ld4(a.L[slot]) + (T * ibl) * light_rad);
+        return;
+    }
+    Surf s = surface_at(a, prim, Hh.z, Hh.w, o, d, t);
+    V3 fn = signf_(dot3(-d, s.gn)) * s.n;
+    const float* m = a.material + (size_t)s.mat * 10;
+    float p0 = __ldg(m + 5), p1 = __ldg(m + 6);
+    V4 light_tint = emission_to_rad(sd, s.mat, Lambda);                                   // :218 (the SHADED surface's colour)
+    if (cl == 0) {
+        // emitter: perfect_spec is reset to 1 every bounce (:219), so the term is never MIS weighted (:222-231)
+        float fCos = dot3(d, s.n);
+        if (fCos < 0.0f) a.L[slot] = st4(ld4(a.L[slot]) + (T * light_rad) * light_tint);
+        return;
+    }
+    V4 reflect_spec = get_spec_power(sd, s.mat, Lambda);                                  // :236
+    float4 R0 = rng4(bp.seed, pix, frame, 1u + 2u * (unsigned)depth);
+    float4 R1 = rng4(bp.seed, pix, frame, 2u + 2u * (unsigned)depth);
+    V3 next_d; float f_or_b = 1.0f, brdf, pdf;
+    if (cl == 2) {
+        int index = (int)(R1.z * (float)HERO_N);                                          // Hero.get_rnd_hero (spectrum/HeroSample.py:33-36)
+        float rl = Lambda + (float)index * HERO_STEP;
+        next_d = glass_sample(d, s.n, get_glass_ior(rl), R0.w, f_or_b);                   // Glass.sample_lambda (brdf/Glass.py:39-65)
+        brdf = 1.0f; pdf = 1.0f;
+    } else {
+        if (a.nl > 0) {
+            LightSample ls = sample_li(a, s.pos, R0.x, R0.y, R0.z);
+            float NdotL_s = dot3(fn, ls.dir), NdotL_l = dot3(ls.normal, ls.dir);
+            if (NdotL_s < 0.0f && NdotL_l > 0.0f) {
+                float b2, p2; disney_evaluate_pdf(fn, -d, -ls.dir, p0, p1, b2, p2);
+                V4 c = mk4(0.0f);
+                if (p2 > 0.0f) {
+                    float light_pdf = ls.dist * ls.dist * ls.choice_pdf / NdotL_l;
+                    float wgt = power_heuristic(light_pdf, p2) / fmaxf(0.0001f, light_pdf);
+                    c = (((((wgt * light_rad) * light_tint) * T) * reflect_spec) * b2) * fabsf(NdotL_s);     // :257
+                }
+                out.shadow = true;
+                out.sA = make_float4(ls.pos.x, ls.pos.y, ls.pos.z, ls.dir.x);
+                out.sB = make_float4(ls.dir.y, ls.dir.z, __int_as_float(prim), __uint_as_float(slot));
+                out.sC = st4(c);
+            }
+        }
+        next_d = disney_sample(d, fn, p0, p1, R0.w, R1.x, R1.y);
+        disney_evaluate_pdf(fn, next_d, -d, p0, p1, brdf, pdf);                           // (N, next_dir, -direction) (:260)
+        brdf *= fabsf(dot3(s.n, next_d));
+    }
+    V3 next_o = offset_ray(s.pos, signf_(f_or_b) * fn);
+    float maxc = fmaxf(T.v[2], fmaxf(T.v[0], T.v[1]));                                    // UF.max_component ignores the 4th lane (UtilsFunc.py:487-488)
+    if (pdf > 0.0f && maxc > 0.0f && !last) {
+        T = T * ((brdf * reflect_spec) / pdf);
+        out.cont = true;
+        out.nA = make_float4(next_o.x, next_o.y, next_o.z, next_d.x);
+        out.nB = make_float4(next_d.y, next_d.z, __uint_as_float(pix), __uint_as_float(slot | SPEC_BIT));
+        out.nC = st4(T);
+    }
+}
+
+template <bool SPEC>
+__device__ __forceinline__ void shade_any(const WfArgs& a, const BatchParams& bp, int depth, int cl,
+                                          float4 A, float4 B, float4 C, float4 Hh, ShadeOut& out) {
+    if (SPEC) shade_path_spec(a, bp, depth, cl, A, B, C, Hh, out); else shade_path(a, bp, depth, cl, A, B, C, Hh, out);
+}
+
 #ifndef WF_SHADE_MIN_BLOCKS
 #define WF_SHADE_MIN_BLOCKS 4
 #endif
-__global__ void __launch_bounds__(WF_THREADS, WF_SHADE_MIN_BLOCKS) k_shade(WfArgs a, int depth) {
+template <bool SPEC>
+__global__ void __launch_bounds__(WF_THREADS, SPEC ? 3 : WF_SHADE_MIN_BLOCKS) k_shade(WfArgs a, int depth) {
     if (tail_took_over(a, depth)) return;
     const BatchParams bp = *a.bp;
     const int n0 = a.ctr->ncls[depth][0], n1 = a.ctr->ncls[depth][1], n2 = a.ctr->ncls[depth][2];
@@ -453,7 +553,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_SHADE_MIN_BLOCKS) k_shade(WfArg
         if (w < n) {
             int cl = (w < n0) ? 0 : (w < n0 + n1 ? 1 : 2);
             int q = a.cls[(size_t)cl * a.cap + (w - (cl == 0 ? 0 : (cl == 1 ? n0 : n0 + n1)))];
-            shade_path(a, bp, depth, cl, a.pa[pp][q], a.pb[pp][q], a.pc[pp][q], a.hit[q], o);
+            shade_any<SPEC>(a, bp, depth, cl, a.pa[pp][q], a.pb[pp][q], a.pc[pp][q], a.hit[q], o);
         }
         int qn = warp_append(&a.ctr->nq[depth + 1], o.cont);
         if (o.cont) { a.pa[np_][qn] = o.nA; a.pb[np_][qn] = o.nB; a.pc[np_][qn] = o.nC; }
@@ -479,7 +579,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_SHADE_MIN_BLOCKS) k_shade(WfArg
 // shadow ray, next bounce, all in registers.  Same device functions, same per-path operation order (NEE terms are added
 // to Lnee in depth order, after shadow(depth-1) of the wavefront: the kernel is enqueued behind it), so the film is
 // bit-identical with or without the hand-over.
-template <bool SMEM>
+template <bool SMEM, bool SPEC>
 __global__ void __launch_bounds__(WF_THREADS) k_tail(WfArgs a, int depth) {
     if (a.ctr->tail_from != depth) return;
     const TrNode* nodes; const TrLeaf* leaves; const TrNodeX* nodesx;
@@ -506,7 +606,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_tail(WfArgs a, int depth) {
                     int mt = (int)__ldg(a.material + (size_t)h.mat * 10);
                     cl = (mt == TR_MAT_LIGHT) ? 0 : (mt == TR_MAT_GLASS ? 2 : 1);
                 }
-                shade_path(a, bp, d, cl, A, B, C, make_float4(h.t, __int_as_float(h.prim), h.u, h.v), o);
+                shade_any<SPEC>(a, bp, d, cl, A, B, C, make_float4(h.t, __int_as_float(h.prim), h.u, h.v), o);
             }
             const bool sh = alive && o.shadow;
             if (__ballot_sync(0xffffffffu, sh) != 0u) {
@@ -515,7 +615,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_tail(WfArgs a, int depth) {
                 bool vis = trace_shadow_visible<SMEM>(nodes, leaves, nodesx, a.nnodes, rs, sh, tleaf, a.ctr->visits + 2);
                 if (sh) {
                     ++n_shadow;
-                    if (vis) { unsigned slot = __float_as_uint(o.sB.w); float4 Lv = a.Lnee[slot]; Lv.x += o.sC.x; Lv.y += o.sC.y; Lv.z += o.sC.z; a.Lnee[slot] = Lv; }
+                    if (vis) { unsigned slot = __float_as_uint(o.sB.w); float4 Lv = a.Lnee[slot]; Lv.x += o.sC.x; Lv.y += o.sC.y; Lv.z += o.sC.z; Lv.w += o.sC.w; a.Lnee[slot] = Lv; }
                 }
             }
             alive = alive && o.cont;
@@ -600,7 +700,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_shadow(WfArgs a, int depth) {
         if ((finm >> lane) & 1u) {
             if (visible && found) {
                 float4 C = a.sc[depth & 1][q];
-                float4 Lv = a.Lnee[slot]; Lv.x += C.x; Lv.y += C.y; Lv.z += C.z; a.Lnee[slot] = Lv;
+                float4 Lv = a.Lnee[slot]; Lv.x += C.x; Lv.y += C.y; Lv.z += C.z; Lv.w += C.w; a.Lnee[slot] = Lv;   // .w: 4th hero lane (0 for PT_RGB)
             }
         }
         idle |= finm;
@@ -611,6 +711,8 @@ __global__ void __launch_bounds__(WF_THREADS) k_shadow(WfArgs a, int depth) {
 }
 
 // ------------------------------------------------------------------ accumulate (PT_RGB.py:134-136)
+// SPEC: AddSplat of PT_Spec (integrator/PT_Spec.py:148-165,279-280)
+template <bool SPEC>
 __global__ void __launch_bounds__(WF_THREADS) k_accumulate(WfArgs a) {
     const BatchParams bp = *a.bp;
     const int stride = gridDim.x * blockDim.x;
@@ -624,6 +726,13 @@ __global__ void __launch_bounds__(WF_THREADS) k_accumulate(WfArgs a) {
             float4 Lt = a.L[(size_t)f * a.npix + p], Lv = a.Lnee[(size_t)f * a.npix + p];
             Lv.x += Lt.x; Lv.y += Lt.y; Lv.z += Lt.z;
             float coff = 1.0f / ((float)(bp.frame_begin + f) + 1.0f);
+            if (SPEC) {
+                Lv.w += Lt.w;
+                unsigned pix = ((unsigned)x << 16) | (unsigned)y;
+                float Lambda = HERO_LAMBDA_MIN + HERO_STEP * rng4(bp.seed, pix, (unsigned)(bp.frame_begin + f), 0u).z;
+                add_splat(a.spec, ld4(Lv), Lambda, coff, r, g, b);
+                continue;
+            }
             r = Lv.x * coff + r * (1.0f - coff);
             g = Lv.y * coff + g * (1.0f - coff);
             b = Lv.z * coff + b * (1.0f - coff);
@@ -715,7 +824,7 @@ __global__ void k_matlin(const float* __restrict__ material, int nm, float4* __r
     out[i] = make_float4(c.x, c.y, c.z, 0.0f);
 }
 
-static int fill_args(tr_ctx* ctx, WfArgs& a) {
+static int fill_args(tr_ctx* ctx, WfArgs& a, bool spec = false) {
     if (!ctx->bvh_ready) return tr_fail(ctx, TR_ERR_INVALID, "render: BVH not built (call tr_bvh_build)");
     if (!ctx->cam_set) return tr_fail(ctx, TR_ERR_INVALID, "render: camera not set");
     if (!ctx->d_hdr) return tr_fail(ctx, TR_ERR_INVALID, "render: film not created");
@@ -743,6 +852,7 @@ static int fill_args(tr_ctx* ctx, WfArgs& a) {
     a.smem_nodes_bytes = (unsigned)((size_t)a.nnodes * sizeof(TrNode));
     a.smem_leaves_bytes = (unsigned)((size_t)a.nleaves * sizeof(TrLeaf));
     a.smem_next_bytes = (unsigned)((size_t)a.nnodes * 8 * sizeof(int));
+    if (spec) { if ((rc = tr_spec_prepare(ctx))) return rc; a.spec = ctx->spec; }
     return TR_OK;
 }
 
@@ -769,6 +879,8 @@ static int launch_cfg(tr_ctx* ctx, const WfArgs& a, LaunchCfg& c) {
     if (c.use_smem) {
         TR_CUDA(ctx, cudaFuncSetAttribute(k_trace<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
         TR_CUDA(ctx, cudaFuncSetAttribute(k_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+        TR_CUDA(ctx, cudaFuncSetAttribute(k_tail<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+        TR_CUDA(ctx, cudaFuncSetAttribute(k_tail<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
         TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, k_trace<true>, WF_THREADS, c.smem));
         TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_shadow<true>, WF_THREADS, c.smem));
     } else {
@@ -797,18 +909,19 @@ static WfArgs chain_args(const WfArgs& a, int j, int fs) {
 //   shade(d+2) needs shadow(d) (the shadow queue is a ping-pong pair).
 // So the long tail of a trace stage overlaps the previous depth's shadow rays.  ss == s serialises everything.
 // ev != nullptr (stage timing, single chain, non-graph mode): 4 events per depth bracket trace / shade / shadow.
+template <bool SPEC>
 static int enqueue_chain(tr_ctx* ctx, const WfArgs& a, const LaunchCfg& c, int max_depth, cudaStream_t s, cudaStream_t ss,
                          cudaEvent_t* dep, uint64_t* launches, cudaEvent_t* ev) {
     const bool split = (ss != s);
     TR_CUDA(ctx, cudaMemsetAsync(a.ctr, 0, sizeof(TrCounters), s));
-    k_generate<<<c.grid_simple, WF_THREADS, 0, s>>>(a); ++*launches;
+    k_generate<SPEC><<<c.grid_simple, WF_THREADS, 0, s>>>(a); ++*launches;
     for (int d = 0; d < max_depth; ++d) {
         if (ev) cudaEventRecord(ev[4 * d + 0], s);
         if (c.use_smem) k_trace<true><<<c.grid_trace, WF_THREADS, c.smem, s>>>(a, d);
         else k_trace<false><<<c.grid_trace, WF_THREADS, 0, s>>>(a, d);
         if (ev) cudaEventRecord(ev[4 * d + 1], s);
         if (split && d >= 2) TR_CUDA(ctx, cudaStreamWaitEvent(s, dep[2 * (d - 2) + 1], 0));
-        k_shade<<<c.grid_simple, WF_THREADS, 0, s>>>(a, d);
+        k_shade<SPEC><<<c.grid_simple, WF_THREADS, 0, s>>>(a, d);
         if (ev) cudaEventRecord(ev[4 * d + 2], s);
         if (a.nl > 0) {
             if (split) { TR_CUDA(ctx, cudaEventRecord(dep[2 * d], s)); TR_CUDA(ctx, cudaStreamWaitEvent(ss, dep[2 * d], 0)); }
@@ -820,8 +933,8 @@ static int enqueue_chain(tr_ctx* ctx, const WfArgs& a, const LaunchCfg& c, int m
         if (a.tail_max > 0 && d + 1 < max_depth) {
             // behind shadow(d) on the same stream: NEE terms stay in depth order; shade(d) (the hand-over decision) is done
             if (split && a.nl == 0) { TR_CUDA(ctx, cudaEventRecord(dep[2 * d], s)); TR_CUDA(ctx, cudaStreamWaitEvent(ss, dep[2 * d], 0)); }
-            if (c.use_smem) k_tail<true><<<c.grid_trace, WF_THREADS, c.smem, ss>>>(a, d + 1);
-            else k_tail<false><<<c.grid_trace, WF_THREADS, 0, ss>>>(a, d + 1);
+            if (c.use_smem) k_tail<true, SPEC><<<c.grid_trace, WF_THREADS, c.smem, ss>>>(a, d + 1);
+            else k_tail<false, SPEC><<<c.grid_trace, WF_THREADS, 0, ss>>>(a, d + 1);
             ++*launches;
         }
         if (ev) cudaEventRecord(ev[4 * d + 3], s);
@@ -838,6 +951,7 @@ static int enqueue_chain(tr_ctx* ctx, const WfArgs& a, const LaunchCfg& c, int m
 // The launch sequence of one batch (captured into a CUDA graph when opt_graph is on): K independent chains over
 // disjoint frame ranges run as parallel branches, so the tail of one chain's stage (a few slow rays) overlaps the
 // next stage of another chain; the frame-ordered running mean (k_accumulate) joins them.
+template <bool SPEC>
 static int enqueue_batch(tr_ctx* ctx, const WfArgs& a, const LaunchCfg& c, int max_depth, int K, int fs, cudaStream_t s,
                          uint64_t* launches, cudaEvent_t* ev) {
     int rc;
@@ -849,23 +963,25 @@ static int enqueue_batch(tr_ctx* ctx, const WfArgs& a, const LaunchCfg& c, int m
         WfArgs cj = chain_args(a, j, fs);
         cudaStream_t sj = (j == 0) ? s : ctx->sub_stream[j];
         cudaStream_t ssj = (ev || !ctx->opt_shadow_overlap) ? sj : ctx->shadow_stream[j];
-        if ((rc = enqueue_chain(ctx, cj, c, max_depth, sj, ssj, ctx->dep_ev.data() + (size_t)j * 2 * (TR_MAX_DEPTH_CAP + 1), launches, K == 1 ? ev : nullptr))) return rc;
+        if ((rc = enqueue_chain<SPEC>(ctx, cj, c, max_depth, sj, ssj, ctx->dep_ev.data() + (size_t)j * 2 * (TR_MAX_DEPTH_CAP + 1), launches, K == 1 ? ev : nullptr))) return rc;
     }
     for (int j = 1; j < K; ++j) {
         TR_CUDA(ctx, cudaEventRecord(ctx->ev_join[j], ctx->sub_stream[j]));
         TR_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join[j], 0));
     }
-    k_accumulate<<<c.grid_simple, WF_THREADS, 0, s>>>(a); ++*launches;
+    k_accumulate<SPEC><<<c.grid_simple, WF_THREADS, 0, s>>>(a); ++*launches;
     TR_CHECK_LAUNCH(ctx);
     return TR_OK;
 }
 
-extern "C" int tr_render_pt_rgb(tr_ctx* ctx, int frame_begin, int n_frames, int max_depth, uint64_t seed) {
+// the wavefront driver shared by PT_RGB (SPEC = false) and PT_Spec (SPEC = true)
+template <bool SPEC>
+static int render_wavefront(tr_ctx* ctx, int frame_begin, int n_frames, int max_depth, uint64_t seed) {
     if (!ctx || n_frames <= 0 || frame_begin < 0 || max_depth <= 0 || max_depth > TR_MAX_DEPTH_CAP)
-        return tr_fail(ctx, TR_ERR_INVALID, "tr_render_pt_rgb: bad arguments (frames %d+%d, depth %d)", frame_begin, n_frames, max_depth);
+        return tr_fail(ctx, TR_ERR_INVALID, "%s: bad arguments (frames %d+%d, depth %d)", SPEC ? "tr_render_pt_spec" : "tr_render_pt_rgb", frame_begin, n_frames, max_depth);
     TR_CUDA(ctx, cudaSetDevice(ctx->device));
     WfArgs a; int rc;
-    if ((rc = fill_args(ctx, a))) return rc;
+    if ((rc = fill_args(ctx, a, SPEC))) return rc;
     if (a.npix == 0) { ctx->stats.frames = n_frames; return TR_OK; }    // this rank owns no tile
     // frames per batch: enough paths in flight to fill the chip a few times, bounded by max_paths
     int F = ctx->opt_batch_frames;
@@ -877,7 +993,7 @@ extern "C" int tr_render_pt_rgb(tr_ctx* ctx, int frame_begin, int n_frames, int 
     if (K < 1) K = 1; if (K > TR_MAX_CHAINS) K = TR_MAX_CHAINS; if (K > F) K = F;
     const int fs = (F + K - 1) / K;                                   // frames per chain
     if ((rc = ensure_wavefront(ctx, (size_t)fs * K * a.npix))) return rc;
-    if ((rc = fill_args(ctx, a))) return rc;
+    if ((rc = fill_args(ctx, a, SPEC))) return rc;
     LaunchCfg cfg; memset(&cfg, 0, sizeof(cfg)); if ((rc = launch_cfg(ctx, a, cfg))) return rc;
     cudaStream_t s = ctx->stream;
     if (ctx->dep_ev.empty()) {
@@ -905,26 +1021,26 @@ extern "C" int tr_render_pt_rgb(tr_ctx* ctx, int frame_begin, int n_frames, int 
         TR_CUDA(ctx, cudaMemcpyAsync(ctx->d_batch_params, &bp, sizeof(bp), cudaMemcpyHostToDevice, s));
         if (ctx->opt_graph && !timing) {
             // a captured graph stays valid as long as the kernel arguments it baked in are unchanged
-            if (!ctx->graph_exec || ctx->graph_depth != max_depth || ctx->graph_chains != K || ctx->graph_fs != fs ||
+            if (!ctx->graph_exec || ctx->graph_spec != (int)SPEC || ctx->graph_depth != max_depth || ctx->graph_chains != K || ctx->graph_fs != fs ||
                 ctx->graph_args.size() != sizeof(WfArgs) + sizeof(LaunchCfg) || memcmp(ctx->graph_args.data(), &a, sizeof(WfArgs)) != 0 ||
                 memcmp(ctx->graph_args.data() + sizeof(WfArgs), &cfg, sizeof(LaunchCfg)) != 0) {
                 if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
                 cudaGraph_t g; uint64_t l2 = 0;
                 TR_CUDA(ctx, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-                rc = enqueue_batch(ctx, a, cfg, max_depth, K, fs, s, &l2, nullptr);
+                rc = enqueue_batch<SPEC>(ctx, a, cfg, max_depth, K, fs, s, &l2, nullptr);
                 cudaError_t e = cudaStreamEndCapture(s, &g);
                 if (rc) return rc;
                 if (e != cudaSuccess) return tr_fail(ctx, TR_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
                 TR_CUDA(ctx, cudaGraphInstantiate(&ctx->graph_exec, g, 0));
                 cudaGraphDestroy(g);
-                ctx->graph_depth = max_depth; ctx->graph_launches = (int)l2; ctx->graph_gen = ctx->gen; ctx->graph_chains = K; ctx->graph_fs = fs;
+                ctx->graph_depth = max_depth; ctx->graph_launches = (int)l2; ctx->graph_gen = ctx->gen; ctx->graph_chains = K; ctx->graph_fs = fs; ctx->graph_spec = (int)SPEC;
                 ctx->graph_args.resize(sizeof(WfArgs) + sizeof(LaunchCfg));
                 memcpy(ctx->graph_args.data(), &a, sizeof(WfArgs)); memcpy(ctx->graph_args.data() + sizeof(WfArgs), &cfg, sizeof(LaunchCfg));
             }
             TR_CUDA(ctx, cudaGraphLaunch(ctx->graph_exec, s));
             launches += (uint64_t)ctx->graph_launches;
         } else {
-            if ((rc = enqueue_batch(ctx, a, cfg, max_depth, K, fs, s, &launches, timing ? ctx->stage_ev.data() : nullptr))) return rc;
+            if ((rc = enqueue_batch<SPEC>(ctx, a, cfg, max_depth, K, fs, s, &launches, timing ? ctx->stage_ev.data() : nullptr))) return rc;
         }
         // ray counters of this batch = queue sizes (device counters)
         TR_CUDA(ctx, cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(TrCounters) * K, cudaMemcpyDeviceToHost, s));
@@ -949,6 +1065,13 @@ extern "C" int tr_render_pt_rgb(tr_ctx* ctx, int frame_begin, int n_frames, int 
     ctx->stats.kernel_launches = launches; ctx->stats.ms_total = ms; ctx->stats.frames = n_frames; ctx->stats.paths_in_flight = (int)((size_t)F * a.npix); ctx->stats.chains = K;
     ctx->stats.ms_trace = ms_trace; ctx->stats.ms_shade = ms_shade; ctx->stats.ms_shadow = ms_shadow;
     return TR_OK;
+}
+
+extern "C" int tr_render_pt_rgb(tr_ctx* ctx, int frame_begin, int n_frames, int max_depth, uint64_t seed) {
+    return render_wavefront<false>(ctx, frame_begin, n_frames, max_depth, seed);
+}
+extern "C" int tr_render_pt_spec(tr_ctx* ctx, int frame_begin, int n_frames, int max_depth, uint64_t seed) {
+    return render_wavefront<true>(ctx, frame_begin, n_frames, max_depth, seed);
 }
 
 extern "C" int tr_render_debug(tr_ctx* ctx) {
