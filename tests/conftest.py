@@ -33,14 +33,16 @@ def oracle_tables():
     from oracle import objload
     cache = {}
 
-    def get(name, sphere_light=False, glass0=False, spectral_walls=False):
-        key = (name, sphere_light, glass0, spectral_walls)
+    def get(name, sphere_light=False, glass0=False, spectral_walls=False, mirror0=False):
+        key = (name, sphere_light, glass0, spectral_walls, mirror0)
         if key not in cache:
             shapes = [objload.sphere_light_rows()] if sphere_light else []
 
             def edit(mats):
                 if glass0:
                     mats[0][0] = 1.0; mats[0][5] = 1.3; mats[0][6] = 5.0
+                if mirror0:                              # example/sky_dome.py:18-19
+                    mats[0][5] = 1.0; mats[0][6] = 0.0
                 if spectral_walls:                       # example/spectral_box.py:22-27
                     for k in range(3):
                         mats[k][0] = 10.0; mats[k][1] = float(k)
@@ -49,7 +51,7 @@ def oracle_tables():
     return get
 
 
-def make_product_scene(name, sphere_light=False, glass0=False, env_power=0.0, spectral_walls=False):
+def make_product_scene(name, sphere_light=False, glass0=False, env_power=0.0, spectral_walls=False, mirror0=False):
     """product-side Scene (host packing only; no device calls)"""
     import Scene
     import SceneData as SCD
@@ -58,6 +60,8 @@ def make_product_scene(name, sphere_light=False, glass0=False, env_power=0.0, sp
         s.add_obj("model/" + f)
     if glass0:
         m = s.material_cpu[0]; m.type = SCD.MAT_GLASS; m.setIor(1.3); m.setExtinciton(5.0)
+    if mirror0:
+        s.material_cpu[0].setMetal(1.0); s.material_cpu[0].setRough(0.0)
     if spectral_walls:
         for k in range(3):
             s.material_cpu[k].type = SCD.MAT_SPECTRAL; s.material_cpu[k].alebdoTex = k

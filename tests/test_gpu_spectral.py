@@ -9,7 +9,7 @@ import pytest
 from conftest import PKG, GOLDEN, make_product_scene
 from oracle import oracle, spectral
 from test_gpu_parity import _compare_radiance
-from test_spectral_cpu import spectral_oracle
+from test_spectral_cpu import spectral_oracle, sky_dome_oracle, srgb8_of
 
 pytestmark = pytest.mark.gpu
 
@@ -215,6 +215,29 @@ def test_pt_spec_full_size_vs_oracle(gpu_ctx, oracle_tables):
         pa = hdr[x0:x1, y0:y1].reshape(-1, 3).mean(0); pa = pa / pa.sum()
         pb = ref[x0:x1, y0:y1].reshape(-1, 3).mean(0); pb = pb / pb.sum()
         assert np.abs(pa - pb).max() < 0.06, (name, pa, pb)
+
+
+def test_sky_dome_example_matches_oracle_and_reference_image(gpu_ctx, oracle_tables):
+    """example/sky_dome.py through the product's example class: film == oracle at 128^2; at the reference's own size
+    (512^2) the tone-mapped image reproduces the reference's render image/skydome.png (means within 2 %, PSNR > 30 dB)"""
+    import cv2, sky_dome
+    import UtilsFunc as UF
+    ex = sky_dome.example(128, 128, 64); ex.build_scene()
+    ex.integrator.render_frames(8)
+    g = ex.integrator.hdr.to_numpy()
+    o = sky_dome_oracle(oracle_tables, 128, 128)
+    ref, cnt = spectral.render_pt_spec(o, 128, 128, 0, 8)
+    frac_bad, mean_err = _compare_radiance(g, ref, rel=2e-3, outlier_budget=5e-3, floor=0.05)
+    assert frac_bad < 5e-3 and mean_err < 2e-3, (frac_bad, mean_err)
+    ex = sky_dome.example(512, 512, 64); ex.build_scene()
+    ex.integrator.render_frames(256)
+    UF.tone_map(0.5, ex.integrator.hdr, ex.integrator.rgb_film)
+    rgb = ex.integrator.rgb_film.to_numpy()
+    out = (np.clip(rgb, 0, 1) * 255 + 0.5).astype(np.uint8).swapaxes(0, 1)[::-1].astype(np.float32)
+    img = cv2.imread(os.path.join(GOLDEN, "skydome.png"))[:, :, ::-1].astype(np.float32)
+    assert np.abs(out.mean((0, 1)) - img.mean((0, 1))).max() < 0.02 * img.mean(), (out.mean((0, 1)), img.mean((0, 1)))
+    mse = float(((out - img) ** 2).mean())
+    assert 10.0 * np.log10(255.0 ** 2 / mse) > 30.0
 
 
 def test_pt_spec_error_paths(gpu_ctx):

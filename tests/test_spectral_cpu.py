@@ -108,6 +108,41 @@ def test_oracle_spectral_box_vs_reference_image(oracle_tables):
     assert 5 <= lightpix.sum() <= 60 and abs(hdr[lightpix][:, 1].mean() - 5.0) < 0.6
 
 
+def sky_dome_oracle(oracle_tables, W, H, fast=False):
+    t = oracle_tables("sphere", sphere_light=True, mirror0=True)
+    o = oracle.OracleScene(t, fast=fast).build()
+    cam = oracle.fit_camera(t, W, H, 2.0)                                   # example/sky_dome.py:33
+    o.set_camera(cam[1], cam[2], *cam[3:])
+    o.process_normal()
+    return spectral.attach(o, PKG)
+
+
+def srgb8_of(hdr, exposure=0.5):
+    """UF.tone_map + ti.imwrite: [x][y] y-up film -> top-down 8-bit RGB image"""
+    img = oracle.tonemap(hdr, exposure)
+    return (np.clip(img, 0, 1) * 255 + 0.5).astype(np.uint8).swapaxes(0, 1)[::-1]
+
+
+def test_oracle_sky_dome_vs_reference_image(oracle_tables):
+    """PIN of the spectral oracle: example/sky_dome.py rendered by the oracle reproduces the reference's own render
+    image/skydome.png (tests/golden): the whole chain D65 normalisation -> Hosek-Wilkie sky -> hero sampling -> CIE
+    observer -> XYZ -> sRGB -> ACES, plus the rgb2spec mirror sphere.  Tone-mapped 8-bit, channel means within 2 %,
+    PSNR > 30 dB against the image box-filtered to the oracle's size."""
+    import cv2
+    W = H = 128
+    o = sky_dome_oracle(oracle_tables, W, H, fast=True)
+    hdr, cnt = spectral.render_pt_spec(o, W, H, 0, 256)
+    assert np.isfinite(hdr).all()
+    out = srgb8_of(hdr).astype(np.float32)
+    ref = cv2.resize(cv2.imread(os.path.join(GOLDEN, "skydome.png")), (W, H), interpolation=cv2.INTER_AREA)[:, :, ::-1].astype(np.float32)
+    assert np.abs(out.mean((0, 1)) - ref.mean((0, 1))).max() < 0.02 * ref.mean(), (out.mean((0, 1)), ref.mean((0, 1)))
+    mse = float(((out - ref) ** 2).mean())
+    psnr = 10.0 * np.log10(255.0 ** 2 / mse)
+    assert psnr > 30.0, psnr
+    # sky gradient: zenith (top rows) bluer than the horizon band, ground (miss with theta clamped) uniform
+    assert np.abs(out[5, 10] - ref[5, 10]).max() <= 4 and np.abs(out[100, 10] - ref[100, 10]).max() <= 4
+
+
 def test_oracle_spectral_determinism_and_frames(oracle_tables):
     """running mean over frames is order-exact: frames 0..3 in one call == four calls"""
     W = H = 32
