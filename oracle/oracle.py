@@ -55,6 +55,9 @@ def _load(fast):
     lib.orc_rng.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _f32p]
     lib.orc_philox_raw.argtypes = [C.c_uint32] * 6 + [_u32p]
     lib.orc_slabs.argtypes = [_f32p, _f32p, _f32p, _f32p]
+    lib.orc_camera_view_set.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int]
+    lib.orc_render_bdpt_rgb.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, _f32p, C.c_void_p, _u64p]
+    lib.orc_bdpt_pixel_dump.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, _f32p, _i32p, _f32p]
     return lib
 
 
@@ -146,6 +149,10 @@ class OracleScene:
         self.lib.orc_camera_set(self.h, np.ascontiguousarray(view_inv, np.float32).reshape(-1),
                                 np.ascontiguousarray(eye, np.float32), fx, fy, cx, cy)
 
+    def set_camera_view(self, view, wid, hgt):
+        """Camera.view / wid / hgt, needed by BDPT (Camera.py:128-129,144-158)"""
+        self.lib.orc_camera_view_set(self.h, np.ascontiguousarray(view, np.float32).reshape(-1), wid, hgt)
+
     def set_env(self, packed, w, h, power):
         self.lib.orc_env_set(self.h, np.ascontiguousarray(packed, np.int32).reshape(-1), w, h, power)
 
@@ -185,6 +192,23 @@ class OracleScene:
         self.lib.orc_render_pt_rgb(self.h, W, H, frame_begin, n_frames, max_depth, seed, hdr.reshape(-1),
                                    m.ctypes.data if m is not None else None, cnt)
         return hdr, dict(closest=int(cnt[0]), shadow=int(cnt[1]), node_visits=int(cnt[2]), leaf_tests=int(cnt[3]))
+
+    def render_bdpt_rgb(self, W, H, frame_begin, n_frames, seed=0, hdr=None, mask=None):
+        if hdr is None:
+            hdr = np.zeros((W, H, 3), np.float32)
+        cnt = np.zeros(4, np.uint64)
+        m = None
+        if mask is not None:
+            m = np.ascontiguousarray(mask, np.uint8).reshape(-1)
+        self.lib.orc_render_bdpt_rgb(self.h, W, H, frame_begin, n_frames, seed, hdr.reshape(-1),
+                                     m.ctypes.data if m is not None else None, cnt)
+        return hdr, dict(closest=int(cnt[0]), shadow=int(cnt[1]))
+
+    def bdpt_pixel_dump(self, i, j, frame, seed=0):
+        """-> verts (13, 20) f32 [eye 0..6, light 0..5], (eye_depth, light_depth), contrib (7, 7, 4) f32 indexed [e-1][l]"""
+        verts = np.zeros((13, 20), np.float32); depths = np.zeros(2, np.int32); contrib = np.zeros((7, 7, 4), np.float32)
+        self.lib.orc_bdpt_pixel_dump(self.h, i, j, frame, seed, verts.reshape(-1), depths, contrib.reshape(-1))
+        return verts, (int(depths[0]), int(depths[1])), contrib
 
     def process_normal(self):
         self.lib.orc_process_normal(self.h)

@@ -118,6 +118,7 @@ struct Scene {
     std::vector<int32_t> env; int env_w = 0, env_h = 0; float env_power = 0.0f;
     // camera (Camera.py)
     float view_inv[16]; float eye[3]; float fx, fy, cx, cy;
+    float view[16] = {0}; int wid = 0, hgt = 0;      // Camera.view / wid / hgt (BDPT: get_image_point, get_optical_axis)
     int stack_size = 64;
     SpecData spec;
     int max_stack_seen = 0; int overflow = 0;
@@ -802,6 +803,7 @@ V3 pt_rgb_pixel(Scene& s, int i, int j, int frame, int max_depth, uint64_t seed,
 }
 
 #include "spec_core.inc"
+#include "bdpt_core.inc"
 
 }  // namespace
 
@@ -1036,5 +1038,6 @@ int orc_num_threads() {
 int orc_slabs(const float* o, const float* d, const float* mn, const float* mx) { return slabs(v3(o[0], o[1], o[2]), v3(d[0], d[1], d[2]), mn, mx); }
 
 #include "spec_api.inc"
+#include "bdpt_api.inc"
 
 }  // extern "C"
