@@ -116,6 +116,13 @@ int tr_render_pt_rgb(tr_ctx* ctx, int frame_begin, int n_frames, int max_depth, 
  * (CIE XYZ -> linear sRGB) as accumulation.  max_depth is the reference's MAX_DEPTH (10).  Requires every
  * tr_spec_*_upload below. */
 int tr_render_pt_spec(tr_ctx* ctx, int frame_begin, int n_frames, int max_depth, uint64_t seed);
+/* replaces BDPT.render (integrator/BDPT_RGB.py:600-641) for frames [frame_begin, frame_begin+n_frames): eye and light
+ * sub-paths (eye_path :104-187, light_path :189-250, Scene.sample_light Scene.py:430-474), every (e, l) connection with
+ * 0 <= e+l-2 <= MAX_DEPTH = 5 (connect_path :436-580, Camera.get_image_point Camera.py:144-158) weighted by mis_weight
+ * (:258-434), light-tracing (e == 1) contributions splatted across pixels, running mean into hdr.  Needs the view matrix of
+ * tr_camera_set and at least one emitter.  With tile sharding every rank's hdr also receives that rank's splats on foreign
+ * pixels, so the film reduce must be a SUM.  Synchronous per batch. */
+int tr_render_bdpt_rgb(tr_ctx* ctx, int frame_begin, int n_frames, uint64_t seed);
 /* replaces Debug.render (integrator/Debug.py:44-66); also fills the first-hit buffers */
 int tr_render_debug(tr_ctx* ctx);
 /* frame-0 primary rays and first hits, index [x*H+y]; any pointer may be NULL */
@@ -157,6 +164,11 @@ int tr_test_rng(tr_ctx* ctx, uint64_t seed, uint32_t pixel, uint32_t frame, uint
 /* arbitrary rays through the traversal kernels; shadow != 0 uses the nearest-hit shadow query */
 int tr_test_trace(tr_ctx* ctx, int n, const float* o, const float* d, int shadow,
                   float* t, int32_t* prim, float* uv /* n x 2 or NULL */);
+
+/* BDPT internals of the last tr_render_bdpt_rgb batch (its first frame) for n pixels: verts n x 13 x 20 f32 (eye 0..6, light
+ * 0..5; pos3 normal3 snormal3 beta3 wo3 fpdf rpdf type+16*delta prim mat, zero beyond the sub-path depth), depths n x 2 i32,
+ * contrib n x 7 x 7 x 4 f32 indexed [e-1][l] (MIS-weighted radiance of each e >= 2 strategy; e == 1 rows are splats, not kept) */
+int tr_test_bdpt_dump(tr_ctx* ctx, int n, const int32_t* px, const int32_t* py, float* verts, int32_t* depths, float* contrib);
 
 /* spectral device functions: Hero.srgb_to_spec (spectrum/HeroSample.py:46-57) for n (srgb, hero wavelength) pairs;
  * Sky.get_solar_radiance (sky/Sky.py:258-265); Spectrum.sample (spectrum/Spectrum.py:43-51) of table `which`, or

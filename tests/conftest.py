@@ -24,6 +24,7 @@ SCENES = {
     "sphere": dict(files=["sphere.obj"]),
     "teapot": dict(files=["Teapot.obj"]),
     "teapot_mc": dict(files=["mc.obj", "Teapot.obj"]),
+    "veach": dict(files=["bdpt.obj"]),
 }
 
 

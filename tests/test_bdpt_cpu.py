@@ -1,0 +1,80 @@
+"""CPU tests of the BDPT oracle (oracle/bdpt_core.inc): pinned against the reference's own render of example/veach_bdpt.py
+(image/veach-bdpt512.png -> tests/golden), plus internal consistency of the per-pixel dump used by the GPU parity tests."""
+import os
+import numpy as np
+import pytest
+from conftest import GOLDEN
+from oracle import oracle
+
+
+def veach_oracle(oracle_tables, W, H, fast):
+    import copy
+    t = copy.copy(oracle_tables("veach"))
+    t.vertex = oracle.OracleScene(oracle_tables("veach"), fast=True).build().process_normal()      # example/veach_bdpt.py:23
+    s = oracle.OracleScene(t, fast=fast).build()
+    cam = oracle.fit_camera(t, W, H, 0.5)                                                           # :27-29
+    s.set_camera(cam[1], cam[2], *cam[3:]); s.set_camera_view(cam[0], W, H)
+    return s
+
+
+def test_veach_scene_tables(oracle_tables):
+    """model/bdpt.obj through the PyWavefront restatement: 11 544 triangles, 6 materials in MTL order
+    (Wall, Wood, Lamp: Disney; Light1, Light2: emitters; Glass: ior 1.5, extinction Ns = 100), 4 emitter triangles"""
+    t = oracle_tables("veach")
+    assert t.primitive.shape[0] == 11544 and t.material.shape[0] == 6 and t.light.size == 4
+    assert list(t.material[:, 0]) == [0.0, 0.0, 0.0, 2.0, 2.0, 1.0]
+    assert t.material[5, 5] == np.float32(1.5) and t.material[5, 6] == np.float32(100.0)
+    assert np.allclose(t.material[3, 2:5], [12048.179, 8605.842, 6196.206])
+
+
+def test_oracle_bdpt_vs_reference_image(oracle_tables):
+    """128 x 128, 24 spp of the oracle against the reference's 512 x 512 render, area-downscaled: channel means within
+    4 %, PSNR of the blurred images > 24 dB (at 256 x 256 x 24 spp: 2 % and 31.9 dB)"""
+    import cv2
+    W = H = 128
+    s = veach_oracle(oracle_tables, W, H, fast=True)
+    hdr, cnt = s.render_bdpt_rgb(W, H, 0, 24)
+    assert np.isfinite(hdr).all()
+    img = (np.clip(oracle.tonemap(hdr, 0.5).swapaxes(0, 1)[::-1], 0, 1) * 255).astype(np.uint8)
+    ref = cv2.resize(cv2.imread(os.path.join(GOLDEN, "veach-bdpt512.png"))[:, :, ::-1], (W, H), interpolation=cv2.INTER_AREA)
+    m, r = img.reshape(-1, 3).mean(0), ref.reshape(-1, 3).mean(0)
+    assert np.all(np.abs(m - r) < 0.04 * r), (m, r)
+    mse = ((cv2.GaussianBlur(img, (5, 5), 0).astype(np.float64) - cv2.GaussianBlur(ref, (5, 5), 0)) ** 2).mean()
+    assert 10 * np.log10(255.0 ** 2 / mse) > 24.0
+    # every sample traces at least its two first segments; connections need one shadow query each (<= 26 per sample)
+    assert 2 * W * H * 24 <= cnt["closest"] <= 11 * W * H * 24 and 0 < cnt["shadow"] <= 26 * W * H * 24
+
+
+def test_oracle_bdpt_dump_reconstructs_frame(oracle_tables):
+    """film of one frame == per pixel: sum of its (e >= 2, l) strategies in loop order + the e == 1 splats aimed at it"""
+    W = H = 24
+    s = veach_oracle(oracle_tables, W, H, fast=False)
+    for frame in (0, 3):
+        hdr, _ = s.render_bdpt_rgb(W, H, frame, 1)
+        hdr = hdr * (frame + 1.0)                             # undo the running-mean weight of a film that started at 0
+        own = np.zeros((W, H, 3), np.float32); spl = np.zeros((W, H, 3), np.float64)
+        for i in range(W):
+            for j in range(H):
+                v, (ed, ld), c = s.bdpt_pixel_dump(i, j, frame)
+                assert 1 <= ed <= 7 and 1 <= ld <= 6
+                acc = np.zeros(3, np.float32)
+                for e in range(2, ed + 1):
+                    for l in range(0, ld + 1):
+                        if l + e - 2 <= 5:
+                            acc = acc + c[e - 1, l, :3]
+                own[i, j] = acc
+                for l in range(2, ld + 1):
+                    if l - 1 <= 5 and c[0, l, 3] >= 0:
+                        pix = int(c[0, l, 3]); spl[pix >> 16, pix & 65535] += c[0, l, :3]
+        assert np.allclose(own + spl, hdr, rtol=1e-4, atol=1e-6)
+
+
+def test_oracle_bdpt_mask_shards_sum(oracle_tables):
+    """masked renders (tile sharding: only the masked pixels trace paths, everybody receives splats) sum to the full film"""
+    W = H = 32
+    s = veach_oracle(oracle_tables, W, H, fast=False)
+    full, _ = s.render_bdpt_rgb(W, H, 0, 2)
+    m = np.zeros((W, H), np.uint8); m[: W // 2] = 1
+    a, _ = s.render_bdpt_rgb(W, H, 0, 2, mask=m)
+    b, _ = s.render_bdpt_rgb(W, H, 0, 2, mask=1 - m)
+    assert np.allclose(a + b, full, rtol=1e-4, atol=1e-6)

@@ -9,12 +9,13 @@ from conftest import ROOT, PKG, make_product_scene
 from oracle import oracle
 
 
-@pytest.mark.parametrize("name", ["cornell", "sphere", "teapot", "teapot_mc"])
+@pytest.mark.parametrize("name", ["cornell", "sphere", "teapot", "teapot_mc", "veach"])
 def test_scene_packing_matches_oracle_loader(oracle_tables, name):
     """two independent ingest implementations (product objio+Scene vs oracle objload) agree bit for bit"""
-    s = make_product_scene(name, sphere_light=(name != "cornell"))
+    sl = name not in ("cornell", "veach")
+    s = make_product_scene(name, sphere_light=sl)
     s.setup_data_cpu()
-    t = oracle_tables(name, sphere_light=(name != "cornell"))
+    t = oracle_tables(name, sphere_light=sl)
     assert np.array_equal(s.vertex_np, t.vertex)
     assert np.array_equal(s.primitive_np, t.primitive)
     assert np.array_equal(s.material_np, t.material)

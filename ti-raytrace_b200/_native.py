@@ -50,6 +50,8 @@ SIGNATURES = {
     "tr_set_shard": (C.c_int, [_vp, C.c_int, C.c_int]),
     "tr_render_pt_rgb": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_uint64]),
     "tr_render_pt_spec": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_uint64]),
+    "tr_render_bdpt_rgb": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint64]),
+    "tr_test_bdpt_dump": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "tr_render_debug": (C.c_int, [_vp]),
     "tr_first_hit_download": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tr_tonemap": (C.c_int, [_vp, C.c_float]),
@@ -210,6 +212,15 @@ class Context:
 
     def render_pt_spec(self, frame_begin, n_frames, max_depth=10, seed=0):
         self._ck(self.lib.tr_render_pt_spec(self.h, int(frame_begin), int(n_frames), int(max_depth), int(seed)), "tr_render_pt_spec")
+
+    def render_bdpt_rgb(self, frame_begin, n_frames, seed=0):
+        self._ck(self.lib.tr_render_bdpt_rgb(self.h, int(frame_begin), int(n_frames), int(seed)), "tr_render_bdpt_rgb")
+
+    def test_bdpt_dump(self, px, py):
+        px = np.ascontiguousarray(px, np.int32); py = np.ascontiguousarray(py, np.int32); n = px.size
+        verts = np.zeros((n, 13, 20), np.float32); depths = np.zeros((n, 2), np.int32); contrib = np.zeros((n, 7, 7, 4), np.float32)
+        self._ck(self.lib.tr_test_bdpt_dump(self.h, n, _ptr(px), _ptr(py), _ptr(verts), _ptr(depths), _ptr(contrib)), "tr_test_bdpt_dump")
+        return verts, depths, contrib
 
     # ---- spectral tables (PT_Spec)
     def spec_sensor_upload(self, xyz, lmin, lmax):

@@ -67,7 +67,8 @@ void tr_ctx_destroy(tr_ctx* ctx) {
                     ctx->d_path[1][1], ctx->d_path[1][2], ctx->d_hit, ctx->d_cls, ctx->d_shq[0][0], ctx->d_shq[0][1],
                     ctx->d_shq[0][2], ctx->d_shq[1][0], ctx->d_shq[1][1], ctx->d_shq[1][2], ctx->d_Lnee, ctx->d_L, ctx->d_ctr, ctx->d_batch_params, ctx->d_matlin, ctx->d_axis, ctx->d_nodesx, ctx->d_smooth,
                     ctx->d_sensor, ctx->d_spectrum[0], ctx->d_spectrum[1], ctx->d_spectrum[2], ctx->d_spectrum[3], ctx->d_rs_scale, ctx->d_rs_data,
-                    ctx->d_sky, ctx->d_matspec, ctx->d_white_point};
+                    ctx->d_sky, ctx->d_matspec, ctx->d_white_point,
+                    ctx->d_bd_vb, ctx->d_bd_depths, ctx->d_bd_contrib, ctx->d_bd_splat, ctx->d_bd_items, ctx->d_bd_tile_slot, ctx->d_bd_ctr};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -144,7 +145,7 @@ int tr_env_upload(tr_ctx* ctx, const int32_t* rgb, int w, int h, float power) {
 int tr_camera_set(tr_ctx* ctx, const float view[16], const float view_inv[16], const float eye[3],
                   float fx, float fy, float cx, float cy) {
     if (!ctx || !view_inv || !eye) return tr_fail(ctx, TR_ERR_INVALID, "tr_camera_set: NULL argument");
-    (void)view;
+    if (view) memcpy(ctx->view, view, 64);
     memcpy(ctx->cam.view_inv, view_inv, 64); memcpy(ctx->cam.eye, eye, 12);
     ctx->cam.fx = fx; ctx->cam.fy = fy; ctx->cam.cx = cx; ctx->cam.cy = cy;
     ctx->cam_set = true; ctx->fh_ready = false; ctx->gen++;
@@ -233,11 +234,13 @@ int tr_build_tiles(tr_ctx* ctx) {
     if (ctx->tiles_ready) return TR_OK;
     if (ctx->W <= 0) return tr_fail(ctx, TR_ERR_INVALID, "film not created");
     int ntx = (ctx->W + TR_TILE - 1) / TR_TILE, nty = (ctx->H + TR_TILE - 1) / TR_TILE;
-    std::vector<int> tiles;
+    std::vector<int> tiles, slot_of((size_t)ntx * nty, -1);      // slot_of: tile -> ordinal in this rank's list (BDPT film pass)
     for (int ty = 0; ty < nty; ++ty) for (int tx = 0; tx < ntx; ++tx)
-        if ((tx + 3 * ty) % ctx->nranks == ctx->rank) tiles.push_back(ty * ntx + tx);
+        if ((tx + 3 * ty) % ctx->nranks == ctx->rank) { slot_of[(size_t)ty * ntx + tx] = (int)tiles.size(); tiles.push_back(ty * ntx + tx); }
     ctx->n_local_tiles = (int)tiles.size();
     int rc; if ((rc = tr_realloc(ctx, &ctx->d_tiles, tiles.size()))) return rc;
+    if ((rc = tr_realloc(ctx, &ctx->d_bd_tile_slot, slot_of.size()))) return rc;
+    TR_CUDA(ctx, cudaMemcpyAsync(ctx->d_bd_tile_slot, slot_of.data(), slot_of.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     if (!tiles.empty()) TR_CUDA(ctx, cudaMemcpyAsync(ctx->d_tiles, tiles.data(), tiles.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     TR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->tiles_ready = true;

@@ -139,6 +139,21 @@ __device__ __forceinline__ void disney_evaluate_pdf(V3 N, V3 V, V3 L, float meta
         pdf = dr * pdfDiff + sr * pdfSpec;
     }
 }
+// brdf/Disney.py:42-63
+__device__ __forceinline__ float disney_pdf(V3 N, V3 V, V3 L, float metal, float rough) {
+    float pdf = 0.0f;
+    float NDotL = dot3(N, L), NDotV = dot3(N, V);
+    if (NDotL > 0.0f && NDotV > 0.0f) {
+        V3 H = normalize3(L + V);
+        float NDotH = dot3(H, N), LDotH = dot3(H, L);
+        float alpha = fmaxf(0.001f, rough);
+        float Ds = gtr2(NDotH, alpha);
+        float dr = 0.5f * (1.0f - metal), sr = 1.0f - dr;
+        float pdfGTR2 = Ds * NDotH, pdfSpec = pdfGTR2 / (4.0f * fabsf(LDotH)), pdfDiff = 1.0f / TR_PI_REF;
+        pdf = dr * pdfDiff + sr * pdfSpec;
+    }
+    return pdf;
+}
 // brdf/Disney.py:17-40 (randoms: lobe probability, r1, r2)
 __device__ __forceinline__ V3 disney_sample(V3 dir, V3 N, float metal, float rough, float prob, float r1, float r2) {
     float dr = 0.5f * (1.0f - metal), alpha = fmaxf(0.001f, rough);

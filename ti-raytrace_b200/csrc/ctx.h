@@ -108,6 +108,12 @@ struct tr_ctx {
     float* d_sky = nullptr; float4* d_matspec = nullptr; bool matspec_ready = false;
     float* d_white_point = nullptr;
 
+    // bidirectional integrator (BDPT_RGB): vertex records, per-strategy contributions, splat film, connection queue
+    float view[16] = {0};                          // Camera.view (get_image_point / get_optical_axis)
+    float4* d_bd_vb = nullptr; int* d_bd_depths = nullptr; float4* d_bd_contrib = nullptr; float* d_bd_splat = nullptr;
+    unsigned* d_bd_items = nullptr; int* d_bd_tile_slot = nullptr; unsigned long long* d_bd_ctr = nullptr;
+    size_t bd_cap = 0; int bd_splat_frames = 0; bool bd_tiles_ready = false;
+
     // options
     int opt_batch_frames = 0;       // 0 = auto
     int opt_stage_timing = 0;

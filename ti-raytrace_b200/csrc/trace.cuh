@@ -192,7 +192,8 @@ __device__ __forceinline__ HitRec trace_closest(const TrNode* __restrict__ nodes
 template <bool SMEM>
 __device__ __forceinline__ bool trace_shadow_visible(const TrNode* __restrict__ nodes, const TrLeaf* __restrict__ leaves,
                                                      const TrNodeX* __restrict__ nodesx, int nnodes,
-                                                     const RayPre& r, bool active, int target_leaf, unsigned long long* cnt) {
+                                                     const RayPre& r, bool active, int target_leaf, unsigned long long* cnt,
+                                                     float* tt_out = nullptr) {
 #ifdef TR_COUNTERS
     unsigned cnt_nodes = 0, cnt_leaves = 0;
 #endif
@@ -236,6 +237,7 @@ __device__ __forceinline__ bool trace_shadow_visible(const TrNode* __restrict__ 
 #ifdef TR_COUNTERS
     if (cnt && active) { atomicAdd(cnt, (unsigned long long)cnt_nodes); atomicAdd(cnt + 1, (unsigned long long)cnt_leaves); }
 #endif
+    if (tt_out) *tt_out = tt;          // distance to the target primitive = the reference's hit_t when the target is the nearest hit
     return visible && found;
 }
 

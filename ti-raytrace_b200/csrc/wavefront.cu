@@ -1163,3 +1163,5 @@ extern "C" int tr_test_trace(tr_ctx* ctx, int n, const float* o, const float* d,
     TR_CHECK_LAUNCH(ctx);
     return TR_OK;
 }
+
+#include "bdpt.cuh"
