@@ -123,6 +123,9 @@ int tr_render_pt_spec(tr_ctx* ctx, int frame_begin, int n_frames, int max_depth,
  * tr_camera_set and at least one emitter.  With tile sharding every rank's hdr also receives that rank's splats on foreign
  * pixels, so the film reduce must be a SUM.  Synchronous per batch. */
 int tr_render_bdpt_rgb(tr_ctx* ctx, int frame_begin, int n_frames, uint64_t seed);
+/* with "stage_timing" on: device time of the last tr_render_bdpt_rgb spent in the closest-hit kernels of the sub-path stages and
+ * in the connection shadow-query kernel (CUDA events around every launch) */
+int tr_bdpt_kernel_ms(tr_ctx* ctx, float* ms_trace_kernels, float* ms_shadow_kernel);
 /* replaces Debug.render (integrator/Debug.py:44-66); also fills the first-hit buffers */
 int tr_render_debug(tr_ctx* ctx);
 /* frame-0 primary rays and first hits, index [x*H+y]; any pointer may be NULL */

@@ -167,3 +167,26 @@ def test_bdpt_needs_emitter(gpu_ctx):
     cam.update()
     with pytest.raises(RuntimeError, match="emitter"):
         integ.render()
+
+
+@pytest.mark.parametrize("name,fit,smooth", [("cornell", 0.8, False), ("veach", 0.5, True)])
+def test_bdpt_wavefront_equals_lockstep(gpu_ctx, name, fit, smooth):
+    """the wavefront pipeline (persistent k_trace / k_shadow<QUERY> + per-stage vertex and connection kernels) and the lock-step
+    pipeline run the same device functions: vertex records, depths and strategy contributions are bit-identical, ray counts
+    equal; the films differ only by the summation order of the splat atomics"""
+    W = H = 64
+    scene, cam, integ = build_gpu(name, W, H, fit, smooth)
+    xs, ys = np.meshgrid(np.arange(W), np.arange(H), indexing="ij")
+    px = xs.reshape(-1).astype(np.int32); py = ys.reshape(-1).astype(np.int32)
+    out = {}
+    for mode in (1, 0):
+        gpu_ctx.set_option("bdpt_wavefront", mode)
+        gpu_ctx.film_clear(); cam.frame = 2; cam.frame_cpu[0] = 2
+        integ.render()
+        st = gpu_ctx.stats()
+        out[mode] = gpu_ctx.test_bdpt_dump(px, py) + (integ.hdr.to_numpy(), int(st["rays_closest"]), int(st["rays_shadow"]))
+    gpu_ctx.set_option("bdpt_wavefront", 1)
+    for k in range(3):
+        assert np.array_equal(out[1][k], out[0][k])
+    assert out[1][4] == out[0][4] and out[1][5] == out[0][5]
+    assert np.allclose(out[1][3], out[0][3], rtol=1e-5, atol=1e-7)

@@ -51,6 +51,7 @@ SIGNATURES = {
     "tr_render_pt_rgb": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_uint64]),
     "tr_render_pt_spec": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_uint64]),
     "tr_render_bdpt_rgb": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint64]),
+    "tr_bdpt_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "tr_test_bdpt_dump": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "tr_render_debug": (C.c_int, [_vp]),
     "tr_first_hit_download": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -215,6 +216,11 @@ class Context:
 
     def render_bdpt_rgb(self, frame_begin, n_frames, seed=0):
         self._ck(self.lib.tr_render_bdpt_rgb(self.h, int(frame_begin), int(n_frames), int(seed)), "tr_render_bdpt_rgb")
+
+    def bdpt_kernel_ms(self):
+        a, b = C.c_float(0), C.c_float(0)
+        self._ck(self.lib.tr_bdpt_kernel_ms(self.h, C.byref(a), C.byref(b)), "tr_bdpt_kernel_ms")
+        return float(a.value), float(b.value)
 
     def test_bdpt_dump(self, px, py):
         px = np.ascontiguousarray(px, np.int32); py = np.ascontiguousarray(py, np.int32); n = px.size

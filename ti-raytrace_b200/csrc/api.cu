@@ -68,7 +68,8 @@ void tr_ctx_destroy(tr_ctx* ctx) {
                     ctx->d_shq[0][2], ctx->d_shq[1][0], ctx->d_shq[1][1], ctx->d_shq[1][2], ctx->d_Lnee, ctx->d_L, ctx->d_ctr, ctx->d_batch_params, ctx->d_matlin, ctx->d_axis, ctx->d_nodesx, ctx->d_smooth,
                     ctx->d_sensor, ctx->d_spectrum[0], ctx->d_spectrum[1], ctx->d_spectrum[2], ctx->d_spectrum[3], ctx->d_rs_scale, ctx->d_rs_data,
                     ctx->d_sky, ctx->d_matspec, ctx->d_white_point,
-                    ctx->d_bd_vb, ctx->d_bd_depths, ctx->d_bd_contrib, ctx->d_bd_splat, ctx->d_bd_items, ctx->d_bd_tile_slot, ctx->d_bd_ctr};
+                    ctx->d_bd_vb, ctx->d_bd_depths, ctx->d_bd_contrib, ctx->d_bd_splat, ctx->d_bd_items, ctx->d_bd_tile_slot, ctx->d_bd_ctr,
+                    ctx->d_bd_sq[0], ctx->d_bd_sq[1], ctx->d_bd_vis};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -214,6 +215,7 @@ int tr_set_option(tr_ctx* ctx, const char* name, int value) {
     else if (!strcmp(name, "chains")) ctx->opt_chains = value;
     else if (!strcmp(name, "shadow_overlap")) ctx->opt_shadow_overlap = value;
     else if (!strcmp(name, "tail_max")) ctx->opt_tail_max = value;
+    else if (!strcmp(name, "bdpt_wavefront")) ctx->opt_bdpt_wavefront = value;
     else if (!strcmp(name, "max_paths")) ctx->opt_max_paths = (size_t)value;
     else return tr_fail(ctx, TR_ERR_INVALID, "tr_set_option: unknown option '%s'", name);
     ctx->gen++;

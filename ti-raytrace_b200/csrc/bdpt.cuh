@@ -3,14 +3,21 @@
 //
 // The reference runs one thread per pixel that builds an eye sub-path (<= 7 vertices) and a light sub-path (<= 6), then
 // loops over every (e, l) prefix pair, tracing one shadow ray per connection and rewriting the end-point vertices in place
-// for the MIS weight (mis_weight, :258-434).  Here one frame batch is five launches over SoA buffers in HBM:
-//   k_bdpt_paths    one lane per (sample, sub-path): warps are homogeneous (all-eye or all-light), vertices go to the
-//                   vertex buffer  vb[(v * 5 + c) * cap + s]  (v = 0..6 eye, 7..12 light; c = 5 float4 words, 80 B / vertex)
-//   k_bdpt_items    enumerates the valid strategies of every sample, strategy-major, into a compact connection queue
-//   k_bdpt_connect  one lane per connection: geometric term, shadow query (the early-exit nearest-hit query of trace.cuh),
-//                   BSDF terms and the MIS weight computed on register copies of the <= 4 vertices the reference
-//                   overwrites; e >= 2 results go to contrib[strategy][s], e == 1 results are splatted with float atomics
-//   k_bdpt_film     per pixel and frame: own strategies summed in the reference's loop order + splats, running mean
+// for the MIS weight (mis_weight, :258-434).  Here one frame batch is a wavefront over SoA buffers in HBM:
+//   k_bdpt_generate        vertex 0 of both sub-paths of every sample + their first rays into the path queue (eye and
+//                          light sub-paths share the queue: 2 entries per sample)
+//   6 x { k_trace, k_bdpt_vertex }   the persistent closest-hit kernel of PT_RGB (per-lane ray replacement, material-
+//                          sorted output queues), then one thread per hit: build the vertex record
+//                          vb[(v * 5 + c) * cap + s]  (v = 0..6 eye, 7..12 light; c = 5 float4 words, 80 B / vertex),
+//                          patch the previous vertex's reverse pdf, sample the BSDF, append the next ray
+//   k_bdpt_items           enumerates the valid strategies of every sample, strategy-major, into a connection queue
+//   k_bdpt_connect_gen     one thread per connection: geometric term -> shadow-queue entry when a visibility query is needed
+//   k_shadow<QUERY>        the persistent early-exit nearest-hit shadow kernel of PT_RGB, writing (visible ? t : -1) per item
+//   k_bdpt_connect_eval    BSDF terms and the MIS weight computed on register copies of the <= 4 vertices the reference
+//                          overwrites; e >= 2 results go to contrib[strategy][s], e == 1 results are splatted (float atomics)
+//   k_bdpt_film            per pixel and frame: own strategies summed in the reference's loop order + splats, running mean
+// The first version (option "bdpt_wavefront" = 0) is kept as a cross-check: k_bdpt_paths / k_bdpt_connect run one lane per
+// sub-path / connection with the warp walking the BVH in lock step; same device functions, same film.
 // Quirks kept literally are listed in oracle/bdpt_core.inc (the restatement this is tested against); RNG blocks as there.
 #pragma once
 
@@ -62,6 +69,86 @@ __device__ __forceinline__ void bv_scalars(const BdArgs& b, size_t s, int v, flo
     delta = (__float_as_int(((const float*)(b.vb + (size_t)(v * 5 + 2) * b.cap + s))[3]) >> 4) & 15;
 }
 
+// One hit of a sub-path (the loop bodies of eye_path, BDPT_RGB.py:118-186, and light_path, :213-249): build vertex `depth`,
+// patch the reverse pdf of vertex depth-1, sample the continuation.  counted: the vertex joins the sub-path (depth += 1);
+// cont: the walk goes on with (origin, dir, beta, pdfFwd) and (pos, normal) as the new previous vertex.
+// The two variants differ where the reference differs: the eye path stores the emitter vertex it hits and measures `to`
+// from the offset ray origin with a clamped distance; the light path stops in front of emitters, measures from the
+// stored previous position, and multiplies fpdf in a different order.
+struct BdStep { bool counted, cont; V3 origin, dir, beta, pos, normal; float pdfFwd; };
+template <bool LIGHT>
+__device__ __forceinline__ BdStep bd_vertex(const WfArgs& a, const BdArgs& b, const BatchParams& bp, size_t s, unsigned pix, unsigned frame, int depth,
+                                            V3 origin, V3 dir, V3 beta, float pdfFwd, V3 prev_pos, V3 prev_normal, int prim, float hu, float hv, float ht) {
+    const int vbase = LIGHT ? BD_EYE_MAX : 0;
+    BdStep st; st.counted = false; st.cont = false;
+    Surf sf = surface_at(a, prim, hu, hv, origin, dir, ht);
+    V3 fn = signf_(dot3(-dir, sf.gn)) * sf.n;
+    const float* m = a.material + (size_t)sf.mat * 10;
+    const int mt = (int)__ldg(m);
+    const float p0 = __ldg(m + 5), p1 = __ldg(m + 6);
+    if (LIGHT && mt == TR_MAT_LIGHT) return st;
+    V3 to; float dist;
+    if (!LIGHT) { to = sf.pos - origin; dist = fmaxf(length3(to), 0.01f); }
+    else { to = sf.pos - prev_pos; dist = length3(to); }
+    const float inv_dist2 = 1.0f / (dist * dist);
+    to = to / dist;
+    BV v; v.pos = sf.pos; v.normal = sf.n; v.snormal = fn; v.wo = dir; v.rpdf = 0.0f; v.prim = prim; v.mat = sf.mat; v.delta = 0;
+    if (!LIGHT) v.fpdf = pdfFwd * fabsf(dot3(to, prev_normal)) * inv_dist2;
+    else v.fpdf = pdfFwd * (fabsf(dot3(to, prev_normal)) * inv_dist2);
+    if (!LIGHT && mt == TR_MAT_LIGHT) {
+        V3 mcol = mk3(__ldg(m + 2), __ldg(m + 3), __ldg(m + 4));
+        v.beta = (beta * mcol) * fabsf(dot3(sf.n, dir)); v.type = BD_VERTEX_LIGHT;
+        bv_store(b, s, vbase + depth, v);
+        st.counted = true;
+        return st;
+    }
+    v.beta = beta * fabsf(dot3(dir, sf.n)); v.type = BD_VERTEX_SURFACE;
+    V3 rc = f4xyz(__ldg(a.matlin + sf.mat));
+    float4 R0 = rng4(bp.seed, pix, frame, (LIGHT ? 42u : 1u) + 2u * (unsigned)(depth - 1));
+    float4 R1 = rng4(bp.seed, pix, frame, (LIGHT ? 43u : 2u) + 2u * (unsigned)(depth - 1));
+    V3 next_dir; float brdf, f_or_b = 1.0f, pdfRev;
+    if (mt == TR_MAT_GLASS) { next_dir = glass_sample(dir, sf.n, p0, R0.w, f_or_b); brdf = 1.0f; pdfFwd = 1.0f; v.delta = 1; }
+    else { next_dir = disney_sample(dir, fn, p0, p1, R0.w, R1.x, R1.y); disney_evaluate_pdf(fn, -dir, next_dir, p0, p1, brdf, pdfFwd); }
+    bv_store(b, s, vbase + depth, v);
+    if (!(pdfFwd > 0.0f)) return st;
+    if (mt == TR_MAT_GLASS) { pdfRev = 0.0f; pdfFwd = 0.0f; beta = beta * (brdf * rc); }
+    else {
+        beta = beta * (((brdf * rc) * fabsf(dot3(sf.n, next_dir))) / pdfFwd);
+        pdfRev = disney_pdf(fn, next_dir, -dir, p0, p1);
+    }
+    bv_set_rpdf(b, s, vbase + depth - 1, pdfRev * fabsf(dot3(to, sf.n)) * inv_dist2);
+    if (f_or_b < 0.0f) { float Rr = expf(-ht / p1); if (R1.z >= Rr) return st; }
+    st.counted = true; st.cont = true;
+    st.origin = offset_ray(sf.pos, signf_(f_or_b) * fn); st.dir = next_dir; st.beta = beta; st.pdfFwd = pdfFwd; st.pos = sf.pos; st.normal = sf.n;
+    return st;
+}
+
+// vertex 0 of a sub-path and its first ray: the lens (eye_path :108-116) or a sampled emitter point with a cosine-hemisphere
+// direction (light_path :194-211, Scene.sample_light Scene.py:430-474: point as in sample_li)
+template <bool LIGHT>
+__device__ __forceinline__ void bd_vertex0(const WfArgs& a, const BdArgs& b, const BatchParams& bp, size_t s, unsigned pix, unsigned frame, int x, int y,
+                                           V3& origin, V3& dir, V3& beta, float& pdfFwd) {
+    BV v0; v0.snormal = mk3(0.f, 0.f, 0.f); v0.wo = mk3(0.f, 0.f, 0.f); v0.rpdf = 0.0f; v0.prim = 0; v0.mat = 0; v0.delta = 0;
+    if (!LIGHT) {
+        float jx = 0.0f, jy = 0.0f;
+        if (frame != 0) { float4 r = rng4(bp.seed, pix, frame, 0u); jx = r.x - 0.5f; jy = r.y - 0.5f; }
+        origin = mk3(a.cam.eye[0], a.cam.eye[1], a.cam.eye[2]); dir = camera_dir(a.cam, x, y, jx, jy);
+        v0.pos = origin; v0.normal = dir; v0.beta = mk3(1.f, 1.f, 1.f); v0.fpdf = 1.0f; v0.type = BD_VERTEX_LENS;
+        beta = mk3(1.f, 1.f, 1.f); pdfFwd = 1.0f;
+    } else {
+        float4 Ra = rng4(bp.seed, pix, frame, 40u), Rb = rng4(bp.seed, pix, frame, 41u);
+        LightSample ls = sample_li(a, mk3(0.f, 0.f, 0.f), Ra.x, Ra.y, Ra.z);
+        V3 p = cosine_sample_hemisphere(Rb.x, Rb.y);
+        pdfFwd = cosine_hemisphere_pdf(p.z);
+        dir = inverse_transform(p, ls.normal);
+        const float light_pdf = ls.choice_pdf;
+        origin = ls.pos;
+        v0.pos = ls.pos; v0.normal = ls.normal; v0.beta = ls.emission / light_pdf; v0.fpdf = light_pdf; v0.wo = dir; v0.type = BD_VERTEX_LIGHT;
+        beta = (ls.emission / light_pdf) * fabsf(dot3(ls.normal, dir));
+    }
+    bv_store(b, s, LIGHT ? BD_EYE_MAX : 0, v0);
+}
+
 // One sub-path (BDPT_RGB.py:104-187 eye_path / :189-250 light_path), one lane per sample, the warp walks in lock step.
 // The two loops differ where the reference differs: the eye path stores the emitter vertex it hits and measures `to`
 // from the offset ray origin with a clamped distance; the light path stops in front of emitters, measures from the
@@ -70,32 +157,11 @@ template <bool SMEM, bool LIGHT>
 __device__ __forceinline__ void bdpt_subpath(const WfArgs& a, const BdArgs& b, const BatchParams& bp, const TrNode* nodes, const TrLeaf* leaves,
                                              const TrNodeX* nodesx, size_t s, bool active, unsigned pix, unsigned frame, int x, int y,
                                              unsigned long long& n_closest) {
-    const int vbase = LIGHT ? BD_EYE_MAX : 0, maxd = LIGHT ? BD_LIGHT_MAX : BD_EYE_MAX;
+    const int maxd = LIGHT ? BD_LIGHT_MAX : BD_EYE_MAX;
     V3 origin = mk3(0.f, 0.f, 0.f), dir = mk3(1.f, 1.f, 1.f), beta = mk3(1.f, 1.f, 1.f), prev_pos = origin, prev_normal = dir;
-    float pdfFwd = 1.0f, pdfRev = 0.0f;
+    float pdfFwd = 1.0f;
     int depth = 1;
-    if (active) {
-        BV v0; v0.snormal = mk3(0.f, 0.f, 0.f); v0.wo = mk3(0.f, 0.f, 0.f); v0.rpdf = 0.0f; v0.prim = 0; v0.mat = 0; v0.delta = 0;
-        if (!LIGHT) {
-            float jx = 0.0f, jy = 0.0f;
-            if (frame != 0) { float4 r = rng4(bp.seed, pix, frame, 0u); jx = r.x - 0.5f; jy = r.y - 0.5f; }
-            origin = mk3(a.cam.eye[0], a.cam.eye[1], a.cam.eye[2]); dir = camera_dir(a.cam, x, y, jx, jy);
-            v0.pos = origin; v0.normal = dir; v0.beta = mk3(1.f, 1.f, 1.f); v0.fpdf = 1.0f; v0.type = BD_VERTEX_LENS;
-        } else {
-            // Scene.sample_light (Scene.py:430-474): point as in sample_li, cosine-hemisphere direction
-            float4 Ra = rng4(bp.seed, pix, frame, 40u), Rb = rng4(bp.seed, pix, frame, 41u);
-            LightSample ls = sample_li(a, mk3(0.f, 0.f, 0.f), Ra.x, Ra.y, Ra.z);
-            V3 p = cosine_sample_hemisphere(Rb.x, Rb.y);
-            pdfFwd = cosine_hemisphere_pdf(p.z);
-            dir = inverse_transform(p, ls.normal);
-            const float light_pdf = ls.choice_pdf;
-            origin = ls.pos;
-            v0.pos = ls.pos; v0.normal = ls.normal; v0.beta = ls.emission / light_pdf; v0.fpdf = light_pdf; v0.wo = dir; v0.type = BD_VERTEX_LIGHT;
-            beta = (ls.emission / light_pdf) * fabsf(dot3(ls.normal, dir));
-        }
-        prev_pos = v0.pos; prev_normal = v0.normal;
-        bv_store(b, s, vbase, v0);
-    }
+    if (active) { bd_vertex0<LIGHT>(a, b, bp, s, pix, frame, x, y, origin, dir, beta, pdfFwd); prev_pos = origin; prev_normal = LIGHT ? f4xyz(b.vb[(size_t)(BD_EYE_MAX * 5 + 1) * b.cap + s]) : dir; }
     bool alive = active;
     for (int it = 1; it < maxd; ++it) {
         if (__ballot_sync(0xffffffffu, alive) == 0u) break;
@@ -104,45 +170,10 @@ __device__ __forceinline__ void bdpt_subpath(const WfArgs& a, const BdArgs& b, c
         if (!alive) continue;
         ++n_closest;
         if (h.prim < 0) { alive = false; continue; }
-        Surf sf = surface_at(a, h.prim, h.u, h.v, origin, dir, h.t);
-        V3 fn = signf_(dot3(-dir, sf.gn)) * sf.n;
-        const float* m = a.material + (size_t)sf.mat * 10;
-        const int mt = (int)__ldg(m);
-        const float p0 = __ldg(m + 5), p1 = __ldg(m + 6);
-        if (LIGHT && mt == TR_MAT_LIGHT) { alive = false; continue; }
-        V3 to; float dist;
-        if (!LIGHT) { to = sf.pos - origin; dist = fmaxf(length3(to), 0.01f); }
-        else { to = sf.pos - prev_pos; dist = length3(to); }
-        const float inv_dist2 = 1.0f / (dist * dist);
-        to = to / dist;
-        BV v; v.pos = sf.pos; v.normal = sf.n; v.snormal = fn; v.wo = dir; v.rpdf = 0.0f; v.prim = h.prim; v.mat = sf.mat; v.delta = 0;
-        if (!LIGHT) v.fpdf = pdfFwd * fabsf(dot3(to, prev_normal)) * inv_dist2;
-        else v.fpdf = pdfFwd * (fabsf(dot3(to, prev_normal)) * inv_dist2);
-        if (!LIGHT && mt == TR_MAT_LIGHT) {
-            V3 mcol = mk3(__ldg(m + 2), __ldg(m + 3), __ldg(m + 4));
-            v.beta = (beta * mcol) * fabsf(dot3(sf.n, dir)); v.type = BD_VERTEX_LIGHT;
-            bv_store(b, s, vbase + depth, v);
-            depth += 1; alive = false; continue;
-        }
-        v.beta = beta * fabsf(dot3(dir, sf.n)); v.type = BD_VERTEX_SURFACE;
-        V3 rc = f4xyz(__ldg(a.matlin + sf.mat));
-        float4 R0 = rng4(bp.seed, pix, frame, (LIGHT ? 42u : 1u) + 2u * (unsigned)(depth - 1));
-        float4 R1 = rng4(bp.seed, pix, frame, (LIGHT ? 43u : 2u) + 2u * (unsigned)(depth - 1));
-        V3 next_dir; float brdf, f_or_b = 1.0f;
-        if (mt == TR_MAT_GLASS) { next_dir = glass_sample(dir, sf.n, p0, R0.w, f_or_b); brdf = 1.0f; pdfFwd = 1.0f; v.delta = 1; }
-        else { next_dir = disney_sample(dir, fn, p0, p1, R0.w, R1.x, R1.y); disney_evaluate_pdf(fn, -dir, next_dir, p0, p1, brdf, pdfFwd); }
-        bv_store(b, s, vbase + depth, v);
-        if (!(pdfFwd > 0.0f)) { alive = false; continue; }
-        if (mt == TR_MAT_GLASS) { pdfRev = 0.0f; pdfFwd = 0.0f; beta = beta * (brdf * rc); }
-        else {
-            beta = beta * (((brdf * rc) * fabsf(dot3(sf.n, next_dir))) / pdfFwd);
-            pdfRev = disney_pdf(fn, next_dir, -dir, p0, p1);
-        }
-        bv_set_rpdf(b, s, vbase + depth - 1, pdfRev * fabsf(dot3(to, sf.n)) * inv_dist2);
-        if (f_or_b < 0.0f) { float Rr = expf(-h.t / p1); if (R1.z >= Rr) { alive = false; continue; } }
-        depth += 1;
-        origin = offset_ray(sf.pos, signf_(f_or_b) * fn);
-        dir = next_dir; prev_pos = sf.pos; prev_normal = sf.n;
+        BdStep st = bd_vertex<LIGHT>(a, b, bp, s, pix, frame, depth, origin, dir, beta, pdfFwd, prev_pos, prev_normal, h.prim, h.u, h.v, h.t);
+        if (st.counted) depth += 1;
+        alive = st.cont;
+        if (st.cont) { prev_pos = st.pos; prev_normal = st.normal; origin = st.origin; dir = st.dir; beta = st.beta; pdfFwd = st.pdfFwd; }
     }
     if (active) b.depths[(LIGHT ? b.cap : 0) + s] = depth;
 }
@@ -302,7 +333,87 @@ __device__ __forceinline__ void bd_image_point(const WfArgs& a, const BdArgs& b,
     wi = normalize3(wi);
 }
 
-// connect_path (BDPT_RGB.py:436-580), one lane per (sample, e, l)
+// connect_path (BDPT_RGB.py:436-580) in three phases shared by both pipelines:
+//   bd_connect_geom   which vertices, whether a visibility query is needed and which ray / target primitive it uses
+//   (shadow query)    lock-step in k_bdpt_connect, the persistent k_shadow<QUERY> kernel in the wavefront pipeline
+//   bd_connect_finish BSDF terms, geometric factor, MIS weight, contribution / splat write
+struct BdConn {
+    bool need; int kind, target, nu, nv;          // kind: 1 e == 1 (light tracing), 2 l == 1 (next-event), 3 general
+    V3 ro, rd, radiance; float c0, c1, dist;
+    BV ev, lv; LightSample ls;
+};
+__device__ __forceinline__ void bd_connect_geom(const WfArgs& a, const BdArgs& b, const BatchParams& bp, size_t s, int e, int l, BdConn& c) {
+    c.need = false; c.kind = 0; c.target = 0; c.nu = -1; c.nv = -1; c.c0 = c.c1 = 0.0f; c.dist = 1.0f;
+    c.radiance = mk3(0.f, 0.f, 0.f); c.ro = mk3(0.f, 0.f, 0.f); c.rd = mk3(1.f, 1.f, 1.f);
+    if (l == 0) {
+        c.ev = bv_load(b, s, e - 1);
+        if (c.ev.type == BD_VERTEX_LIGHT) c.radiance = c.ev.beta;
+    } else if (e == 1) {
+        c.lv = bv_load(b, s, BD_EYE_MAX + l - 1);
+        bd_image_point(a, b, c.lv.pos, c.nu, c.nv, c.rd);
+        c.c0 = dot3(c.rd, c.lv.snormal);                                   // NdotL
+        if (c.nu >= 0 && c.lv.delta != 1 && c.c0 < 0.0f && c.lv.type == BD_VERTEX_SURFACE) {
+            c.need = true; c.kind = 1; c.target = c.lv.prim; c.ro = mk3(a.cam.eye[0], a.cam.eye[1], a.cam.eye[2]);
+        }
+    } else if (l == 1) {
+        c.ev = bv_load(b, s, e - 1);
+        if (c.ev.delta != 1) {
+            int x, y; slot_to_pixel(a, (int)(s % (size_t)a.npix), x, y);
+            unsigned pix = ((unsigned)x << 16) | (unsigned)y, frame = (unsigned)bp.frame_begin + (unsigned)(s / (size_t)a.npix);
+            float4 R0 = rng4(bp.seed, pix, frame, 1u + 2u * (unsigned)(e - 2));
+            c.ro = offset_ray(c.ev.pos, c.ev.snormal);
+            c.ls = sample_li(a, c.ro, R0.x, R0.y, R0.z);
+            c.c0 = dot3(c.ls.dir, c.ls.normal); c.c1 = dot3(c.ls.dir, c.ev.snormal);        // NdotLl, NdotLe
+            c.need = true; c.kind = 2; c.target = c.ls.prim; c.rd = -c.ls.dir;
+        }
+    } else {
+        c.ev = bv_load(b, s, e - 1); c.lv = bv_load(b, s, BD_EYE_MAX + l - 1);
+        if (c.lv.delta != 1 && c.ev.delta != 1 && c.ev.type == BD_VERTEX_SURFACE && c.lv.type == BD_VERTEX_SURFACE) {
+            V3 d = c.ev.pos - c.lv.pos; c.dist = length3(d); d = d / c.dist;
+            c.c0 = dot3(d, c.lv.snormal); c.c1 = dot3(d, c.ev.snormal);                 // NdotLl, NdotLe
+            c.need = true; c.kind = 3; c.target = c.ev.prim; c.ro = c.lv.pos; c.rd = d;
+        }
+    }
+}
+// vis / tt: the target primitive is the nearest hit of the query ray, at distance tt (closet_hit_shadow, Scene.py:671-699)
+__device__ __forceinline__ void bd_connect_finish(const WfArgs& a, const BdArgs& b, size_t s, int e, int l, BdConn& c, bool vis, float tt) {
+    V3 radiance = c.radiance, smp_pos = mk3(0.f, 0.f, 0.f), smp_normal = smp_pos; float smp_fpdf = 1.0f;
+    const BV& ev = c.ev; const BV& lv = c.lv;
+    if (c.need) {
+        if (c.kind == 1 && vis) {
+            const float* m = a.material + (size_t)lv.mat * 10;
+            float brdf, pdf; disney_evaluate_pdf(lv.snormal, -lv.wo, -c.rd, __ldg(m + 5), __ldg(m + 6), brdf, pdf);
+            if (pdf > 0.0f) { float G = fabsf(c.c0) / (tt * tt); radiance = (((G * lv.beta) * f4xyz(__ldg(a.matlin + lv.mat))) * brdf) / pdf; }
+        } else if (c.kind == 2 && vis && tt > BD_EPS) {
+            const float* m = a.material + (size_t)ev.mat * 10;
+            const float light_pdf = c.ls.choice_pdf;
+            float brdf, pdf; disney_evaluate_pdf(ev.snormal, -ev.wo, -c.ls.dir, __ldg(m + 5), __ldg(m + 6), brdf, pdf);
+            if (pdf > 0.0f) {
+                float G = fabsf(c.c1 * c.c0) / (tt * tt);
+                radiance = (((((G * ev.beta) * brdf) / pdf) * f4xyz(__ldg(a.matlin + ev.mat))) * c.ls.emission) / light_pdf;
+            }
+            smp_pos = c.ls.pos; smp_normal = c.ls.normal; smp_fpdf = light_pdf;
+        } else if (c.kind == 3 && vis && tt > BD_EPS) {
+            const float* mE = a.material + (size_t)ev.mat * 10; const float* mL = a.material + (size_t)lv.mat * 10;
+            float brdfL, lpdf, brdfE, epdf;
+            disney_evaluate_pdf(lv.snormal, -lv.wo, c.rd, __ldg(mL + 5), __ldg(mL + 6), brdfL, lpdf);
+            disney_evaluate_pdf(ev.snormal, -ev.wo, -c.rd, __ldg(mE + 5), __ldg(mE + 6), brdfE, epdf);
+            if (brdfL > 0.0f && brdfE > 0.0f) {
+                float G = fabsf(c.c1 * c.c0) / (c.dist * c.dist);
+                radiance = (((((((G * ev.beta) * lv.beta) * brdfL) / lpdf) * brdfE) / epdf) * f4xyz(__ldg(a.matlin + ev.mat))) * f4xyz(__ldg(a.matlin + lv.mat));
+            }
+        }
+    }
+    if (radiance.x > 0.0f && radiance.y > 0.0f && radiance.z > 0.0f) radiance = radiance * bdpt_mis_weight(a, b, s, e, l, smp_pos, smp_normal, smp_fpdf);
+    if (e == 1) {
+        if (c.nu >= 0 && (radiance.x != 0.0f || radiance.y != 0.0f || radiance.z != 0.0f)) {
+            float* o = b.splat + ((size_t)(s / (size_t)a.npix) * a.W * a.H + (size_t)c.nu * a.H + c.nv) * 3;
+            atomicAdd(o, radiance.x); atomicAdd(o + 1, radiance.y); atomicAdd(o + 2, radiance.z);
+        }
+    } else b.contrib[(size_t)bd_row(e, l) * b.cap + s] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
+}
+
+// lock-step pipeline: one lane per (sample, e, l), the warp walks the BVH together
 template <bool SMEM>
 __global__ void __launch_bounds__(WF_THREADS) k_bdpt_connect(WfArgs a, BdArgs b) {
     const TrNode* nodes; const TrLeaf* leaves; const TrNodeX* nodesx;
@@ -317,84 +428,109 @@ __global__ void __launch_bounds__(WF_THREADS) k_bdpt_connect(WfArgs a, BdArgs b)
         const bool active = it < n;
         unsigned item = active ? b.items[it] : 0u;
         const size_t s = item & 0x3ffffffu; const int e = (item >> 26) & 7, l = (int)(item >> 29);
-        V3 radiance = mk3(0.f, 0.f, 0.f), ro = mk3(0.f, 0.f, 0.f), rd = mk3(1.f, 1.f, 1.f);
-        V3 smp_pos = ro, smp_normal = ro; float smp_fpdf = 1.0f;
-        bool need = false; int target = 0, nu = -1, nv = -1, kind = 0;       // kind: 1 e == 1, 2 l == 1, 3 general
-        BV ev, lv; LightSample ls; float c0 = 0.0f, c1 = 0.0f, dist = 1.0f;
-        if (active) {
-            if (l == 0) {
-                ev = bv_load(b, s, e - 1);
-                if (ev.type == BD_VERTEX_LIGHT) radiance = ev.beta;
-            } else if (e == 1) {
-                lv = bv_load(b, s, BD_EYE_MAX + l - 1);
-                bd_image_point(a, b, lv.pos, nu, nv, rd);
-                c0 = dot3(rd, lv.snormal);                                   // NdotL
-                if (nu >= 0 && lv.delta != 1 && c0 < 0.0f && lv.type == BD_VERTEX_SURFACE) {
-                    need = true; kind = 1; target = lv.prim; ro = mk3(a.cam.eye[0], a.cam.eye[1], a.cam.eye[2]);
-                }
-            } else if (l == 1) {
-                ev = bv_load(b, s, e - 1);
-                if (ev.delta != 1) {
-                    int x, y; slot_to_pixel(a, (int)(s % (size_t)a.npix), x, y);
-                    unsigned pix = ((unsigned)x << 16) | (unsigned)y, frame = (unsigned)bp.frame_begin + (unsigned)(s / (size_t)a.npix);
-                    float4 R0 = rng4(bp.seed, pix, frame, 1u + 2u * (unsigned)(e - 2));
-                    ro = offset_ray(ev.pos, ev.snormal);
-                    ls = sample_li(a, ro, R0.x, R0.y, R0.z);
-                    c0 = dot3(ls.dir, ls.normal); c1 = dot3(ls.dir, ev.snormal);        // NdotLl, NdotLe
-                    need = true; kind = 2; target = ls.prim; rd = -ls.dir;
-                }
-            } else {
-                ev = bv_load(b, s, e - 1); lv = bv_load(b, s, BD_EYE_MAX + l - 1);
-                if (lv.delta != 1 && ev.delta != 1 && ev.type == BD_VERTEX_SURFACE && lv.type == BD_VERTEX_SURFACE) {
-                    V3 d = ev.pos - lv.pos; dist = length3(d); d = d / dist;
-                    c0 = dot3(d, lv.snormal); c1 = dot3(d, ev.snormal);                 // NdotLl, NdotLe
-                    need = true; kind = 3; target = ev.prim; ro = lv.pos; rd = d;
-                }
-            }
+        BdConn c; c.need = false;
+        if (active) bd_connect_geom(a, b, bp, s, e, l, c);
+        bool vis = false; float tt = TR_INF;
+        if (__ballot_sync(0xffffffffu, c.need) != 0u) {
+            RayPre r = make_ray(c.need ? c.ro : mk3(0.f, 0.f, 0.f), c.need ? c.rd : mk3(1.f, 1.f, 1.f));
+            int tleaf = c.need ? __ldg(a.leaf_of_prim + c.target) : 0;
+            vis = trace_shadow_visible<SMEM>(nodes, leaves, nodesx, a.nnodes, r, c.need, tleaf, a.ctr->visits + 2, &tt);
+            if (c.need) ++n_shadow;
         }
-        if (__ballot_sync(0xffffffffu, need) != 0u) {
-            RayPre r = make_ray(ro, rd);
-            int tleaf = need ? __ldg(a.leaf_of_prim + target) : 0;
-            float tt = TR_INF;
-            bool vis = trace_shadow_visible<SMEM>(nodes, leaves, nodesx, a.nnodes, r, need, tleaf, a.ctr->visits + 2, &tt);
-            if (need) {
-                ++n_shadow;
-                if (kind == 1 && vis) {
-                    const float* m = a.material + (size_t)lv.mat * 10;
-                    float brdf, pdf; disney_evaluate_pdf(lv.snormal, -lv.wo, -rd, __ldg(m + 5), __ldg(m + 6), brdf, pdf);
-                    if (pdf > 0.0f) { float G = fabsf(c0) / (tt * tt); radiance = (((G * lv.beta) * f4xyz(__ldg(a.matlin + lv.mat))) * brdf) / pdf; }
-                } else if (kind == 2 && vis && tt > BD_EPS) {
-                    const float* m = a.material + (size_t)ev.mat * 10;
-                    const float light_pdf = ls.choice_pdf;
-                    float brdf, pdf; disney_evaluate_pdf(ev.snormal, -ev.wo, -ls.dir, __ldg(m + 5), __ldg(m + 6), brdf, pdf);
-                    if (pdf > 0.0f) {
-                        float G = fabsf(c1 * c0) / (tt * tt);
-                        radiance = (((((G * ev.beta) * brdf) / pdf) * f4xyz(__ldg(a.matlin + ev.mat))) * ls.emission) / light_pdf;
-                    }
-                    smp_pos = ls.pos; smp_normal = ls.normal; smp_fpdf = light_pdf;
-                } else if (kind == 3 && vis && tt > BD_EPS) {
-                    const float* mE = a.material + (size_t)ev.mat * 10; const float* mL = a.material + (size_t)lv.mat * 10;
-                    float brdfL, lpdf, brdfE, epdf;
-                    disney_evaluate_pdf(lv.snormal, -lv.wo, rd, __ldg(mL + 5), __ldg(mL + 6), brdfL, lpdf);
-                    disney_evaluate_pdf(ev.snormal, -ev.wo, -rd, __ldg(mE + 5), __ldg(mE + 6), brdfE, epdf);
-                    if (brdfL > 0.0f && brdfE > 0.0f) {
-                        float G = fabsf(c1 * c0) / (dist * dist);
-                        radiance = (((((((G * ev.beta) * lv.beta) * brdfL) / lpdf) * brdfE) / epdf) * f4xyz(__ldg(a.matlin + ev.mat))) * f4xyz(__ldg(a.matlin + lv.mat));
-                    }
-                }
-            }
-        }
-        if (active) {
-            if (radiance.x > 0.0f && radiance.y > 0.0f && radiance.z > 0.0f) radiance = radiance * bdpt_mis_weight(a, b, s, e, l, smp_pos, smp_normal, smp_fpdf);
-            if (e == 1) {
-                if (nu >= 0 && (radiance.x != 0.0f || radiance.y != 0.0f || radiance.z != 0.0f)) {
-                    float* o = b.splat + ((size_t)(s / (size_t)a.npix) * a.W * a.H + (size_t)nu * a.H + nv) * 3;
-                    atomicAdd(o, radiance.x); atomicAdd(o + 1, radiance.y); atomicAdd(o + 2, radiance.z);
-                }
-            } else b.contrib[(size_t)bd_row(e, l) * b.cap + s] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
-        }
+        if (active) bd_connect_finish(a, b, s, e, l, c, vis, tt);
     }
     if (n_shadow) atomicAdd(b.ctr + 1, n_shadow);
+}
+
+// ------------------------------------------------------------------ wavefront pipeline
+// Path-queue record (the PT_RGB layout, so k_trace is shared):  A = (o.xyz, d.x)  B = (d.y, d.z, pdfFwd, sample | light << 31)
+// C = (beta.rgb, -).  Stage d traces the segment that ends in vertex d + 1 of either sub-path.
+__global__ void __launch_bounds__(WF_THREADS) k_bdpt_generate(WfArgs a, BdArgs b) {
+    const BatchParams bp = *a.bp;
+    const int nsamp = bp.n_frames * a.npix, nsamp_r = (nsamp + 31) & ~31;
+    const int stride = gridDim.x * blockDim.x;
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < 2 * nsamp_r; w += stride) {
+        const bool light = w >= nsamp_r;                                // warp-uniform
+        const int s = w - (light ? nsamp_r : 0);
+        int x = 0, y = 0; bool active = false; unsigned frame = 0;
+        if (s < nsamp) { int f = s / a.npix, p = s - f * a.npix; frame = (unsigned)(bp.frame_begin + f); active = slot_to_pixel(a, p, x, y); }
+        const unsigned pix = ((unsigned)x << 16) | (unsigned)y;
+        if (s < nsamp) b.depths[(light ? b.cap : 0) + s] = active ? 1 : 0;
+        V3 origin = mk3(0.f, 0.f, 0.f), dir = mk3(1.f, 1.f, 1.f), beta = dir; float pdfFwd = 1.0f;
+        if (active) { if (light) bd_vertex0<true>(a, b, bp, (size_t)s, pix, frame, x, y, origin, dir, beta, pdfFwd); else bd_vertex0<false>(a, b, bp, (size_t)s, pix, frame, x, y, origin, dir, beta, pdfFwd); }
+        int q = warp_append(&a.ctr->nq[0], active);
+        if (active) {
+            a.pa[0][q] = make_float4(origin.x, origin.y, origin.z, dir.x);
+            a.pb[0][q] = make_float4(dir.y, dir.z, pdfFwd, __uint_as_float((unsigned)s | (light ? SPEC_BIT : 0u)));
+            a.pc[0][q] = make_float4(beta.x, beta.y, beta.z, 0.0f);
+        }
+    }
+}
+
+// one thread per traced segment of stage d, walking the material-sorted queues k_trace filled (terminal | Disney | glass)
+__global__ void __launch_bounds__(WF_THREADS, 3) k_bdpt_vertex(WfArgs a, BdArgs b, int d) {
+    const BatchParams bp = *a.bp;
+    const int n0 = a.ctr->ncls[d][0], n1 = a.ctr->ncls[d][1], n2 = a.ctr->ncls[d][2];
+    const int n = n0 + n1 + n2, n_r = (n + 31) & ~31;
+    const int pp = d & 1, np_ = pp ^ 1, depth = d + 1;
+    const int stride = gridDim.x * blockDim.x;
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_r; w += stride) {
+        BdStep st; st.cont = false; unsigned sw = 0; bool light = false;
+        if (w < n) {
+            int cl = (w < n0) ? 0 : (w < n0 + n1 ? 1 : 2);
+            int q = a.cls[(size_t)cl * a.cap + (w - (cl == 0 ? 0 : (cl == 1 ? n0 : n0 + n1)))];
+            float4 A = a.pa[pp][q], B = a.pb[pp][q], C = a.pc[pp][q], Hh = a.hit[q];
+            const int prim = __float_as_int(Hh.y);
+            sw = __float_as_uint(B.w); light = (sw & SPEC_BIT) != 0;
+            const size_t s = sw & ~SPEC_BIT;
+            if (prim >= 0) {
+                int x, y; slot_to_pixel(a, (int)(s % (size_t)a.npix), x, y);
+                const unsigned pix = ((unsigned)x << 16) | (unsigned)y, frame = (unsigned)bp.frame_begin + (unsigned)(s / (size_t)a.npix);
+                const int vprev = (light ? BD_EYE_MAX : 0) + depth - 1;
+                V3 prev_pos = f4xyz(b.vb[(size_t)(vprev * 5) * b.cap + s]), prev_normal = f4xyz(b.vb[(size_t)(vprev * 5 + 1) * b.cap + s]);
+                V3 o = mk3(A.x, A.y, A.z), dir = mk3(A.w, B.x, B.y), beta = mk3(C.x, C.y, C.z);
+                if (light) st = bd_vertex<true>(a, b, bp, s, pix, frame, depth, o, dir, beta, B.z, prev_pos, prev_normal, prim, Hh.z, Hh.w, Hh.x);
+                else st = bd_vertex<false>(a, b, bp, s, pix, frame, depth, o, dir, beta, B.z, prev_pos, prev_normal, prim, Hh.z, Hh.w, Hh.x);
+                if (st.counted) b.depths[(light ? b.cap : 0) + s] = depth + 1;
+                if (depth + 1 >= (light ? BD_LIGHT_MAX : BD_EYE_MAX)) st.cont = false;         // the sub-path is full
+            }
+        }
+        int qn = warp_append(&a.ctr->nq[d + 1], st.cont);
+        if (st.cont) {
+            a.pa[np_][qn] = make_float4(st.origin.x, st.origin.y, st.origin.z, st.dir.x);
+            a.pb[np_][qn] = make_float4(st.dir.y, st.dir.z, st.pdfFwd, __uint_as_float(sw));
+            a.pc[np_][qn] = make_float4(st.beta.x, st.beta.y, st.beta.z, 0.0f);
+        }
+    }
+}
+
+// one thread per connection: geometry, then a shadow-queue entry  sa = (o.xyz, d.x)  sb = (d.y, d.z, target prim, item)
+__global__ void __launch_bounds__(WF_THREADS) k_bdpt_connect_gen(WfArgs a, BdArgs b) {
+    const BatchParams bp = *a.bp;
+    const int n = (int)b.ctr[2], n_r = (n + 31) & ~31;
+    const int stride = gridDim.x * blockDim.x;
+    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < n_r; it += stride) {
+        BdConn c; c.need = false;
+        if (it < n) { unsigned item = b.items[it]; bd_connect_geom(a, b, bp, item & 0x3ffffffu, (item >> 26) & 7, (int)(item >> 29), c); }
+        int q = warp_append(&a.ctr->nshadow[0], c.need);
+        if (c.need) {
+            a.sa[0][q] = make_float4(c.ro.x, c.ro.y, c.ro.z, c.rd.x);
+            a.sb[0][q] = make_float4(c.rd.y, c.rd.z, __int_as_float(c.target), __int_as_float(it));
+        }
+    }
+}
+// one thread per connection: geometry again (cheaper than spilling BdConn to HBM), the query result, BSDF terms + MIS
+__global__ void __launch_bounds__(WF_THREADS) k_bdpt_connect_eval(WfArgs a, BdArgs b) {
+    const BatchParams bp = *a.bp;
+    const int n = (int)b.ctr[2];
+    const int stride = gridDim.x * blockDim.x;
+    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < n; it += stride) {
+        unsigned item = b.items[it];
+        const size_t s = item & 0x3ffffffu; const int e = (item >> 26) & 7, l = (int)(item >> 29);
+        BdConn c; bd_connect_geom(a, b, bp, s, e, l, c);
+        float tt = c.need ? a.vis[it] : -1.0f;
+        bd_connect_finish(a, b, s, e, l, c, tt >= 0.0f, tt);
+    }
 }
 
 // render() tail (BDPT_RGB.py:625-641): radiance = own strategies in loop order + splats, then the running mean, frame by frame.
@@ -433,8 +569,10 @@ static int render_bdpt(tr_ctx* ctx, int frame_begin, int n_frames, uint64_t seed
     WfArgs a; int rc;
     if ((rc = fill_args(ctx, a, false))) return rc;
     if (ctx->nl <= 0) return tr_fail(ctx, TR_ERR_INVALID, "tr_render_bdpt_rgb: the scene has no emitter (Scene.sample_light needs one)");
-    // frames per batch: ~1.5 KB of vertex / contribution / queue records per sample
-    const size_t per_sample = (size_t)BD_NVERT * 80 + BD_NCONTRIB * 16 + BD_NSTRAT * 4 + 8;
+    const bool wave = ctx->opt_bdpt_wavefront != 0;
+    // bytes per sample: 13 vertex records + 21 contributions + 26 queue items + depths; the wavefront pipeline adds two path-queue
+    // slots (PT_RGB's 252 B each) and a worst-case connection shadow queue (26 x (32 B + 4 B))
+    const size_t per_sample = (size_t)BD_NVERT * 80 + BD_NCONTRIB * 16 + BD_NSTRAT * 4 + 8 + (wave ? 2 * 252 + BD_NSTRAT * 36 : 0);
     size_t budget = ctx->opt_max_paths * 252 / per_sample;
     const size_t npix = (size_t)(a.npix > 0 ? a.npix : 1);
     int F = ctx->opt_batch_frames > 0 ? ctx->opt_batch_frames : (int)(budget / npix);
@@ -448,25 +586,42 @@ static int render_bdpt(tr_ctx* ctx, int frame_begin, int n_frames, uint64_t seed
         if ((rc = tr_realloc(ctx, &ctx->d_bd_items, cap * BD_NSTRAT))) return rc;
         ctx->bd_cap = cap;
     }
+    if (wave) {
+        if ((rc = ensure_wavefront(ctx, 2 * ctx->bd_cap + 64))) return rc;
+        for (int k = 0; k < 2; ++k) if ((rc = tr_realloc(ctx, &ctx->d_bd_sq[k], ctx->bd_cap * BD_NSTRAT))) return rc;
+        if ((rc = tr_realloc(ctx, &ctx->d_bd_vis, ctx->bd_cap * BD_NSTRAT))) return rc;
+        if ((rc = fill_args(ctx, a, false))) return rc;
+        a.sa[0] = ctx->d_bd_sq[0]; a.sb[0] = ctx->d_bd_sq[1]; a.vis = ctx->d_bd_vis; a.tail_max = 0;
+    }
     if (F > ctx->bd_splat_frames || !ctx->d_bd_splat) { if ((rc = tr_realloc(ctx, &ctx->d_bd_splat, (size_t)F * ctx->W * ctx->H * 3))) return rc; ctx->bd_splat_frames = F; }
     if (!ctx->d_bd_ctr) TR_CUDA(ctx, cudaMalloc((void**)&ctx->d_bd_ctr, 4 * sizeof(unsigned long long)));
     BdArgs b; memset(&b, 0, sizeof(b));
     b.vb = ctx->d_bd_vb; b.depths = ctx->d_bd_depths; b.contrib = ctx->d_bd_contrib; b.splat = ctx->d_bd_splat; b.items = ctx->d_bd_items;
     b.tile_slot = ctx->d_bd_tile_slot; b.ctr = ctx->d_bd_ctr; b.cap = ctx->bd_cap; memcpy(b.view, ctx->view, 64);
     LaunchCfg cfg; memset(&cfg, 0, sizeof(cfg)); if ((rc = launch_cfg(ctx, a, cfg))) return rc;
-    int bp_ = 1, bc_ = 1;
+    int bp_ = 1, bc_ = 1, bq_ = 1;
     if (cfg.use_smem) {
         TR_CUDA(ctx, cudaFuncSetAttribute(k_bdpt_paths<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
         TR_CUDA(ctx, cudaFuncSetAttribute(k_bdpt_connect<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+        TR_CUDA(ctx, cudaFuncSetAttribute(k_shadow<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
         TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bp_, k_bdpt_paths<true>, WF_THREADS, cfg.smem));
         TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bc_, k_bdpt_connect<true>, WF_THREADS, cfg.smem));
+        TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bq_, k_shadow<true, true>, WF_THREADS, cfg.smem));
     } else {
         TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bp_, k_bdpt_paths<false>, WF_THREADS, 0));
         TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bc_, k_bdpt_connect<false>, WF_THREADS, 0));
+        TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bq_, k_shadow<false, true>, WF_THREADS, 0));
     }
-    if (bp_ < 1) bp_ = 1; if (bc_ < 1) bc_ = 1;
+    if (bp_ < 1) bp_ = 1; if (bc_ < 1) bc_ = 1; if (bq_ < 1) bq_ = 1;
     cudaStream_t s = ctx->stream;
-    uint64_t launches = 0, rays_c = 0, rays_s = 0;
+    uint64_t launches = 0, rays_c = 0, rays_s = 0, vis[4] = {0, 0, 0, 0};
+    const bool timing = ctx->opt_stage_timing != 0;
+    if (timing && ctx->stage_ev.empty()) {
+        ctx->stage_ev.resize(4 * TR_MAX_DEPTH_CAP);
+        for (auto& e : ctx->stage_ev) TR_CUDA(ctx, cudaEventCreate(&e));
+    }
+    cudaEvent_t* ev = timing ? ctx->stage_ev.data() : nullptr;
+    float ms_paths = 0.0f, ms_connect = 0.0f, ms_other = 0.0f, ms_ktrace = 0.0f, ms_kshadow = 0.0f;
     TR_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
     for (int f0 = 0; f0 < n_frames; f0 += F) {
         const int nf = (n_frames - f0 < F) ? n_frames - f0 : F;
@@ -475,34 +630,80 @@ static int render_bdpt(tr_ctx* ctx, int frame_begin, int n_frames, uint64_t seed
         TR_CUDA(ctx, cudaMemsetAsync(ctx->d_ctr, 0, sizeof(TrCounters), s));
         TR_CUDA(ctx, cudaMemsetAsync(ctx->d_bd_ctr, 0, 4 * sizeof(unsigned long long), s));
         TR_CUDA(ctx, cudaMemsetAsync(ctx->d_bd_splat, 0, (size_t)nf * ctx->W * ctx->H * 3 * sizeof(float), s));
-        if (a.npix > 0) {
+        if (ev) cudaEventRecord(ev[0], s);
+        if (a.npix > 0 && wave) {
+            // stage events (timing mode): ev[8 + 2d], ev[9 + 2d] bracket k_trace(d); ev[5], ev[6] bracket the shadow-query kernel
+            k_bdpt_generate<<<cfg.grid_simple, WF_THREADS, 0, s>>>(a, b); ++launches;
+            for (int d = 0; d < BD_EYE_MAX - 1; ++d) {
+                if (ev) cudaEventRecord(ev[8 + 2 * d], s);
+                if (cfg.use_smem) k_trace<true><<<cfg.grid_trace, WF_THREADS, cfg.smem, s>>>(a, d);
+                else k_trace<false><<<cfg.grid_trace, WF_THREADS, 0, s>>>(a, d);
+                if (ev) cudaEventRecord(ev[9 + 2 * d], s);
+                k_bdpt_vertex<<<cfg.grid_simple, WF_THREADS, 0, s>>>(a, b, d);
+                launches += 2;
+            }
+            if (ev) cudaEventRecord(ev[1], s);
+            k_bdpt_items<<<cfg.grid_simple, WF_THREADS, 0, s>>>(a, b);
+            if (ev) cudaEventRecord(ev[2], s);
+            k_bdpt_connect_gen<<<cfg.grid_simple, WF_THREADS, 0, s>>>(a, b);
+            if (ev) cudaEventRecord(ev[5], s);
+            if (cfg.use_smem) k_shadow<true, true><<<ctx->num_sms * bq_, WF_THREADS, cfg.smem, s>>>(a, 0);
+            else k_shadow<false, true><<<ctx->num_sms * bq_, WF_THREADS, 0, s>>>(a, 0);
+            if (ev) cudaEventRecord(ev[6], s);
+            k_bdpt_connect_eval<<<cfg.grid_simple, WF_THREADS, 0, s>>>(a, b);
+            if (ev) cudaEventRecord(ev[3], s);
+            launches += 4;
+        } else if (a.npix > 0) {
             if (cfg.use_smem) k_bdpt_paths<true><<<ctx->num_sms * bp_, WF_THREADS, cfg.smem, s>>>(a, b);
             else k_bdpt_paths<false><<<ctx->num_sms * bp_, WF_THREADS, 0, s>>>(a, b);
+            if (ev) cudaEventRecord(ev[1], s);
             k_bdpt_items<<<cfg.grid_simple, WF_THREADS, 0, s>>>(a, b);
+            if (ev) cudaEventRecord(ev[2], s);
             if (cfg.use_smem) k_bdpt_connect<true><<<ctx->num_sms * bc_, WF_THREADS, cfg.smem, s>>>(a, b);
             else k_bdpt_connect<false><<<ctx->num_sms * bc_, WF_THREADS, 0, s>>>(a, b);
+            if (ev) cudaEventRecord(ev[3], s);
             launches += 3;
         }
         k_bdpt_film<<<cfg.grid_simple, WF_THREADS, 0, s>>>(a, b); ++launches;
+        if (ev) cudaEventRecord(ev[4], s);
         TR_CHECK_LAUNCH(ctx);
         unsigned long long hc[4];
         TR_CUDA(ctx, cudaMemcpyAsync(hc, ctx->d_bd_ctr, sizeof(hc), cudaMemcpyDeviceToHost, s));
         TR_CUDA(ctx, cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(TrCounters), cudaMemcpyDeviceToHost, s));
         TR_CUDA(ctx, cudaStreamSynchronize(s));
-        rays_c += hc[0]; rays_s += hc[1];
+        if (wave) { for (int d = 0; d < BD_EYE_MAX - 1; ++d) rays_c += (uint64_t)ctx->h_ctr[0].nq[d]; rays_s += (uint64_t)ctx->h_ctr[0].nshadow[0]; }
+        else { rays_c += hc[0]; rays_s += hc[1]; }
+        for (int k = 0; k < 4; ++k) vis[k] += ctx->h_ctr[0].visits[k];
+        if (ev && a.npix > 0) {
+            float t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+            cudaEventElapsedTime(&t0, ev[0], ev[1]); cudaEventElapsedTime(&t1, ev[1], ev[2]); cudaEventElapsedTime(&t2, ev[2], ev[3]); cudaEventElapsedTime(&t3, ev[3], ev[4]);
+            ms_paths += t0; ms_connect += t2; ms_other += t1 + t3;
+            if (wave) {
+                for (int d = 0; d < BD_EYE_MAX - 1; ++d) { float t = 0; cudaEventElapsedTime(&t, ev[8 + 2 * d], ev[9 + 2 * d]); ms_ktrace += t; }
+                float t = 0; cudaEventElapsedTime(&t, ev[5], ev[6]); ms_kshadow += t;
+            }
+        }
     }
     TR_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
     TR_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
     float ms = 0.0f; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->stats.rays_closest = rays_c; ctx->stats.rays_shadow = rays_s;
-    ctx->stats.node_visits = ctx->h_ctr[0].visits[0]; ctx->stats.leaf_tests = ctx->h_ctr[0].visits[1];
-    ctx->stats.node_visits_shadow = ctx->h_ctr[0].visits[2]; ctx->stats.leaf_tests_shadow = ctx->h_ctr[0].visits[3];
+    ctx->stats.node_visits = vis[0]; ctx->stats.leaf_tests = vis[1]; ctx->stats.node_visits_shadow = vis[2]; ctx->stats.leaf_tests_shadow = vis[3];
     ctx->stats.kernel_launches = launches; ctx->stats.ms_total = ms; ctx->stats.frames = n_frames; ctx->stats.paths_in_flight = (int)cap; ctx->stats.chains = 1;
-    ctx->stats.ms_trace = ctx->stats.ms_shade = ctx->stats.ms_shadow = 0.0f;
+    // stage timing: ms_trace = the sub-path stage, ms_shadow = the connection stage, ms_shade = items + film; the traversal
+    // kernels alone (wavefront pipeline) are reported through tr_bdpt_kernel_ms
+    ctx->stats.ms_trace = ms_paths; ctx->stats.ms_shade = ms_other; ctx->stats.ms_shadow = ms_connect;
+    ctx->bd_ms_ktrace = ms_ktrace; ctx->bd_ms_kshadow = ms_kshadow;
     return TR_OK;
 }
 
 extern "C" int tr_render_bdpt_rgb(tr_ctx* ctx, int frame_begin, int n_frames, uint64_t seed) { return render_bdpt(ctx, frame_begin, n_frames, seed); }
+extern "C" int tr_bdpt_kernel_ms(tr_ctx* ctx, float* ms_trace_kernels, float* ms_shadow_kernel) {
+    if (!ctx) return TR_ERR_INVALID;
+    if (ms_trace_kernels) *ms_trace_kernels = ctx->bd_ms_ktrace;
+    if (ms_shadow_kernel) *ms_shadow_kernel = ctx->bd_ms_kshadow;
+    return TR_OK;
+}
 
 // ---- unit hook: vertices, depths and per-strategy contributions of the samples of the LAST batch (frame 0 of it), for the
 // pixel list given; layouts as oracle orc_bdpt_pixel_dump: verts n x 13 x 20, depths n x 2, contrib n x 7 x 7 x 4 (e == 1 rows are

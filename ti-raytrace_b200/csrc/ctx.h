@@ -112,7 +112,8 @@ struct tr_ctx {
     float view[16] = {0};                          // Camera.view (get_image_point / get_optical_axis)
     float4* d_bd_vb = nullptr; int* d_bd_depths = nullptr; float4* d_bd_contrib = nullptr; float* d_bd_splat = nullptr;
     unsigned* d_bd_items = nullptr; int* d_bd_tile_slot = nullptr; unsigned long long* d_bd_ctr = nullptr;
-    size_t bd_cap = 0; int bd_splat_frames = 0; bool bd_tiles_ready = false;
+    float4* d_bd_sq[2] = {nullptr, nullptr}; float* d_bd_vis = nullptr;      // wavefront pipeline: connection shadow queue (sa, sb) + query results
+    size_t bd_cap = 0; int bd_splat_frames = 0; float bd_ms_ktrace = 0.0f, bd_ms_kshadow = 0.0f;
 
     // options
     int opt_batch_frames = 0;       // 0 = auto
@@ -122,6 +123,7 @@ struct tr_ctx {
     int opt_chains = 4;
     int opt_shadow_overlap = 1;
     int opt_tail_max = 16384;
+    int opt_bdpt_wavefront = 1;     // 0: lock-step BDPT pipeline (cross-check)
     size_t opt_max_paths = (size_t)20 << 20;   // path slots per batch (188 B each): more paths in flight amortise the per-stage tails
 
     // cuda graph cache for the batch pipeline

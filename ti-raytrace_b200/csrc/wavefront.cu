@@ -37,6 +37,7 @@ struct WfArgs {
     float4* sa[2]; float4* sb[2]; float4* sc[2];   // shadow queue, ping-pong by depth parity (shadow(d) overlaps trace/shade(d+1))
     float4* L;                                     // terminal term (emitter / environment) per sample
     float4* Lnee;                                  // sum of the NEE terms per sample, in depth order
+    float* vis;                                    // BDPT connection queries (k_shadow<.., QUERY>): t of the visible target or -1, per item
     TrCounters* ctr;
     const BatchParams* bp;
     int tail_max;                                  // hand the chain to k_tail once its live paths drop to this (0 = never)
@@ -629,7 +630,9 @@ __global__ void __launch_bounds__(WF_THREADS) k_tail(WfArgs a, int depth) {
 // ------------------------------------------------------------------ shadow
 // Same persistent schedule as k_trace; the walk is bounded by the target's own t and stops at the first
 // primitive that would have won the reference's nearest-hit comparison (see trace_shadow_visible).
-template <bool SMEM>
+// QUERY (BDPT connections): instead of adding a contribution, report per queue item (sb.w) the distance to the target when it is
+// the nearest hit, -1 otherwise.
+template <bool SMEM, bool QUERY = false>
 __global__ void __launch_bounds__(WF_THREADS) k_shadow(WfArgs a, int depth) {
     if (tail_took_over(a, depth)) return;
     const TrNode* nodes; const TrLeaf* leaves; const TrNodeX* nodesx;
@@ -697,7 +700,8 @@ __global__ void __launch_bounds__(WF_THREADS) k_shadow(WfArgs a, int depth) {
                 pend = -1;
             }
         }
-        if ((finm >> lane) & 1u) {
+        if (QUERY) { if ((finm >> lane) & 1u) a.vis[slot] = (visible && found) ? tt : -1.0f; }
+        else if ((finm >> lane) & 1u) {
             if (visible && found) {
                 float4 C = a.sc[depth & 1][q];
                 float4 Lv = a.Lnee[slot]; Lv.x += C.x; Lv.y += C.y; Lv.z += C.z; Lv.w += C.w; a.Lnee[slot] = Lv;   // .w: 4th hero lane (0 for PT_RGB)
