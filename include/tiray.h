@@ -74,6 +74,18 @@ int tr_material_upload(tr_ctx* ctx, const float* material, int nm);
 /* replaces Texture.setup_data_gpu (texture/Texture.py:41-42): buf[x][y] packed RGB i32 */
 int tr_env_upload(tr_ctx* ctx, const int32_t* rgb, int w, int h, float power);
 
+/* ---- OBJ / MTL ingest (host code): replaces pywavefront.Wavefront(filename).parse() and the per-vertex loops of Scene.add_obj
+ * (Scene.py:59-141).  tr_obj_open parses the file (and the MTL it names); materials come back in PyWavefront's order with
+ * props = Kd[3], Ke[3], d (transparency), Ns (shininess), Ni (optical density) and n_vertices = 3 x triangles;
+ * tr_obj_material_vertices fills n_vertices x 9 f64 rows (pos3, normal3, tex3; zeros where the file has no vn / vt). */
+typedef struct tr_obj tr_obj;
+int  tr_obj_open(const char* path, tr_obj** out);
+void tr_obj_close(tr_obj* obj);
+const char* tr_obj_last_error(void);
+int  tr_obj_material_count(const tr_obj* obj);
+int  tr_obj_material(const tr_obj* obj, int k, char* name, int name_cap, double props[9], int64_t* n_vertices, int* has_vt, int* has_vn);
+int  tr_obj_material_vertices(const tr_obj* obj, int k, double* rows);
+
 /* ---- LBVH: replaces Bvh.setup_data_gpu (accel/LBvh.py:192-226): build_morton_3d, radix_sort_host,
  * build_lbvh, gen_aabb loop and the host-side flatten_tree, all on the device. */
 int tr_bvh_build(tr_ctx* ctx);

@@ -114,3 +114,40 @@ def test_reference_example_constructs_unchanged(monkeypatch):
     ex.scene.setup_data_cpu()
     assert ex.scene.primitive_count == 36 and ex.integrator.stack_size == 64
     sys.modules.pop("Example", None)
+
+
+def test_native_obj_reader_numbers_and_errors(tmp_path):
+    """csrc/objparse.cpp: decimal strings become the doubles Python's float() gives (fast path and strtod fallback); polygons
+    fan like PyWavefront; negative indices; malformed input raises with file:line"""
+    import objio
+    rng = np.random.RandomState(7)
+    vals = ["0", "-0.0", "1", "-1.5", "3.14159265358979", "1e-3", "-2.5E+2", "123456789012345678", "0.1234567890123456789012",
+            "1e22", "1e23", "9007199254740993", "4.9e-324", "1.7976931348623157e308", ".5", "5.", "+7.25", "00012.500"]
+    vals += ["%.*g" % (rng.randint(1, 18), x) for x in rng.randn(300) * 10.0 ** rng.randint(-12, 12, 300)]
+    vals += ["%.6f" % x for x in rng.rand(300) * 1000 - 500]
+    while len(vals) % 3:
+        vals.append("1")
+    p = tmp_path / "n.obj"
+    lines = ["v %s %s %s" % tuple(vals[k:k + 3]) for k in range(0, len(vals), 3)]
+    n = len(lines)
+    lines += ["f %d %d %d" % (k + 1, (k + 1) % n + 1, (k + 2) % n + 1) for k in range(n)]
+    p.write_text("\n".join(lines) + "\n")
+    m = objio.read_obj(str(p))
+    assert len(m) == 1 and m[0].name == "default0" and m[0].rows.shape == (3 * n, 9)
+    got = m[0].rows[0::3, 0:3].reshape(-1)
+    want = np.array([float(v) for v in vals], np.float64)
+    assert np.array_equal(got, want) and np.array_equal(np.signbit(got), np.signbit(want))
+    # a quad and a pentagon with negative indices, vt / vn present, CRLF line ends
+    q = tmp_path / "q.obj"
+    q.write_bytes(b"v 0 0 0\r\nv 1 0 0\r\nv 1 1 0\r\nv 0 1 0\r\nv 0.5 2 0\r\nvt 0.25 0.75\r\nvn 0 0 1\r\n"
+                  b"usemtl a\r\nf 1/1/1 2/1/1 3/1/1 4/1/1\r\nusemtl b\r\nf -5//-1 -4//-1 -3//-1 -2//-1 -1//-1\r\n")
+    a, b = objio.read_obj(str(q))
+    assert (a.name, a.has_vt, a.has_vn, b.name, b.has_vt, b.has_vn) == ("a", True, True, "b", False, True)
+    assert a.rows[:, 0:2].tolist() == [[0, 0], [1, 0], [1, 1], [0, 1], [0, 0], [1, 1]]           # (v1 v2 v3) (v4 v1 v3)
+    assert np.all(a.rows[:, 6:8] == [0.25, 0.75]) and np.all(a.rows[:, 3:6] == [0, 0, 1])
+    assert b.rows[:, 0:2].tolist() == [[0, 0], [1, 0], [1, 1], [0, 1], [0, 0], [1, 1], [0.5, 2], [0, 0], [0, 1]]
+    for body, msg in (("v 0 0 0\nf 1 2 3\n", "out of range"), ("v 0 0 x\n", "bad number"), ("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1/1 2/1 3/1\n", "out of range"),
+                      ("v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nf 1 2 3\nf 1//1 2//1 3//1\n", "mixes vertex formats"), ("mtllib missing.mtl\n", "cannot open")):
+        bad = tmp_path / "bad.obj"; bad.write_text(body)
+        with pytest.raises((ValueError, FileNotFoundError), match=msg):
+            objio.read_obj(str(bad))

@@ -44,8 +44,7 @@ class Scene:
 
     # ------------------------------------------------------------------ ingest (Scene.py:59-141)
     def add_obj(self, filename):
-        mats, P, N, T = objio.read_obj(_paths.resolve(filename))
-        for m in mats:
+        for m in objio.read_obj(_paths.resolve(filename)):
             rec = SCD.Material()
             if m.emissive[0] > 1.0 and m.emissive[1] > 1.0 and m.emissive[2] > 1.0:
                 rec.type = SCD.MAT_LIGHT
@@ -59,7 +58,7 @@ class Scene:
             rec.alebdoTex = -1 if m.texture is None else float(m.texture)
             self.material_cpu.append(rec)
 
-            rows = objio.material_vertices(m, P, N, T)
+            rows = m.rows
             ntri = rows.shape[0] // 3
             if ntri:
                 self.maxboundarynp[0, :] = np.maximum(self.maxboundarynp[0, :], rows[:, 0:3].max(axis=0).astype(np.float32))

@@ -35,6 +35,12 @@ SIGNATURES = {
     "tr_scene_upload": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp]),
     "tr_material_upload": (C.c_int, [_vp, _vp, C.c_int]),
     "tr_env_upload": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_float]),
+    "tr_obj_open": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
+    "tr_obj_close": (None, [_vp]),
+    "tr_obj_last_error": (C.c_char_p, []),
+    "tr_obj_material_count": (C.c_int, [_vp]),
+    "tr_obj_material": (C.c_int, [_vp, C.c_int, C.c_char_p, C.c_int, _vp, C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "tr_obj_material_vertices": (C.c_int, [_vp, C.c_int, _vp]),
     "tr_bvh_build": (C.c_int, [_vp]),
     "tr_bvh_download": (C.c_int, [_vp, _vp, _vp, _vp]),
     "tr_morton_download": (C.c_int, [_vp, _vp]),

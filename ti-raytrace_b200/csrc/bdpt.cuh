@@ -221,100 +221,105 @@ __global__ void __launch_bounds__(WF_THREADS) k_bdpt_items(WfArgs a, BdArgs b) {
 }
 
 // mis_weight (BDPT_RGB.py:258-434).  The reference saves <= 4 end-point vertices, overwrites them in the per-pixel vertex
-// fields, walks the pdf ratios and restores them; here the same four vertices are register copies and the walk reads the
-// untouched (fpdf, rpdf, delta) scalars of the others from the vertex buffer.  smp_*: the freshly sampled emitter vertex
-// that replaces light[0] for l == 1 (the e == 1 replacement of eye[0] by the lens sample changes nothing that is read).
-__device__ __forceinline__ float bdpt_mis_weight(const WfArgs& a, const BdArgs& b, size_t s, int e, int l,
+// fields, walks the pdf ratios and restores them; here the end points are the register copies the connection already holds
+// (E1 = eye[e-1], L1 = light[l-1]), of eye[e-2] / light[l-2] only position and type are fetched, and the walk reads each
+// remaining vertex's (fpdf, rpdf, delta) scalars once.  For l == 1 the freshly sampled emitter vertex (smp_*) stands in for
+// light[0]; for e == 1 the lens sample that replaces eye[0] changes nothing that is read (same position, fpdf = 1).
+__device__ __forceinline__ float bdpt_mis_weight(const WfArgs& a, const BdArgs& b, size_t s, int e, int l, const BV& Ein, const BV& Lin,
                                                  V3 smp_pos, V3 smp_normal, float smp_fpdf) {
     if (l + e == 2) return 1.0f;
-    BV E1, E2, L1, L2;
-    E1 = bv_load(b, s, e - 1);
-    if (e > 1) E2 = bv_load(b, s, e - 2); else E2 = E1;
-    if (l > 0) L1 = bv_load(b, s, BD_EYE_MAX + l - 1); else L1 = E1;
-    if (l > 1) L2 = bv_load(b, s, BD_EYE_MAX + l - 2); else L2 = L1;
-    if (l == 1) { L1.pos = smp_pos; L1.normal = smp_normal; L1.snormal = smp_normal; L1.fpdf = smp_fpdf; L1.type = BD_VERTEX_LIGHT; }
-    float e1_rpdf = E1.rpdf, e2_rpdf = E2.rpdf, l1_rpdf = L1.rpdf, l2_rpdf = L2.rpdf;
+    // end points: position, normals, type, material, fpdf
+    V3 E1pos, E1normal = mk3(0.f, 0.f, 0.f), E1snormal = E1normal; int E1type, E1mat = 0, E1prim = 0; float E1fpdf;
+    if (e == 1) { E1pos = mk3(a.cam.eye[0], a.cam.eye[1], a.cam.eye[2]); E1type = BD_VERTEX_LENS; E1fpdf = 1.0f; }
+    else { E1pos = Ein.pos; E1normal = Ein.normal; E1snormal = Ein.snormal; E1type = Ein.type; E1mat = Ein.mat; E1prim = Ein.prim; E1fpdf = Ein.fpdf; }
+    V3 L1pos = smp_pos, L1normal = smp_normal, L1snormal = smp_normal; int L1mat = 0; float L1fpdf = smp_fpdf;
+    if (l > 1) { L1pos = Lin.pos; L1normal = Lin.normal; L1snormal = Lin.snormal; L1mat = Lin.mat; L1fpdf = Lin.fpdf; }
+    V3 E2pos = E1pos, L2pos = L1pos; int E2type = 0, L2type = 0;
+    if (e > 1) { E2pos = f4xyz(b.vb[(size_t)((e - 2) * 5) * b.cap + s]); E2type = __float_as_int(((const float*)(b.vb + (size_t)((e - 2) * 5 + 2) * b.cap + s))[3]) & 15; }
+    if (l > 1) { const int v = BD_EYE_MAX + l - 2; L2pos = f4xyz(b.vb[(size_t)(v * 5) * b.cap + s]); L2type = __float_as_int(((const float*)(b.vb + (size_t)(v * 5 + 2) * b.cap + s))[3]) & 15; }
+    float e1_rpdf, e2_rpdf = 0.0f, l1_rpdf = 0.0f, l2_rpdf = 0.0f;
     const V3 axis = mk3(b.view[8], b.view[9], b.view[10]);                // Camera.get_optical_axis (Camera.py:128-129)
     // eye[e-1].rpdf (:290-316)
     if (l == 0) {
-        float pdfPos = 1.0f / __ldg(&a.shade[E1.prim].q[2].w), pdfChoice = 1.0f / (float)a.nl;
+        float pdfPos = 1.0f / __ldg(&a.shade[E1prim].q[2].w), pdfChoice = 1.0f / (float)a.nl;
         e1_rpdf = pdfPos * pdfChoice;
     } else if (l == 1) {
-        if (E1.type == BD_VERTEX_SURFACE) {
-            V3 to = E1.pos - L1.pos; float dist = length3(to); to = to / dist;
-            float c = fabsf(dot3(to, L1.normal));
+        if (E1type == BD_VERTEX_SURFACE) {
+            V3 to = E1pos - L1pos; float dist = length3(to); to = to / dist;
+            float c = fabsf(dot3(to, L1normal));
             e1_rpdf = cosine_hemisphere_pdf(c) * c / (dist * dist);
         } else e1_rpdf = 1.0f;
     } else {
-        V3 wi = L2.pos - L1.pos, wo = E1.pos - L1.pos; float dist = length3(wo);
+        V3 wi = L2pos - L1pos, wo = E1pos - L1pos; float dist = length3(wo);
         wi = normalize3(wi); wo = normalize3(wo);
         float pdf = 1.0f;
-        if (L1.mat == TR_MAT_DISNEY) { const float* m = a.material + (size_t)L1.mat * 10; pdf = disney_pdf(L1.snormal, wi, wo, __ldg(m + 5), __ldg(m + 6)); }   // material INDEX == 0 (sic, :312)
-        e1_rpdf = pdf * fabsf(dot3(L1.normal, wo)) / (dist * dist);
+        if (L1mat == TR_MAT_DISNEY) { const float* m = a.material + (size_t)L1mat * 10; pdf = disney_pdf(L1snormal, wi, wo, __ldg(m + 5), __ldg(m + 6)); }   // material INDEX == 0 (sic, :312)
+        e1_rpdf = pdf * fabsf(dot3(L1normal, wo)) / (dist * dist);
     }
     // light[l-1].rpdf (:317-343)
     if (l > 0) {
         if (e > 1) {
-            if (E1.type == BD_VERTEX_SURFACE) {
-                V3 wi = E2.pos - E1.pos, wo = L1.pos - E1.pos; float dist = length3(wo);
+            if (E1type == BD_VERTEX_SURFACE) {
+                V3 wi = E2pos - E1pos, wo = L1pos - E1pos; float dist = length3(wo);
                 wi = normalize3(wi); wo = normalize3(wo);
                 float pdf = 1.0f;
-                if (E1.mat == TR_MAT_DISNEY) { const float* m = a.material + (size_t)E1.mat * 10; pdf = disney_pdf(E1.snormal, wi, wo, __ldg(m + 5), __ldg(m + 6)); }
-                l1_rpdf = pdf * fabsf(dot3(E1.normal, wo)) / (dist * dist);
+                if (E1mat == TR_MAT_DISNEY) { const float* m = a.material + (size_t)E1mat * 10; pdf = disney_pdf(E1snormal, wi, wo, __ldg(m + 5), __ldg(m + 6)); }
+                l1_rpdf = pdf * fabsf(dot3(E1normal, wo)) / (dist * dist);
             } else l1_rpdf = 1.0f;
         } else {
-            V3 to = E1.pos - L1.pos; float dist = length3(to); to = to / dist;      // e == 1: eye[0] = the lens
+            V3 to = E1pos - L1pos; float dist = length3(to); to = to / dist;      // e == 1: eye[0] = the lens
             l1_rpdf = dot3(to, axis) / (dist * dist);
         }
     }
     // eye[e-2].rpdf (:345-369)
     if (e > 1) {
         if (l == 0) {
-            V3 to = E2.pos - E1.pos; float dist = length3(to); to = to / dist;
-            float pdfDir = cosine_hemisphere_pdf(fabsf(dot3(to, E1.normal)));
-            float LdotN = dot3(to, E1.normal);
+            V3 to = E2pos - E1pos; float dist = length3(to); to = to / dist;
+            float pdfDir = cosine_hemisphere_pdf(fabsf(dot3(to, E1normal)));
+            float LdotN = dot3(to, E1normal);
             e2_rpdf = fabsf(pdfDir * LdotN) / (dist * dist);
-        } else if (E1.type == BD_VERTEX_SURFACE) {
-            V3 wi = L1.pos - E1.pos, wo = E2.pos - E1.pos; float dist = length3(wo);
+        } else if (E1type == BD_VERTEX_SURFACE) {
+            V3 wi = L1pos - E1pos, wo = E2pos - E1pos; float dist = length3(wo);
             wi = normalize3(wi); wo = normalize3(wo);
-            const float* m = a.material + (size_t)E1.mat * 10;
-            float pdf = disney_pdf(E1.snormal, wi, wo, __ldg(m + 5), __ldg(m + 6));
+            const float* m = a.material + (size_t)E1mat * 10;
+            float pdf = disney_pdf(E1snormal, wi, wo, __ldg(m + 5), __ldg(m + 6));
             e2_rpdf = pdf / (dist * dist);
-            if (E2.type == BD_VERTEX_SURFACE) e2_rpdf *= fabsf(dot3(E1.normal, wo));
+            if (E2type == BD_VERTEX_SURFACE) e2_rpdf *= fabsf(dot3(E1normal, wo));
         } else e2_rpdf = 1.0f;
     }
     // light[l-2].rpdf (:371-388)
     if (l > 1) {
-        if (E1.type != BD_VERTEX_LIGHT) {
-            V3 wi = E1.pos - L1.pos, wo = L2.pos - L1.pos; float dist = length3(wo);
+        if (E1type != BD_VERTEX_LIGHT) {
+            V3 wi = E1pos - L1pos, wo = L2pos - L1pos; float dist = length3(wo);
             wi = normalize3(wi); wo = normalize3(wo);
             float pdf = 1.0f;
-            if (L1.mat == TR_MAT_DISNEY) { const float* m = a.material + (size_t)L1.mat * 10; pdf = disney_pdf(L1.normal, wi, wo, __ldg(m + 5), __ldg(m + 6)); }
+            if (L1mat == TR_MAT_DISNEY) { const float* m = a.material + (size_t)L1mat * 10; pdf = disney_pdf(L1normal, wi, wo, __ldg(m + 5), __ldg(m + 6)); }
             l2_rpdf = pdf / (dist * dist);
-            if (L2.type == BD_VERTEX_SURFACE) l2_rpdf *= fabsf(dot3(L1.normal, wo));
+            if (L2type == BD_VERTEX_SURFACE) l2_rpdf *= fabsf(dot3(L1normal, wo));
         } else l2_rpdf = 1.0f;
     }
-    // the walks (:394-416); delta of eye[e-1] and light[l-1] is forced to 0 (:283-286)
+    // the walks (:394-416); delta of eye[e-1] and light[l-1] is forced to 0 (:283-286); delta of eye[0] (lens) and light[0] is 0
     float weight_sum = 0.0f, weight = 1.0f;
-    int dk = 0;                                                           // delta of vertex k (from the previous iteration: k+1 -> k)
+    int d_above = 0;                                                      // delta of vertex k (k = e-1 first)
     for (int k = e - 1; k > 0; --k) {
-        float f, r; int d0, d1;
-        if (k == e - 1) { f = E1.fpdf; r = e1_rpdf; d0 = 0; }
-        else { bv_scalars(b, s, k, f, r, d0); d0 = dk; if (k == e - 2) r = e2_rpdf; }
-        { float f1, r1; bv_scalars(b, s, k - 1, f1, r1, d1); }
+        float f, r; int d_below = 0;
+        if (k == e - 1) { f = E1fpdf; r = e1_rpdf; }
+        else { f = ((const float*)(b.vb + (size_t)(k * 5) * b.cap + s))[3]; r = (k == e - 2) ? e2_rpdf : ((const float*)(b.vb + (size_t)(k * 5 + 1) * b.cap + s))[3]; }
+        if (k - 1 > 0) d_below = (__float_as_int(((const float*)(b.vb + (size_t)((k - 1) * 5 + 2) * b.cap + s))[3]) >> 4) & 15;
         weight *= (r == 0.0f ? 1.0f : r) / (f == 0.0f ? 1.0f : f);
-        if (d0 == 0 && d1 == 0) weight_sum += weight;
-        dk = d1;
+        if (d_above == 0 && d_below == 0) weight_sum += weight;
+        d_above = d_below;
     }
-    weight = 1.0f; dk = 0;
+    weight = 1.0f; d_above = 0;
     for (int k = l - 1; k >= 0; --k) {
-        float f, r; int d0, d1 = 0;
-        if (k == l - 1) { f = L1.fpdf; r = l1_rpdf; d0 = 0; }
-        else { bv_scalars(b, s, BD_EYE_MAX + k, f, r, d0); d0 = dk; if (k == l - 2) r = l2_rpdf; }
-        if (k > 0) { float f1, r1; bv_scalars(b, s, BD_EYE_MAX + k - 1, f1, r1, d1); }
+        float f, r; int d_below = 0;
+        const int v = BD_EYE_MAX + k;
+        if (k == l - 1) { f = L1fpdf; r = l1_rpdf; }
+        else { f = ((const float*)(b.vb + (size_t)(v * 5) * b.cap + s))[3]; r = (k == l - 2) ? l2_rpdf : ((const float*)(b.vb + (size_t)(v * 5 + 1) * b.cap + s))[3]; }
+        if (k - 1 > 0) d_below = (__float_as_int(((const float*)(b.vb + (size_t)((v - 1) * 5 + 2) * b.cap + s))[3]) >> 4) & 15;
         weight *= (r == 0.0f ? 1.0f : r) / (f == 0.0f ? 1.0f : f);
-        if (d0 == 0 && d1 == 0) weight_sum += weight;
-        dk = d1;
+        if (d_above == 0 && d_below == 0) weight_sum += weight;
+        d_above = d_below;
     }
     return 1.0f / (1.0f + weight_sum);
 }
@@ -404,7 +409,7 @@ __device__ __forceinline__ void bd_connect_finish(const WfArgs& a, const BdArgs&
             }
         }
     }
-    if (radiance.x > 0.0f && radiance.y > 0.0f && radiance.z > 0.0f) radiance = radiance * bdpt_mis_weight(a, b, s, e, l, smp_pos, smp_normal, smp_fpdf);
+    if (radiance.x > 0.0f && radiance.y > 0.0f && radiance.z > 0.0f) radiance = radiance * bdpt_mis_weight(a, b, s, e, l, ev, lv, smp_pos, smp_normal, smp_fpdf);
     if (e == 1) {
         if (c.nu >= 0 && (radiance.x != 0.0f || radiance.y != 0.0f || radiance.z != 0.0f)) {
             float* o = b.splat + ((size_t)(s / (size_t)a.npix) * a.W * a.H + (size_t)c.nu * a.H + c.nv) * 3;
@@ -520,7 +525,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_bdpt_connect_gen(WfArgs a, BdArg
     }
 }
 // one thread per connection: geometry again (cheaper than spilling BdConn to HBM), the query result, BSDF terms + MIS
-__global__ void __launch_bounds__(WF_THREADS) k_bdpt_connect_eval(WfArgs a, BdArgs b) {
+__global__ void __launch_bounds__(WF_THREADS, 3) k_bdpt_connect_eval(WfArgs a, BdArgs b) {
     const BatchParams bp = *a.bp;
     const int n = (int)b.ctr[2];
     const int stride = gridDim.x * blockDim.x;
