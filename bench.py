@@ -180,14 +180,15 @@ def run_native(args, wl):
     integ, cam = ex.integrator, ex.cam
     spp = wl["spp"]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:%d" % local)     # > 126 MB L2
+    film = parallel.film_tensor(ctx)            # torch view of the device film (zero copy), made once
 
     def one_step():
         ctx.film_clear(); cam.frame = 0; cam.frame_cpu[0] = 0
-        st = integ.render_frames(spp)
+        integ.render_frames(spp, stats=False)           # asynchronous: the film reduce is enqueued right behind the last kernel
         if world > 1:
             with torch.cuda.stream(stream):
-                parallel.reduce_film(parallel.film_tensor(ctx), dst=0)
-        return st
+                parallel.reduce_film(film, dst=0)
+        return ctx.stats()
 
     for _ in range(args.warmup):
         one_step()
@@ -243,7 +244,7 @@ def run_native(args, wl):
         cam.dirty = True
         ctx.film_clear(); cam.frame = 0; cam.frame_cpu[0] = 0
         tb = time.perf_counter()
-        st2 = integ.render_frames(spp)
+        integ.render_frames(spp, stats=False)
         tc = time.perf_counter()
         if world > 1:
             with torch.cuda.stream(stream):
@@ -252,9 +253,10 @@ def run_native(args, wl):
         hdr_host, rgb_host = ctx.film_download(True, True)
         torch.cuda.synchronize(local)
         dt = time.perf_counter() - t0
+        st2 = ctx.stats()
         if args.verbose and rank == 0:
-            print("e2e pass %d: upload+build %.2f ms, normals %.2f, render %.2f (device %.2f), reduce+tonemap+download %.2f" %
-                  (k, (ta - t0) * 1e3, (tb - ta) * 1e3, (tc - tb) * 1e3, st2["ms_total"], (time.perf_counter() - tc) * 1e3), file=sys.stderr)
+            print("e2e pass %d: upload+build %.2f ms, normals %.2f, render enqueue %.2f (device %.2f), reduce+tonemap+download (incl. waiting for the render) %.2f" %
+                  (k, (ta - t0) * 1e3, (tb - ta) * 1e3, (tc - tb) * 1e3, st2["ms_total"], (t0 + dt - tc) * 1e3), file=sys.stderr)
         if k > 0:                                # first pass is warm-up (graph re-capture after the rebuild)
             e2e_t += dt; e2e_rays += int(st2["rays_closest"]) + int(st2["rays_shadow"])
     if world > 1:

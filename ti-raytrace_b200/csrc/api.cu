@@ -59,6 +59,7 @@ void tr_ctx_destroy(tr_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+    if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
     void* ptrs[] = {ctx->d_vertex, ctx->d_prim, ctx->d_material, ctx->d_shape, ctx->d_light, ctx->d_env,
                     ctx->d_morton_unsorted, ctx->d_keys[0], ctx->d_keys[1], ctx->d_vals[0], ctx->d_vals[1],
                     ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_boxes, ctx->d_leafcount, ctx->d_flag, ctx->d_pre,
@@ -215,6 +216,7 @@ int tr_set_option(tr_ctx* ctx, const char* name, int value) {
     else if (!strcmp(name, "chains")) ctx->opt_chains = value;
     else if (!strcmp(name, "shadow_overlap")) ctx->opt_shadow_overlap = value;
     else if (!strcmp(name, "tail_max")) ctx->opt_tail_max = value;
+    else if (!strcmp(name, "tail_chunk")) ctx->opt_tail_chunk = value;
     else if (!strcmp(name, "bdpt_wavefront")) ctx->opt_bdpt_wavefront = value;
     else if (!strcmp(name, "max_paths")) ctx->opt_max_paths = (size_t)value;
     else return tr_fail(ctx, TR_ERR_INVALID, "tr_set_option: unknown option '%s'", name);
@@ -225,6 +227,7 @@ int tr_set_option(tr_ctx* ctx, const char* name, int value) {
 
 int tr_stats_get(tr_ctx* ctx, tr_stats* out) {
     if (!ctx || !out) return TR_ERR_INVALID;
+    int rc = tr_stats_resolve(ctx); if (rc) return rc;
     *out = ctx->stats;
     return TR_OK;
 }

@@ -572,6 +572,7 @@ static int render_bdpt(tr_ctx* ctx, int frame_begin, int n_frames, uint64_t seed
     if (!ctx || n_frames <= 0 || frame_begin < 0) return tr_fail(ctx, TR_ERR_INVALID, "tr_render_bdpt_rgb: bad arguments (frames %d+%d)", frame_begin, n_frames);
     TR_CUDA(ctx, cudaSetDevice(ctx->device));
     WfArgs a; int rc;
+    if ((rc = tr_stats_resolve(ctx))) return rc;
     if ((rc = fill_args(ctx, a, false))) return rc;
     if (ctx->nl <= 0) return tr_fail(ctx, TR_ERR_INVALID, "tr_render_bdpt_rgb: the scene has no emitter (Scene.sample_light needs one)");
     const bool wave = ctx->opt_bdpt_wavefront != 0;

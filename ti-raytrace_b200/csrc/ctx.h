@@ -98,6 +98,8 @@ struct tr_ctx {
     float4* d_L = nullptr; float4* d_Lnee = nullptr;          // per-sample radiance: terminal term, NEE sum
     TrCounters* d_ctr = nullptr;          // TR_MAX_CHAINS entries
     TrCounters h_ctr[TR_MAX_CHAINS];
+    // deferred statistics of an asynchronous render: per-batch counter snapshots land in a pinned ring, tr_stats_get folds them
+    TrCounters* h_ring = nullptr; int ring_batches = 0, ring_K = 0, ring_depth = 0; bool stats_pending = false;
     float4* d_matlin = nullptr; bool matlin_ready = false;
     cudaStream_t sub_stream[TR_MAX_CHAINS] = {}; cudaEvent_t ev_join[TR_MAX_CHAINS] = {}; cudaEvent_t ev_fork = nullptr;
 
@@ -120,9 +122,10 @@ struct tr_ctx {
     int opt_stage_timing = 0;
     int opt_graph = 1;
     int opt_smem_bvh = 1;
-    int opt_chains = 4;
+    int opt_chains = 2;
     int opt_shadow_overlap = 1;
     int opt_tail_max = 16384;
+    int opt_tail_chunk = 8;
     int opt_bdpt_wavefront = 1;     // 0: lock-step BDPT pipeline (cross-check)
     size_t opt_max_paths = (size_t)20 << 20;   // path slots per batch (188 B each): more paths in flight amortise the per-stage tails
 
@@ -166,4 +169,6 @@ template <typename T> static inline int tr_realloc(tr_ctx* ctx, T** p, size_t co
 // implemented across the .cu files
 int tr_build_shade_table(tr_ctx* ctx);
 int tr_build_tiles(tr_ctx* ctx);
-int tr_spec_prepare(tr_ctx* ctx);      // spectral.cu: checks the PT_Spec tables and builds the per-material coefficient table
+int tr_spec_prepare(tr_ctx* ctx);
+int tr_stats_resolve(tr_ctx* ctx);     // wavefront.cu: wait for the last asynchronous render and fold its counters into ctx->stats
+#define TR_RING_BATCHES 64      // spectral.cu: checks the PT_Spec tables and builds the per-material coefficient table

@@ -41,6 +41,7 @@ struct WfArgs {
     TrCounters* ctr;
     const BatchParams* bp;
     int tail_max;                                  // hand the chain to k_tail once its live paths drop to this (0 = never)
+    int tail_chunk;                                // k_tail: at least this many paths per warp
     int frame_off, sub_frames;                     // this chain renders local frames [frame_off, frame_off + sub_frames) of the batch
     unsigned smem_nodes_bytes, smem_leaves_bytes, smem_next_bytes;
     SpecDev spec;                                  // tables of the spectral integrator (PT_Spec), zero for PT_RGB
@@ -576,55 +577,125 @@ __global__ void __launch_bounds__(WF_THREADS, SPEC ? 3 : WF_SHADE_MIN_BLOCKS) k_
 // ------------------------------------------------------------------ tail (megakernel for the last few paths)
 // Deep bounces carry a tiny fraction of the rays (C3: 1.7 % beyond depth 2) but every wavefront stage pays the latency
 // of its slowest ray (~0.1-0.2 ms for a 1000-node walk), 3 stages x 13 depths.  Once a chain's live-path count drops to
-// tail_max, this kernel takes the remaining paths and runs them to completion, one path per lane: closest hit, shade,
-// shadow ray, next bounce, all in registers.  Same device functions, same per-path operation order (NEE terms are added
-// to Lnee in depth order, after shadow(depth-1) of the wavefront: the kernel is enqueued behind it), so the film is
-// bit-identical with or without the hand-over.
+// tail_max, this kernel takes the remaining paths and runs them to completion in registers.  Every lane is its own state
+// machine (closest-hit walk -> shade -> shadow walk -> next bounce ...): a lane never waits for the other lanes' walks, so a
+// path costs the sum of ITS OWN walk latencies instead of the per-bounce maximum over a warp -- what matters when a rank of
+// an 8-GPU run is left with a few thousand paths and nothing else to overlap them with.  Paths are dealt out a few per warp
+// (n / #warps) so that all resident warps work.  Same device functions and the same per-path operation order as the
+// wavefront stages (NEE terms are added to Lnee in depth order, after shadow(depth-1): the kernel is enqueued behind it),
+// so the film is bit-identical with or without the hand-over.
 template <bool SMEM, bool SPEC>
 __global__ void __launch_bounds__(WF_THREADS) k_tail(WfArgs a, int depth) {
     if (a.ctr->tail_from != depth) return;
     const TrNode* nodes; const TrLeaf* leaves; const TrNodeX* nodesx;
     bvh_view<SMEM>(a, nodes, leaves, nodesx);
     const BatchParams bp = *a.bp;
-    const int n = a.ctr->nq[depth], pp = depth & 1;
+    const int n = a.ctr->nq[depth], pp = depth & 1, nnodes = a.nnodes;
     const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int chunk = min(32, max(a.tail_chunk, (n + nwarps - 1) / nwarps));
+    int* cursor = &a.ctr->wf_trace[TR_MAX_DEPTH_CAP];                  // free slot: stage cursors use [0, max_depth)
     unsigned long long n_closest = 0, n_shadow = 0;
-    for (int base = warp * 32; base < n; base += nwarps * 32) {
-        const int q = base + lane;
-        bool alive = q < n;
-        float4 A = make_float4(0.f, 0.f, 0.f, 1.f), B = make_float4(1.f, 1.f, 1.f, 0.f), C = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (alive) { A = a.pa[pp][q]; B = a.pb[pp][q]; C = a.pc[pp][q]; }
-        for (int d = depth; d < bp.max_depth; ++d) {
-            if (__ballot_sync(0xffffffffu, alive) == 0u) break;
-            RayPre r = make_ray(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y));
-            HitRec h = trace_closest<SMEM>(nodes, leaves, nodesx, a.nnodes, r, alive, a.ctr->visits);
-            ShadeOut o; o.cont = false; o.shadow = false;
-            if (alive) {
+#ifdef TR_COUNTERS
+    unsigned long long cnt[4] = {0, 0, 0, 0};
+#endif
+    int mode = 0, d = depth;                                           // 0 idle, 1 closest-hit walk, 2 shadow walk
+    float4 A = make_float4(0.f, 0.f, 0.f, 1.f), B = make_float4(1.f, 1.f, 1.f, 0.f), C = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 nA = A, nB = B, nC = C, sC = C; bool st_cont = false; unsigned sslot = 0;
+    RayPre r = make_ray(mk3(0.f, 0.f, 0.f), mk3(1.f, 1.f, 1.f)); bool anypar = false;
+    int idx = nnodes, pend = -1, tleaf = 0; bool visible = false, found = false; float tt = TR_INF;
+    HitRec h; h.t = TR_INF; h.u = h.v = 0.0f; h.prim = -1; h.mat = 0; h.leaf = -1;
+    bool more = true;
+    while (true) {
+        if (__ballot_sync(0xffffffffu, mode != 0) == 0u) {
+            if (!more) break;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(cursor, chunk);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= n) break;
+            if (base + chunk >= n) more = false;
+            const int q = base + lane;
+            if (lane < chunk && q < n) {
+                A = a.pa[pp][q]; B = a.pb[pp][q]; C = a.pc[pp][q]; d = depth; mode = 1;
+                r = make_ray(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y)); anypar = r.px || r.py || r.pz;
+                h.t = TR_INF; h.u = h.v = 0.0f; h.prim = -1; h.mat = 0; h.leaf = -1; idx = 0; pend = -1;
+            }
+        }
+        // ---- node steps (same code for internal nodes and leaves, as in k_trace / k_shadow)
+#pragma unroll
+        for (int step = 0; step < WF_NODE_STEPS; ++step) {
+            if (mode != 0 && pend < 0 && idx < nnodes) {
+                float4 lo, hi; int esc;
+                if (SMEM) { lo = nodes[idx].lo; hi = nodes[idx].hi; esc = __float_as_int(lo.w); }
+                else { const TrNodeX* nd = nodesx + idx; lo = nd->lo; hi = nd->hi; esc = nd->next[r.oct]; }
+                const int link = __float_as_int(hi.w);
+                const float bound = (mode == 1) ? h.t : tt;
+                float tmin;
+                const bool hit = (anypar ? slabs(r, lo, hi, tmin) : slabs_fast(r, lo, hi, tmin)) && !(tmin > bound * TR_PRUNE_GUARD);
+                if (link < 0) {
+                    const int k = -link - 1;
+                    if (mode == 2 && k == tleaf) found = true; else if (hit) pend = k;
+                }
+#ifdef TR_COUNTERS
+                else ++cnt[mode == 1 ? 0 : 2];
+#endif
+                idx = next_node<!SMEM>(idx, link, hit, esc, r.oct);
+            }
+        }
+        // ---- leaf step
+        if (mode != 0 && pend >= 0) {
+            const TrLeaf* lf = leaves + pend;
+            float4 la = lf->a, lb = lf->b, lc = lf->c;
+            float u, v, t = intersect_leaf(r, la, lb, lc, u, v);
+#ifdef TR_COUNTERS
+            ++cnt[mode == 1 ? 1 : 3];
+#endif
+            if (mode == 1) { if (closer(t, pend, h.t, h.leaf)) { h.t = t; h.u = u; h.v = v; h.prim = __float_as_int(la.w); h.mat = __float_as_int(lc.w); h.leaf = pend; } }
+            else if (t > 0.0f && t < TR_INF && (t < tt || (t == tt && pend > tleaf))) { visible = false; idx = nnodes; }
+            pend = -1;
+        }
+        // ---- a finished walk: shade / add the NEE term, then start the lane's next walk
+        if (mode != 0 && pend < 0 && idx >= nnodes) {
+            bool advance = true;
+            if (mode == 1) {
                 ++n_closest;
                 int cl = 0;
                 if (h.prim >= 0) {
                     int mt = (int)__ldg(a.material + (size_t)h.mat * 10);
                     cl = (mt == TR_MAT_LIGHT) ? 0 : (mt == TR_MAT_GLASS ? 2 : 1);
                 }
+                ShadeOut o; o.cont = false; o.shadow = false;
                 shade_any<SPEC>(a, bp, d, cl, A, B, C, make_float4(h.t, __int_as_float(h.prim), h.u, h.v), o);
-            }
-            const bool sh = alive && o.shadow;
-            if (__ballot_sync(0xffffffffu, sh) != 0u) {
-                RayPre rs = make_ray(mk3(o.sA.x, o.sA.y, o.sA.z), mk3(o.sA.w, o.sB.x, o.sB.y));
-                int tleaf = sh ? __ldg(a.leaf_of_prim + __float_as_int(o.sB.z)) : 0;
-                bool vis = trace_shadow_visible<SMEM>(nodes, leaves, nodesx, a.nnodes, rs, sh, tleaf, a.ctr->visits + 2);
-                if (sh) {
+                st_cont = o.cont; nA = o.nA; nB = o.nB; nC = o.nC;
+                if (o.shadow) {
                     ++n_shadow;
-                    if (vis) { unsigned slot = __float_as_uint(o.sB.w); float4 Lv = a.Lnee[slot]; Lv.x += o.sC.x; Lv.y += o.sC.y; Lv.z += o.sC.z; Lv.w += o.sC.w; a.Lnee[slot] = Lv; }
+                    r = make_ray(mk3(o.sA.x, o.sA.y, o.sA.z), mk3(o.sA.w, o.sB.x, o.sB.y)); anypar = r.px || r.py || r.pz;
+                    tleaf = __ldg(a.leaf_of_prim + __float_as_int(o.sB.z)); sslot = __float_as_uint(o.sB.w); sC = o.sC;
+                    const TrLeaf* lf = leaves + tleaf;
+                    float u, v; tt = intersect_leaf(r, lf->a, lf->b, lf->c, u, v);
+#ifdef TR_COUNTERS
+                    ++cnt[3];
+#endif
+                    visible = (tt > 0.0f && tt < TR_INF); found = false;
+                    idx = visible ? 0 : nnodes; pend = -1; mode = 2; advance = false;
                 }
+            } else if (visible && found) {
+                float4 Lv = a.Lnee[sslot]; Lv.x += sC.x; Lv.y += sC.y; Lv.z += sC.z; Lv.w += sC.w; a.Lnee[sslot] = Lv;
             }
-            alive = alive && o.cont;
-            if (alive) { A = o.nA; B = o.nB; C = o.nC; }
+            if (advance) {
+                if (st_cont) {
+                    A = nA; B = nB; C = nC; ++d; mode = 1; st_cont = false;
+                    r = make_ray(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y)); anypar = r.px || r.py || r.pz;
+                    h.t = TR_INF; h.u = h.v = 0.0f; h.prim = -1; h.mat = 0; h.leaf = -1; idx = 0; pend = -1;
+                } else mode = 0;
+            }
         }
     }
     if (n_closest) atomicAdd(&a.ctr->tail_rays[0], n_closest);
     if (n_shadow) atomicAdd(&a.ctr->tail_rays[1], n_shadow);
+#ifdef TR_COUNTERS
+    for (int k = 0; k < 4; ++k) if (cnt[k]) atomicAdd(a.ctr->visits + k, cnt[k]);
+#endif
 }
 
 // ------------------------------------------------------------------ shadow
@@ -852,7 +923,7 @@ static int fill_args(tr_ctx* ctx, WfArgs& a, bool spec = false) {
     for (int k = 0; k < 2; ++k) { a.sa[k] = ctx->d_shq[k][0]; a.sb[k] = ctx->d_shq[k][1]; a.sc[k] = ctx->d_shq[k][2]; }
     a.L = ctx->d_L; a.Lnee = ctx->d_Lnee;
     a.ctr = ctx->d_ctr; a.bp = (const BatchParams*)ctx->d_batch_params;
-    a.frame_off = 0; a.sub_frames = 1 << 20; a.tail_max = ctx->opt_tail_max;
+    a.frame_off = 0; a.sub_frames = 1 << 20; a.tail_max = ctx->opt_tail_max; a.tail_chunk = ctx->opt_tail_chunk < 1 ? 1 : ctx->opt_tail_chunk;
     a.smem_nodes_bytes = (unsigned)((size_t)a.nnodes * sizeof(TrNode));
     a.smem_leaves_bytes = (unsigned)((size_t)a.nleaves * sizeof(TrLeaf));
     a.smem_next_bytes = (unsigned)((size_t)a.nnodes * 8 * sizeof(int));
@@ -873,7 +944,7 @@ static int ensure_wavefront(tr_ctx* ctx, size_t slots) {
     return TR_OK;
 }
 
-struct LaunchCfg { int grid_trace, grid_shadow, grid_simple; size_t smem; bool use_smem; };   // memset before use (compared bytewise)
+struct LaunchCfg { int grid_trace, grid_shadow, grid_simple, grid_tail[2]; size_t smem; bool use_smem; };   // grid_tail[SPEC]   // memset before use (compared bytewise)
 
 static int launch_cfg(tr_ctx* ctx, const WfArgs& a, LaunchCfg& c) {
     size_t bytes = (size_t)a.smem_nodes_bytes + a.smem_leaves_bytes;
@@ -892,6 +963,15 @@ static int launch_cfg(tr_ctx* ctx, const WfArgs& a, LaunchCfg& c) {
         TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_shadow<false>, WF_THREADS, 0));
     }
     if (bt < 1) bt = 1; if (bs < 1) bs = 1;
+    int t0 = 0, t1 = 0;        // the tail kernel deals its paths over the warps that are resident at once
+    if (c.use_smem) {
+        TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t0, k_tail<true, false>, WF_THREADS, c.smem));
+        TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t1, k_tail<true, true>, WF_THREADS, c.smem));
+    } else {
+        TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t0, k_tail<false, false>, WF_THREADS, 0));
+        TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t1, k_tail<false, true>, WF_THREADS, 0));
+    }
+    c.grid_tail[0] = ctx->num_sms * (t0 < 1 ? 1 : t0); c.grid_tail[1] = ctx->num_sms * (t1 < 1 ? 1 : t1);
     c.grid_trace = ctx->num_sms * bt; c.grid_shadow = ctx->num_sms * bs;
     c.grid_simple = ctx->num_sms * 8;
     return TR_OK;
@@ -937,8 +1017,8 @@ static int enqueue_chain(tr_ctx* ctx, const WfArgs& a, const LaunchCfg& c, int m
         if (a.tail_max > 0 && d + 1 < max_depth) {
             // behind shadow(d) on the same stream: NEE terms stay in depth order; shade(d) (the hand-over decision) is done
             if (split && a.nl == 0) { TR_CUDA(ctx, cudaEventRecord(dep[2 * d], s)); TR_CUDA(ctx, cudaStreamWaitEvent(ss, dep[2 * d], 0)); }
-            if (c.use_smem) k_tail<true, SPEC><<<c.grid_trace, WF_THREADS, c.smem, ss>>>(a, d + 1);
-            else k_tail<false, SPEC><<<c.grid_trace, WF_THREADS, 0, ss>>>(a, d + 1);
+            if (c.use_smem) k_tail<true, SPEC><<<c.grid_tail[SPEC], WF_THREADS, c.smem, ss>>>(a, d + 1);
+            else k_tail<false, SPEC><<<c.grid_tail[SPEC], WF_THREADS, 0, ss>>>(a, d + 1);
             ++*launches;
         }
         if (ev) cudaEventRecord(ev[4 * d + 3], s);
@@ -985,8 +1065,10 @@ static int render_wavefront(tr_ctx* ctx, int frame_begin, int n_frames, int max_
         return tr_fail(ctx, TR_ERR_INVALID, "%s: bad arguments (frames %d+%d, depth %d)", SPEC ? "tr_render_pt_spec" : "tr_render_pt_rgb", frame_begin, n_frames, max_depth);
     TR_CUDA(ctx, cudaSetDevice(ctx->device));
     WfArgs a; int rc;
+    if ((rc = tr_stats_resolve(ctx))) return rc;                        // an earlier asynchronous render still owns ev0 / ev1 / the ring
+    if (!ctx->h_ring) TR_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_ring, sizeof(TrCounters) * TR_MAX_CHAINS * TR_RING_BATCHES, cudaHostAllocDefault));
     if ((rc = fill_args(ctx, a, SPEC))) return rc;
-    if (a.npix == 0) { ctx->stats.frames = n_frames; return TR_OK; }    // this rank owns no tile
+    if (a.npix == 0) { memset(&ctx->stats, 0, sizeof(ctx->stats)); ctx->stats.frames = n_frames; return TR_OK; }    // this rank owns no tile
     // frames per batch: enough paths in flight to fill the chip a few times, bounded by max_paths
     int F = ctx->opt_batch_frames;
     if (F <= 0) { F = (int)(ctx->opt_max_paths / (size_t)a.npix); if (F < 1) F = 1; }     // auto: as many frames per batch as the path budget allows
@@ -1046,7 +1128,16 @@ static int render_wavefront(tr_ctx* ctx, int frame_begin, int n_frames, int max_
         } else {
             if ((rc = enqueue_batch<SPEC>(ctx, a, cfg, max_depth, K, fs, s, &launches, timing ? ctx->stage_ev.data() : nullptr))) return rc;
         }
-        // ray counters of this batch = queue sizes (device counters)
+        // ray counters of this batch = queue sizes (device counters).  Asynchronous mode: snapshot into the pinned ring and go
+        // on (no host round trip between batches or before whatever the caller enqueues next, e.g. the NCCL film reduce);
+        // tr_stats_get folds the snapshots.  Stage timing needs the events of this batch, so it stays synchronous.
+        const int bi = f0 / F;
+        if (!timing && bi < TR_RING_BATCHES) {
+            TR_CUDA(ctx, cudaMemcpyAsync(ctx->h_ring + (size_t)bi * TR_MAX_CHAINS, ctx->d_ctr, sizeof(TrCounters) * K, cudaMemcpyDeviceToHost, s));
+            ctx->ring_batches = bi + 1;
+            if (bi + 1 == TR_RING_BATCHES && f0 + F < n_frames) TR_CUDA(ctx, cudaStreamSynchronize(s));     // ring full: later batches fall back to the synchronous path
+            continue;
+        }
         TR_CUDA(ctx, cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(TrCounters) * K, cudaMemcpyDeviceToHost, s));
         TR_CUDA(ctx, cudaStreamSynchronize(s));
         for (int j = 0; j < K; ++j) {
@@ -1062,12 +1153,33 @@ static int render_wavefront(tr_ctx* ctx, int frame_begin, int n_frames, int max_
         }
     }
     TR_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
-    TR_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
-    float ms = 0.0f; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->stats.rays_closest = rays_c; ctx->stats.rays_shadow = rays_s;
     ctx->stats.node_visits = vis[0]; ctx->stats.leaf_tests = vis[1]; ctx->stats.node_visits_shadow = vis[2]; ctx->stats.leaf_tests_shadow = vis[3];
-    ctx->stats.kernel_launches = launches; ctx->stats.ms_total = ms; ctx->stats.frames = n_frames; ctx->stats.paths_in_flight = (int)((size_t)F * a.npix); ctx->stats.chains = K;
+    ctx->stats.kernel_launches = launches; ctx->stats.ms_total = 0.0f; ctx->stats.frames = n_frames; ctx->stats.paths_in_flight = (int)((size_t)F * a.npix); ctx->stats.chains = K;
     ctx->stats.ms_trace = ms_trace; ctx->stats.ms_shade = ms_shade; ctx->stats.ms_shadow = ms_shadow;
+    ctx->ring_K = K; ctx->ring_depth = max_depth; ctx->stats_pending = true;
+    if (timing) return tr_stats_resolve(ctx);
+    return TR_OK;
+}
+
+// Wait for the last render (its ev1) and fold the per-batch counter snapshots into ctx->stats.
+int tr_stats_resolve(tr_ctx* ctx) {
+    if (!ctx->stats_pending) return TR_OK;
+    TR_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    ctx->stats_pending = false;
+    uint64_t rays_c = 0, rays_s = 0, vis[4] = {0, 0, 0, 0};
+    for (int b = 0; b < ctx->ring_batches; ++b) for (int j = 0; j < ctx->ring_K; ++j) {
+        const TrCounters& c = ctx->h_ring[(size_t)b * TR_MAX_CHAINS + j];
+        const int tf = c.tail_from;
+        for (int d = 0; d < ctx->ring_depth; ++d) { if (tf == 0 || d != tf) rays_c += (uint64_t)c.nq[d]; rays_s += (uint64_t)c.nshadow[d]; }
+        rays_c += c.tail_rays[0]; rays_s += c.tail_rays[1];
+        for (int k = 0; k < 4; ++k) vis[k] += c.visits[k];
+    }
+    ctx->ring_batches = 0;
+    ctx->stats.rays_closest += rays_c; ctx->stats.rays_shadow += rays_s;
+    ctx->stats.node_visits += vis[0]; ctx->stats.leaf_tests += vis[1]; ctx->stats.node_visits_shadow += vis[2]; ctx->stats.leaf_tests_shadow += vis[3];
+    float ms = 0.0f; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->stats.ms_total = ms;
     return TR_OK;
 }
 
@@ -1082,6 +1194,7 @@ extern "C" int tr_render_debug(tr_ctx* ctx) {
     if (!ctx) return TR_ERR_INVALID;
     TR_CUDA(ctx, cudaSetDevice(ctx->device));
     WfArgs a; int rc;
+    if ((rc = tr_stats_resolve(ctx))) return rc;
     if ((rc = fill_args(ctx, a))) return rc;
     TR_CUDA(ctx, cudaMemsetAsync(ctx->d_ctr, 0, sizeof(TrCounters), ctx->stream));
     k_debug<<<cdiv(ctx->W * ctx->H, 128), 128, 0, ctx->stream>>>(a, ctx->d_fh);

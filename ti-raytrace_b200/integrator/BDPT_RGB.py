@@ -39,8 +39,8 @@ class BDPT:
     def render(self):
         self._prepare().render_bdpt_rgb(self.cam.frame, 1, self.seed)
 
-    def render_frames(self, n_frames):
+    def render_frames(self, n_frames, stats=True):
         ctx = self._prepare()
         ctx.render_bdpt_rgb(self.cam.frame, n_frames, self.seed)
         self.cam.update_frame(n_frames)
-        return ctx.stats()
+        return ctx.stats() if stats else None      # stats() waits for the (asynchronous) render

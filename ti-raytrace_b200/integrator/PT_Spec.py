@@ -72,8 +72,8 @@ class PathTrace:
     def render(self):
         self._prepare().render_pt_spec(self.cam.frame, 1, self.max_depth, self.seed)
 
-    def render_frames(self, n_frames):
+    def render_frames(self, n_frames, stats=True):
         ctx = self._prepare()
         ctx.render_pt_spec(self.cam.frame, n_frames, self.max_depth, self.seed)
         self.cam.update_frame(n_frames)
-        return ctx.stats()
+        return ctx.stats() if stats else None      # stats() waits for the (asynchronous) render
