@@ -15,7 +15,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, all_ranks):
+def _worker(rank, world, port, all_ranks, bdpt=False):
     for p in (PKG, ROOT):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -31,12 +31,24 @@ def _worker(rank, world, port, all_ranks):
     s = oracle.OracleScene(t).build()
     cam = oracle.fit_camera(t, W, H)
     s.set_camera(cam[1], cam[2], *cam[3:])
-    part, _ = s.render_pt_rgb(W, H, 0, 2, seed=3, mask=parallel.tile_mask(W, H, rank, world))
+    if bdpt:
+        # BDPT: a rank traces only its tiles' paths but its light-tracing splats land on ANY pixel, so every rank's film is
+        # dense and the exchange has to be a sum (SURVEY 8e "Exception"); float summation order differs -> allclose
+        s.set_camera_view(cam[0], W, H)
+        part, _ = s.render_bdpt_rgb(W, H, 0, 2, seed=3, mask=parallel.tile_mask(W, H, rank, world))
+        foreign = part[~parallel.tile_mask(W, H, rank, world)]
+        assert foreign.any(), "no splat crossed a tile boundary: the test would not exercise the sum"
+    else:
+        part, _ = s.render_pt_rgb(W, H, 0, 2, seed=3, mask=parallel.tile_mask(W, H, rank, world))
     film = torch.from_numpy(part)
     parallel.reduce_film(film, dst=0, all_ranks=all_ranks)
     if rank == 0 or all_ranks:
-        full, _ = s.render_pt_rgb(W, H, 0, 2, seed=3)
-        assert np.array_equal(film.numpy(), full)
+        if bdpt:
+            full, _ = s.render_bdpt_rgb(W, H, 0, 2, seed=3)
+            assert np.allclose(film.numpy(), full, rtol=1e-4, atol=1e-6)
+        else:
+            full, _ = s.render_pt_rgb(W, H, 0, 2, seed=3)
+            assert np.array_equal(film.numpy(), full)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -45,3 +57,8 @@ def _worker(rank, world, port, all_ranks):
 def test_two_rank_tile_shard_and_reduce(all_ranks):
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(2, _free_port(), all_ranks), nprocs=2, join=True)
+
+
+def test_two_rank_bdpt_splats_need_a_sum():
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(2, _free_port(), False, True), nprocs=2, join=True)

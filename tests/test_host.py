@@ -113,6 +113,12 @@ def test_reference_example_constructs_unchanged(monkeypatch):
     ex = mod.example(64, 64, 4)
     ex.scene.setup_data_cpu()
     assert ex.scene.primitive_count == 36 and ex.integrator.stack_size == 64
+    # ... and so does its example/veach_bdpt.py (BDPT_RGB.BDPT, model/bdpt.obj through the native reader)
+    spec = importlib.util.spec_from_file_location("ref_veach_bdpt", "/root/reference/example/veach_bdpt.py")
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    ex = mod.example(64, 64, 4)
+    ex.scene.setup_data_cpu()
+    assert ex.scene.primitive_count == 11544 and ex.scene.light_count == 4 and type(ex.integrator).__name__ == "BDPT"
     sys.modules.pop("Example", None)
 
 
