@@ -94,6 +94,19 @@ def measured_peak_gbs():
         return 6650.0, "fallback"
 
 
+def ncu_traffic(workload, kernel_prefix):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel, from the committed ncu capture of the same
+    command line (profiles/r01_dram_traffic.json, written from `ncu --metrics dram__bytes_*` by tools/); None if absent"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))[workload]
+        for k, v in t.items():
+            if k.startswith(kernel_prefix):
+                return v["dram_bytes_per_launch_all"]
+    except Exception:
+        pass
+    return None
+
+
 def oracle_tables(wl):
     from oracle import objload
     shapes = [objload.sphere_light_rows()] if wl["sphere_light"] else []
@@ -304,7 +317,8 @@ def run_native(args, wl):
         peak, how = measured_peak_gbs()
         achieved = algo_bytes / trace_s / 1e9
         out["roofline"] = {"kernel": "k_trace (closest hit)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                           "frac": achieved / peak, "traffic": None, "peak_source": how,
+                           "frac": achieved / peak, "traffic": ncu_traffic(args.workload, "k_trace"), "peak_source": how,
+                           "traffic_note": "ncu dram__bytes_read+write per launch (profiles/r01_dram_traffic.json): far below the algorithmic bytes because the BVH is cache resident",
                            "launches_per_step": n_trace_launches, "avg_launch_ms": stt["ms_trace"] / n_trace_launches,
                            "algorithmic_bytes_per_step": int(algo_bytes), "bytes_per_ray": algo_bytes / max(1, cs["rays_closest"]),
                            "node_visits_per_ray": cs["node_visits"] / max(1, cs["rays_closest"]),
@@ -359,7 +373,8 @@ def bdpt_roofline(out, args, wl, ex, ctx, local, spp):
           "avg_launch_ms": ms_ktrace / (6 * n_batches), "algorithmic_bytes_per_step": int(t_bytes), "bytes_per_ray": t_bytes / max(1, cs["rays_closest"]),
           "node_visits_per_ray": cs["node_visits"] / max(1, cs["rays_closest"]), "leaf_tests_per_ray": cs["leaf_tests"] / max(1, cs["rays_closest"])}
     top, other = (kq, kt) if ms_kshadow >= ms_ktrace else (kt, kq)
-    out["roofline"] = dict(top, bound="hbm", peak=peak, unit="GB/s", frac=top["achieved"] / peak, traffic=None, peak_source=how,
+    out["roofline"] = dict(top, bound="hbm", peak=peak, unit="GB/s", frac=top["achieved"] / peak,
+                           traffic=ncu_traffic(args.workload, "k_trace" if top is kt else "k_shadow"), peak_source=how,
                            second_kernel=dict(other, frac=other["achieved"] / peak),
                            stage_ms_per_step={"sub-paths (generate + 6 x (trace, vertex))": stt["ms_trace"], "of which k_trace": ms_ktrace,
                                               "connections (gen + query + eval)": stt["ms_shadow"], "of which k_shadow<QUERY>": ms_kshadow,

@@ -13,8 +13,9 @@
 //   k_bdpt_items           enumerates the valid strategies of every sample, strategy-major, into a connection queue
 //   k_bdpt_connect_gen     one thread per connection: geometric term -> shadow-queue entry when a visibility query is needed
 //   k_shadow<QUERY>        the persistent early-exit nearest-hit shadow kernel of PT_RGB, writing (visible ? t : -1) per item
-//   k_bdpt_connect_eval    BSDF terms and the MIS weight computed on register copies of the <= 4 vertices the reference
-//                          overwrites; e >= 2 results go to contrib[strategy][s], e == 1 results are splatted (float atomics)
+//   k_bdpt_connect_eval    BSDF terms; connections that carry light (three positive channels) are compacted into a MIS queue
+//   k_bdpt_mis             the MIS weight computed on register copies of the <= 4 vertices the reference overwrites;
+//                          e >= 2 results go to contrib[strategy][s], e == 1 results are splatted (float atomics)
 //   k_bdpt_film            per pixel and frame: own strategies summed in the reference's loop order + splats, running mean
 // The first version (option "bdpt_wavefront" = 0) is kept as a cross-check: k_bdpt_paths / k_bdpt_connect run one lane per
 // sub-path / connection with the warp walking the BVH in lock step; same device functions, same film.
@@ -36,7 +37,7 @@
 struct BdArgs {
     float4* vb; int* depths; float4* contrib; float* splat; unsigned* items;
     const int* tile_slot;
-    unsigned long long* ctr;           // [0] closest-hit traversals, [1] shadow traversals, [2] connection queue size (low 32 bits)
+    unsigned long long* ctr;           // [0] closest-hit traversals, [1] shadow traversals, [2] connection queue size, [3] MIS queue size (low 32 bits)
     size_t cap;                        // samples per batch
     float view[16];
 };
@@ -63,12 +64,6 @@ __device__ __forceinline__ BV bv_load(const BdArgs& b, size_t s, int v) {
     return x;
 }
 __device__ __forceinline__ void bv_set_rpdf(const BdArgs& b, size_t s, int v, float r) { ((float*)(b.vb + (size_t)(v * 5 + 1) * b.cap + s))[3] = r; }
-__device__ __forceinline__ void bv_scalars(const BdArgs& b, size_t s, int v, float& fpdf, float& rpdf, int& delta) {
-    fpdf = ((const float*)(b.vb + (size_t)(v * 5) * b.cap + s))[3];
-    rpdf = ((const float*)(b.vb + (size_t)(v * 5 + 1) * b.cap + s))[3];
-    delta = (__float_as_int(((const float*)(b.vb + (size_t)(v * 5 + 2) * b.cap + s))[3]) >> 4) & 15;
-}
-
 // One hit of a sub-path (the loop bodies of eye_path, BDPT_RGB.py:118-186, and light_path, :213-249): build vertex `depth`,
 // patch the reverse pdf of vertex depth-1, sample the continuation.  counted: the vertex joins the sub-path (depth += 1);
 // cont: the walk goes on with (origin, dir, beta, pdfFwd) and (pos, normal) as the new previous vertex.
@@ -380,9 +375,10 @@ __device__ __forceinline__ void bd_connect_geom(const WfArgs& a, const BdArgs& b
         }
     }
 }
-// vis / tt: the target primitive is the nearest hit of the query ray, at distance tt (closet_hit_shadow, Scene.py:671-699)
-__device__ __forceinline__ void bd_connect_finish(const WfArgs& a, const BdArgs& b, size_t s, int e, int l, BdConn& c, bool vis, float tt) {
-    V3 radiance = c.radiance, smp_pos = mk3(0.f, 0.f, 0.f), smp_normal = smp_pos; float smp_fpdf = 1.0f;
+// vis / tt: the target primitive is the nearest hit of the query ray, at distance tt (closet_hit_shadow, Scene.py:671-699).
+// Returns the unweighted contribution of the strategy.
+__device__ __forceinline__ V3 bd_connect_radiance(const WfArgs& a, const BdConn& c, bool vis, float tt) {
+    V3 radiance = c.radiance;
     const BV& ev = c.ev; const BV& lv = c.lv;
     if (c.need) {
         if (c.kind == 1 && vis) {
@@ -397,7 +393,6 @@ __device__ __forceinline__ void bd_connect_finish(const WfArgs& a, const BdArgs&
                 float G = fabsf(c.c1 * c.c0) / (tt * tt);
                 radiance = (((((G * ev.beta) * brdf) / pdf) * f4xyz(__ldg(a.matlin + ev.mat))) * c.ls.emission) / light_pdf;
             }
-            smp_pos = c.ls.pos; smp_normal = c.ls.normal; smp_fpdf = light_pdf;
         } else if (c.kind == 3 && vis && tt > BD_EPS) {
             const float* mE = a.material + (size_t)ev.mat * 10; const float* mL = a.material + (size_t)lv.mat * 10;
             float brdfL, lpdf, brdfE, epdf;
@@ -409,13 +404,29 @@ __device__ __forceinline__ void bd_connect_finish(const WfArgs& a, const BdArgs&
             }
         }
     }
-    if (radiance.x > 0.0f && radiance.y > 0.0f && radiance.z > 0.0f) radiance = radiance * bdpt_mis_weight(a, b, s, e, l, ev, lv, smp_pos, smp_normal, smp_fpdf);
+    return radiance;
+}
+// mis_weight is only evaluated for contributions with three positive channels (BDPT_RGB.py:578-579)
+__device__ __forceinline__ bool bd_needs_mis(V3 r) { return r.x > 0.0f && r.y > 0.0f && r.z > 0.0f; }
+// the freshly sampled emitter vertex of the l == 1 strategy stands in for light[0] in the weight (sample.* of :522-528)
+__device__ __forceinline__ float bd_connect_weight(const WfArgs& a, const BdArgs& b, size_t s, int e, int l, const BdConn& c) {
+    V3 z = mk3(0.f, 0.f, 0.f);
+    if (c.kind == 2) return bdpt_mis_weight(a, b, s, e, l, c.ev, c.lv, c.ls.pos, c.ls.normal, c.ls.choice_pdf);
+    return bdpt_mis_weight(a, b, s, e, l, c.ev, c.lv, z, z, 1.0f);
+}
+// e >= 2: the strategy's slot of the per-sample contribution table; e == 1: splat onto the pixel the light vertex projects to
+__device__ __forceinline__ void bd_connect_write(const WfArgs& a, const BdArgs& b, size_t s, int e, int l, const BdConn& c, V3 radiance) {
     if (e == 1) {
         if (c.nu >= 0 && (radiance.x != 0.0f || radiance.y != 0.0f || radiance.z != 0.0f)) {
             float* o = b.splat + ((size_t)(s / (size_t)a.npix) * a.W * a.H + (size_t)c.nu * a.H + c.nv) * 3;
             atomicAdd(o, radiance.x); atomicAdd(o + 1, radiance.y); atomicAdd(o + 2, radiance.z);
         }
     } else b.contrib[(size_t)bd_row(e, l) * b.cap + s] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
+}
+__device__ __forceinline__ void bd_connect_finish(const WfArgs& a, const BdArgs& b, size_t s, int e, int l, BdConn& c, bool vis, float tt) {
+    V3 radiance = bd_connect_radiance(a, c, vis, tt);
+    if (bd_needs_mis(radiance)) radiance = radiance * bd_connect_weight(a, b, s, e, l, c);
+    bd_connect_write(a, b, s, e, l, c, radiance);
 }
 
 // lock-step pipeline: one lane per (sample, e, l), the warp walks the BVH together
@@ -524,17 +535,41 @@ __global__ void __launch_bounds__(WF_THREADS) k_bdpt_connect_gen(WfArgs a, BdArg
         }
     }
 }
-// one thread per connection: geometry again (cheaper than spilling BdConn to HBM), the query result, BSDF terms + MIS
+// one thread per connection: geometry again (cheaper than spilling BdConn to HBM), the query result, BSDF terms.  Only a
+// fraction of the connections carries light and needs the MIS weight: those are compacted into their own queue
+// (radiance.rgb, item) -- it lives in the connection shadow queue, which is free once k_shadow<QUERY> is done -- so that the
+// weight kernel runs with full warps instead of a third of the lanes.
 __global__ void __launch_bounds__(WF_THREADS, 3) k_bdpt_connect_eval(WfArgs a, BdArgs b) {
     const BatchParams bp = *a.bp;
-    const int n = (int)b.ctr[2];
+    const int n = (int)b.ctr[2], n_r = (n + 31) & ~31;
     const int stride = gridDim.x * blockDim.x;
-    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < n; it += stride) {
-        unsigned item = b.items[it];
+    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < n_r; it += stride) {
+        bool defer = false; V3 radiance = mk3(0.f, 0.f, 0.f);
+        if (it < n) {
+            unsigned item = b.items[it];
+            const size_t s = item & 0x3ffffffu; const int e = (item >> 26) & 7, l = (int)(item >> 29);
+            BdConn c; bd_connect_geom(a, b, bp, s, e, l, c);
+            float tt = c.need ? a.vis[it] : -1.0f;
+            radiance = bd_connect_radiance(a, c, tt >= 0.0f, tt);
+            defer = bd_needs_mis(radiance) && (l + e != 2);
+            if (!defer) bd_connect_write(a, b, s, e, l, c, radiance);
+        }
+        int q = warp_append((int*)(b.ctr + 3), defer);
+        if (defer) a.sa[0][q] = make_float4(radiance.x, radiance.y, radiance.z, __int_as_float(it));
+    }
+}
+// one thread per light-carrying connection: mis_weight (BDPT_RGB.py:258-434), then the contribution / splat write
+__global__ void __launch_bounds__(WF_THREADS, 3) k_bdpt_mis(WfArgs a, BdArgs b) {
+    const BatchParams bp = *a.bp;
+    const int n = (int)b.ctr[3];
+    const int stride = gridDim.x * blockDim.x;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) {
+        const float4 Q = a.sa[0][q];
+        const unsigned item = b.items[__float_as_int(Q.w)];
         const size_t s = item & 0x3ffffffu; const int e = (item >> 26) & 7, l = (int)(item >> 29);
-        BdConn c; bd_connect_geom(a, b, bp, s, e, l, c);
-        float tt = c.need ? a.vis[it] : -1.0f;
-        bd_connect_finish(a, b, s, e, l, c, tt >= 0.0f, tt);
+        BdConn c; bd_connect_geom(a, b, bp, s, e, l, c);                   // end-point vertices, light sample, splat pixel: as in the eval pass
+        V3 radiance = mk3(Q.x, Q.y, Q.z) * bd_connect_weight(a, b, s, e, l, c);
+        bd_connect_write(a, b, s, e, l, c, radiance);
     }
 }
 
@@ -657,8 +692,9 @@ static int render_bdpt(tr_ctx* ctx, int frame_begin, int n_frames, uint64_t seed
             else k_shadow<false, true><<<ctx->num_sms * bq_, WF_THREADS, 0, s>>>(a, 0);
             if (ev) cudaEventRecord(ev[6], s);
             k_bdpt_connect_eval<<<cfg.grid_simple, WF_THREADS, 0, s>>>(a, b);
+            k_bdpt_mis<<<cfg.grid_simple, WF_THREADS, 0, s>>>(a, b);
             if (ev) cudaEventRecord(ev[3], s);
-            launches += 4;
+            launches += 5;
         } else if (a.npix > 0) {
             if (cfg.use_smem) k_bdpt_paths<true><<<ctx->num_sms * bp_, WF_THREADS, cfg.smem, s>>>(a, b);
             else k_bdpt_paths<false><<<ctx->num_sms * bp_, WF_THREADS, 0, s>>>(a, b);
