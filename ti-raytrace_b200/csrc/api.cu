@@ -148,6 +148,7 @@ int tr_camera_set(tr_ctx* ctx, const float view[16], const float view_inv[16], c
                   float fx, float fy, float cx, float cy) {
     if (!ctx || !view_inv || !eye) return tr_fail(ctx, TR_ERR_INVALID, "tr_camera_set: NULL argument");
     if (view) memcpy(ctx->view, view, 64);
+    ctx->view_set = view != nullptr;
     memcpy(ctx->cam.view_inv, view_inv, 64); memcpy(ctx->cam.eye, eye, 12);
     ctx->cam.fx = fx; ctx->cam.fy = fy; ctx->cam.cx = cx; ctx->cam.cy = cy;
     ctx->cam_set = true; ctx->fh_ready = false; ctx->gen++;

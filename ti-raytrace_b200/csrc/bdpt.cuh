@@ -201,16 +201,29 @@ __global__ void __launch_bounds__(WF_THREADS) k_bdpt_items(WfArgs a, BdArgs b) {
     const BatchParams bp = *a.bp;
     const int nsamp = bp.n_frames * a.npix, nsamp_r = (nsamp + 31) & ~31;
     const int stride = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nsamp_r; s += stride) {
         int ed = 0, ld = 0;
         if (s < nsamp) { ed = b.depths[s]; ld = b.depths[b.cap + s]; }
+        // one queue reservation per warp: count the warp's strategies first, then write them strategy-major
+        int total = 0;
         for (int e = 1; e <= BD_EYE_MAX; ++e)
             for (int l = 0; l <= BD_LIGHT_MAX; ++l) {
                 const int depth = l + e - 2;
                 if ((l == 1 && e == 1) || depth < 0 || depth > BD_MAX_DEPTH) continue;      // warp-uniform
+                total += __popc(__ballot_sync(0xffffffffu, e <= ed && l <= ld));
+            }
+        int off = 0;
+        if (lane == 0 && total > 0) off = atomicAdd((int*)(b.ctr + 2), total);
+        off = __shfl_sync(0xffffffffu, off, 0);
+        for (int e = 1; e <= BD_EYE_MAX; ++e)
+            for (int l = 0; l <= BD_LIGHT_MAX; ++l) {
+                const int depth = l + e - 2;
+                if ((l == 1 && e == 1) || depth < 0 || depth > BD_MAX_DEPTH) continue;
                 const bool valid = e <= ed && l <= ld;
-                int q = warp_append((int*)(b.ctr + 2), valid);
-                if (valid) b.items[q] = (unsigned)s | ((unsigned)e << 26) | ((unsigned)l << 29);
+                const unsigned m = __ballot_sync(0xffffffffu, valid);
+                if (valid) b.items[off + __popc(m & ((1u << lane) - 1u))] = (unsigned)s | ((unsigned)e << 26) | ((unsigned)l << 29);
+                off += __popc(m);
             }
     }
 }
@@ -610,6 +623,7 @@ static int render_bdpt(tr_ctx* ctx, int frame_begin, int n_frames, uint64_t seed
     if ((rc = tr_stats_resolve(ctx))) return rc;
     if ((rc = fill_args(ctx, a, false))) return rc;
     if (ctx->nl <= 0) return tr_fail(ctx, TR_ERR_INVALID, "tr_render_bdpt_rgb: the scene has no emitter (Scene.sample_light needs one)");
+    if (!ctx->view_set) return tr_fail(ctx, TR_ERR_INVALID, "tr_render_bdpt_rgb: tr_camera_set was called without the view matrix (Camera.get_image_point needs it)");
     const bool wave = ctx->opt_bdpt_wavefront != 0;
     // bytes per sample: 13 vertex records + 21 contributions + 26 queue items + depths; the wavefront pipeline adds two path-queue
     // slots (PT_RGB's 252 B each) and a worst-case connection shadow queue (26 x (32 B + 4 B))

@@ -111,7 +111,7 @@ struct tr_ctx {
     float* d_white_point = nullptr;
 
     // bidirectional integrator (BDPT_RGB): vertex records, per-strategy contributions, splat film, connection queue
-    float view[16] = {0};                          // Camera.view (get_image_point / get_optical_axis)
+    float view[16] = {0}; bool view_set = false;   // Camera.view (get_image_point / get_optical_axis)
     float4* d_bd_vb = nullptr; int* d_bd_depths = nullptr; float4* d_bd_contrib = nullptr; float* d_bd_splat = nullptr;
     unsigned* d_bd_items = nullptr; int* d_bd_tile_slot = nullptr; unsigned long long* d_bd_ctr = nullptr;
     float4* d_bd_sq[2] = {nullptr, nullptr}; float* d_bd_vis = nullptr;      // wavefront pipeline: connection shadow queue (sa, sb) + query results
