@@ -107,6 +107,15 @@ def ncu_traffic(workload, kernel_prefix):
     return None
 
 
+def ncu_issue(workload):
+    """issue-slot utilisation etc. of the dominant kernel from the committed --set full capture (None if absent): the kernels are
+    issue-bound, not DRAM-bound, which is why the effective-bandwidth fraction can exceed 1"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))[workload].get("ncu_full")
+    except Exception:
+        return None
+
+
 def oracle_tables(wl):
     from oracle import objload
     shapes = [objload.sphere_light_rows()] if wl["sphere_light"] else []
@@ -168,10 +177,12 @@ def run_reference(args, wl):
 
 # --------------------------------------------------------------------------------------------- native arm
 def build_example(wl):
+    import contextlib
     import importlib
     mod = importlib.import_module(wl["module"])
-    ex = mod.example(wl["W"], wl["H"], max(wl["spp"], 4))
-    ex.build_scene()
+    with contextlib.redirect_stdout(sys.stderr):          # the example scripts print like the reference's; stdout carries only the JSON line
+        ex = mod.example(wl["W"], wl["H"], max(wl["spp"], 4))
+        ex.build_scene()
     return ex
 
 
@@ -319,6 +330,7 @@ def run_native(args, wl):
         out["roofline"] = {"kernel": "k_trace (closest hit)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                            "frac": achieved / peak, "traffic": ncu_traffic(args.workload, "k_trace"), "peak_source": how,
                            "traffic_note": "ncu dram__bytes_read+write per launch (profiles/r01_dram_traffic.json): far below the algorithmic bytes because the BVH is cache resident",
+                           "ncu": ncu_issue(args.workload),
                            "launches_per_step": n_trace_launches, "avg_launch_ms": stt["ms_trace"] / n_trace_launches,
                            "algorithmic_bytes_per_step": int(algo_bytes), "bytes_per_ray": algo_bytes / max(1, cs["rays_closest"]),
                            "node_visits_per_ray": cs["node_visits"] / max(1, cs["rays_closest"]),
@@ -374,7 +386,7 @@ def bdpt_roofline(out, args, wl, ex, ctx, local, spp):
           "node_visits_per_ray": cs["node_visits"] / max(1, cs["rays_closest"]), "leaf_tests_per_ray": cs["leaf_tests"] / max(1, cs["rays_closest"])}
     top, other = (kq, kt) if ms_kshadow >= ms_ktrace else (kt, kq)
     out["roofline"] = dict(top, bound="hbm", peak=peak, unit="GB/s", frac=top["achieved"] / peak,
-                           traffic=ncu_traffic(args.workload, "k_trace" if top is kt else "k_shadow"), peak_source=how,
+                           traffic=ncu_traffic(args.workload, "k_trace" if top is kt else "k_shadow"), peak_source=how, ncu=ncu_issue(args.workload),
                            second_kernel=dict(other, frac=other["achieved"] / peak),
                            stage_ms_per_step={"sub-paths (generate + 6 x (trace, vertex))": stt["ms_trace"], "of which k_trace": ms_ktrace,
                                               "connections (gen + query + eval)": stt["ms_shadow"], "of which k_shadow<QUERY>": ms_kshadow,
