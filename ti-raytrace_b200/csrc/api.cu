@@ -222,7 +222,10 @@ int tr_set_option(tr_ctx* ctx, const char* name, int value) {
     else if (!strcmp(name, "max_paths")) ctx->opt_max_paths = (size_t)value;
     else return tr_fail(ctx, TR_ERR_INVALID, "tr_set_option: unknown option '%s'", name);
     ctx->gen++;
-    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }   // options are baked into the captured graph
+    if (ctx->graph_exec) {                                                                       // options are baked into the captured graph
+        cudaStreamSynchronize(ctx->stream);                                                      // an asynchronous render may still be replaying it
+        cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr;
+    }
     return TR_OK;
 }
 

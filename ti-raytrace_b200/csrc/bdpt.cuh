@@ -787,7 +787,7 @@ extern "C" int tr_test_bdpt_dump(tr_ctx* ctx, int n, const int32_t* px, const in
             float4 w[5];
             for (int c = 0; c < 5; ++c) TR_CUDA(ctx, cudaMemcpy(&w[c], ctx->d_bd_vb + (size_t)(v * 5 + c) * cap + s, 16, cudaMemcpyDeviceToHost));
             float* o = verts + ((size_t)k * BD_NVERT + v) * 20;
-            const bool valid = v < BD_EYE_MAX ? v < d[0] || (v == d[0] && false) : (v - BD_EYE_MAX) < d[1];
+            const bool valid = v < BD_EYE_MAX ? v < d[0] : (v - BD_EYE_MAX) < d[1];
             if (!valid) { for (int c = 0; c < 20; ++c) o[c] = 0.0f; continue; }
             int fl; memcpy(&fl, &w[2].w, 4); int prim; memcpy(&prim, &w[3].w, 4);
             o[0] = w[0].x; o[1] = w[0].y; o[2] = w[0].z; o[3] = w[1].x; o[4] = w[1].y; o[5] = w[1].z; o[6] = w[2].x; o[7] = w[2].y; o[8] = w[2].z;

@@ -1110,7 +1110,7 @@ static int render_wavefront(tr_ctx* ctx, int frame_begin, int n_frames, int max_
             if (!ctx->graph_exec || ctx->graph_spec != (int)SPEC || ctx->graph_depth != max_depth || ctx->graph_chains != K || ctx->graph_fs != fs ||
                 ctx->graph_args.size() != sizeof(WfArgs) + sizeof(LaunchCfg) || memcmp(ctx->graph_args.data(), &a, sizeof(WfArgs)) != 0 ||
                 memcmp(ctx->graph_args.data() + sizeof(WfArgs), &cfg, sizeof(LaunchCfg)) != 0) {
-                if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+                if (ctx->graph_exec) { cudaStreamSynchronize(s); cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }   // the previous (asynchronous) batch may still replay it
                 cudaGraph_t g; uint64_t l2 = 0;
                 TR_CUDA(ctx, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
                 rc = enqueue_batch<SPEC>(ctx, a, cfg, max_depth, K, fs, s, &l2, nullptr);
