@@ -64,6 +64,11 @@ __device__ __forceinline__ BV bv_load(const BdArgs& b, size_t s, int v) {
     return x;
 }
 __device__ __forceinline__ void bv_set_rpdf(const BdArgs& b, size_t s, int v, float r) { ((float*)(b.vb + (size_t)(v * 5 + 1) * b.cap + s))[3] = r; }
+// Out-of-line copies of the Disney evaluations for the connection / MIS kernels: they are called from up to six places per
+// kernel, and the inlined code (3 600 SASS instructions for k_bdpt_mis) made instruction fetch a top stall reason.
+__device__ __noinline__ float bd_disney_pdf(V3 N, V3 V, V3 L, float metal, float rough) { return disney_pdf(N, V, L, metal, rough); }
+__device__ __noinline__ float2 bd_disney_evaluate_pdf(V3 N, V3 V, V3 L, float metal, float rough) { float o, p; disney_evaluate_pdf(N, V, L, metal, rough, o, p); return make_float2(o, p); }
+
 // One hit of a sub-path (the loop bodies of eye_path, BDPT_RGB.py:118-186, and light_path, :213-249): build vertex `depth`,
 // patch the reverse pdf of vertex depth-1, sample the continuation.  counted: the vertex joins the sub-path (depth += 1);
 // cont: the walk goes on with (origin, dir, beta, pdfFwd) and (pos, normal) as the new previous vertex.
@@ -71,8 +76,7 @@ __device__ __forceinline__ void bv_set_rpdf(const BdArgs& b, size_t s, int v, fl
 // from the offset ray origin with a clamped distance; the light path stops in front of emitters, measures from the
 // stored previous position, and multiplies fpdf in a different order.
 struct BdStep { bool counted, cont; V3 origin, dir, beta, pos, normal; float pdfFwd; };
-template <bool LIGHT>
-__device__ __forceinline__ BdStep bd_vertex(const WfArgs& a, const BdArgs& b, const BatchParams& bp, size_t s, unsigned pix, unsigned frame, int depth,
+__device__ __forceinline__ BdStep bd_vertex(const bool LIGHT, const WfArgs& a, const BdArgs& b, const BatchParams& bp, size_t s, unsigned pix, unsigned frame, int depth,
                                             V3 origin, V3 dir, V3 beta, float pdfFwd, V3 prev_pos, V3 prev_normal, int prim, float hu, float hv, float ht) {
     const int vbase = LIGHT ? BD_EYE_MAX : 0;
     BdStep st; st.counted = false; st.cont = false;
@@ -165,7 +169,7 @@ __device__ __forceinline__ void bdpt_subpath(const WfArgs& a, const BdArgs& b, c
         if (!alive) continue;
         ++n_closest;
         if (h.prim < 0) { alive = false; continue; }
-        BdStep st = bd_vertex<LIGHT>(a, b, bp, s, pix, frame, depth, origin, dir, beta, pdfFwd, prev_pos, prev_normal, h.prim, h.u, h.v, h.t);
+        BdStep st = bd_vertex(LIGHT, a, b, bp, s, pix, frame, depth, origin, dir, beta, pdfFwd, prev_pos, prev_normal, h.prim, h.u, h.v, h.t);
         if (st.counted) depth += 1;
         alive = st.cont;
         if (st.cont) { prev_pos = st.pos; prev_normal = st.normal; origin = st.origin; dir = st.dir; beta = st.beta; pdfFwd = st.pdfFwd; }
@@ -261,7 +265,7 @@ __device__ __forceinline__ float bdpt_mis_weight(const WfArgs& a, const BdArgs& 
         V3 wi = L2pos - L1pos, wo = E1pos - L1pos; float dist = length3(wo);
         wi = normalize3(wi); wo = normalize3(wo);
         float pdf = 1.0f;
-        if (L1mat == TR_MAT_DISNEY) { const float* m = a.material + (size_t)L1mat * 10; pdf = disney_pdf(L1snormal, wi, wo, __ldg(m + 5), __ldg(m + 6)); }   // material INDEX == 0 (sic, :312)
+        if (L1mat == TR_MAT_DISNEY) { const float* m = a.material + (size_t)L1mat * 10; pdf = bd_disney_pdf(L1snormal, wi, wo, __ldg(m + 5), __ldg(m + 6)); }   // material INDEX == 0 (sic, :312)
         e1_rpdf = pdf * fabsf(dot3(L1normal, wo)) / (dist * dist);
     }
     // light[l-1].rpdf (:317-343)
@@ -271,7 +275,7 @@ __device__ __forceinline__ float bdpt_mis_weight(const WfArgs& a, const BdArgs& 
                 V3 wi = E2pos - E1pos, wo = L1pos - E1pos; float dist = length3(wo);
                 wi = normalize3(wi); wo = normalize3(wo);
                 float pdf = 1.0f;
-                if (E1mat == TR_MAT_DISNEY) { const float* m = a.material + (size_t)E1mat * 10; pdf = disney_pdf(E1snormal, wi, wo, __ldg(m + 5), __ldg(m + 6)); }
+                if (E1mat == TR_MAT_DISNEY) { const float* m = a.material + (size_t)E1mat * 10; pdf = bd_disney_pdf(E1snormal, wi, wo, __ldg(m + 5), __ldg(m + 6)); }
                 l1_rpdf = pdf * fabsf(dot3(E1normal, wo)) / (dist * dist);
             } else l1_rpdf = 1.0f;
         } else {
@@ -290,7 +294,7 @@ __device__ __forceinline__ float bdpt_mis_weight(const WfArgs& a, const BdArgs& 
             V3 wi = L1pos - E1pos, wo = E2pos - E1pos; float dist = length3(wo);
             wi = normalize3(wi); wo = normalize3(wo);
             const float* m = a.material + (size_t)E1mat * 10;
-            float pdf = disney_pdf(E1snormal, wi, wo, __ldg(m + 5), __ldg(m + 6));
+            float pdf = bd_disney_pdf(E1snormal, wi, wo, __ldg(m + 5), __ldg(m + 6));
             e2_rpdf = pdf / (dist * dist);
             if (E2type == BD_VERTEX_SURFACE) e2_rpdf *= fabsf(dot3(E1normal, wo));
         } else e2_rpdf = 1.0f;
@@ -301,7 +305,7 @@ __device__ __forceinline__ float bdpt_mis_weight(const WfArgs& a, const BdArgs& 
             V3 wi = E1pos - L1pos, wo = L2pos - L1pos; float dist = length3(wo);
             wi = normalize3(wi); wo = normalize3(wo);
             float pdf = 1.0f;
-            if (L1mat == TR_MAT_DISNEY) { const float* m = a.material + (size_t)L1mat * 10; pdf = disney_pdf(L1normal, wi, wo, __ldg(m + 5), __ldg(m + 6)); }
+            if (L1mat == TR_MAT_DISNEY) { const float* m = a.material + (size_t)L1mat * 10; pdf = bd_disney_pdf(L1normal, wi, wo, __ldg(m + 5), __ldg(m + 6)); }
             l2_rpdf = pdf / (dist * dist);
             if (L2type == BD_VERTEX_SURFACE) l2_rpdf *= fabsf(dot3(L1normal, wo));
         } else l2_rpdf = 1.0f;
@@ -396,21 +400,20 @@ __device__ __forceinline__ V3 bd_connect_radiance(const WfArgs& a, const BdConn&
     if (c.need) {
         if (c.kind == 1 && vis) {
             const float* m = a.material + (size_t)lv.mat * 10;
-            float brdf, pdf; disney_evaluate_pdf(lv.snormal, -lv.wo, -c.rd, __ldg(m + 5), __ldg(m + 6), brdf, pdf);
+            float2 bp_ = bd_disney_evaluate_pdf(lv.snormal, -lv.wo, -c.rd, __ldg(m + 5), __ldg(m + 6)); const float brdf = bp_.x, pdf = bp_.y;
             if (pdf > 0.0f) { float G = fabsf(c.c0) / (tt * tt); radiance = (((G * lv.beta) * f4xyz(__ldg(a.matlin + lv.mat))) * brdf) / pdf; }
         } else if (c.kind == 2 && vis && tt > BD_EPS) {
             const float* m = a.material + (size_t)ev.mat * 10;
             const float light_pdf = c.ls.choice_pdf;
-            float brdf, pdf; disney_evaluate_pdf(ev.snormal, -ev.wo, -c.ls.dir, __ldg(m + 5), __ldg(m + 6), brdf, pdf);
+            float2 bp_ = bd_disney_evaluate_pdf(ev.snormal, -ev.wo, -c.ls.dir, __ldg(m + 5), __ldg(m + 6)); const float brdf = bp_.x, pdf = bp_.y;
             if (pdf > 0.0f) {
                 float G = fabsf(c.c1 * c.c0) / (tt * tt);
                 radiance = (((((G * ev.beta) * brdf) / pdf) * f4xyz(__ldg(a.matlin + ev.mat))) * c.ls.emission) / light_pdf;
             }
         } else if (c.kind == 3 && vis && tt > BD_EPS) {
             const float* mE = a.material + (size_t)ev.mat * 10; const float* mL = a.material + (size_t)lv.mat * 10;
-            float brdfL, lpdf, brdfE, epdf;
-            disney_evaluate_pdf(lv.snormal, -lv.wo, c.rd, __ldg(mL + 5), __ldg(mL + 6), brdfL, lpdf);
-            disney_evaluate_pdf(ev.snormal, -ev.wo, -c.rd, __ldg(mE + 5), __ldg(mE + 6), brdfE, epdf);
+            const float2 bl = bd_disney_evaluate_pdf(lv.snormal, -lv.wo, c.rd, __ldg(mL + 5), __ldg(mL + 6)), be = bd_disney_evaluate_pdf(ev.snormal, -ev.wo, -c.rd, __ldg(mE + 5), __ldg(mE + 6));
+            const float brdfL = bl.x, lpdf = bl.y, brdfE = be.x, epdf = be.y;
             if (brdfL > 0.0f && brdfE > 0.0f) {
                 float G = fabsf(c.c1 * c.c0) / (c.dist * c.dist);
                 radiance = (((((((G * ev.beta) * lv.beta) * brdfL) / lpdf) * brdfE) / epdf) * f4xyz(__ldg(a.matlin + ev.mat))) * f4xyz(__ldg(a.matlin + lv.mat));
@@ -476,7 +479,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_bdpt_connect(WfArgs a, BdArgs b)
 // C = (beta.rgb, -).  Stage d traces the segment that ends in vertex d + 1 of either sub-path.
 __global__ void __launch_bounds__(WF_THREADS) k_bdpt_generate(WfArgs a, BdArgs b) {
     const BatchParams bp = *a.bp;
-    const int nsamp = bp.n_frames * a.npix, nsamp_r = (nsamp + 31) & ~31;
+    const int nsamp = bp.n_frames * a.npix, nsamp_r = (nsamp + WF_THREADS - 1) / WF_THREADS * WF_THREADS;    // block-uniform halves (block_append)
     const int stride = gridDim.x * blockDim.x;
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < 2 * nsamp_r; w += stride) {
         const bool light = w >= nsamp_r;                                // warp-uniform
@@ -487,7 +490,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_bdpt_generate(WfArgs a, BdArgs b
         if (s < nsamp) b.depths[(light ? b.cap : 0) + s] = active ? 1 : 0;
         V3 origin = mk3(0.f, 0.f, 0.f), dir = mk3(1.f, 1.f, 1.f), beta = dir; float pdfFwd = 1.0f;
         if (active) { if (light) bd_vertex0<true>(a, b, bp, (size_t)s, pix, frame, x, y, origin, dir, beta, pdfFwd); else bd_vertex0<false>(a, b, bp, (size_t)s, pix, frame, x, y, origin, dir, beta, pdfFwd); }
-        int q = warp_append(&a.ctr->nq[0], active);
+        int q = block_append(&a.ctr->nq[0], active);
         if (active) {
             a.pa[0][q] = make_float4(origin.x, origin.y, origin.z, dir.x);
             a.pb[0][q] = make_float4(dir.y, dir.z, pdfFwd, __uint_as_float((unsigned)s | (light ? SPEC_BIT : 0u)));
@@ -500,7 +503,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_bdpt_generate(WfArgs a, BdArgs b
 __global__ void __launch_bounds__(WF_THREADS, 3) k_bdpt_vertex(WfArgs a, BdArgs b, int d) {
     const BatchParams bp = *a.bp;
     const int n0 = a.ctr->ncls[d][0], n1 = a.ctr->ncls[d][1], n2 = a.ctr->ncls[d][2];
-    const int n = n0 + n1 + n2, n_r = (n + 31) & ~31;
+    const int n = n0 + n1 + n2, n_r = (n + WF_THREADS - 1) / WF_THREADS * WF_THREADS;       // block-uniform trip count (block_append)
     const int pp = d & 1, np_ = pp ^ 1, depth = d + 1;
     const int stride = gridDim.x * blockDim.x;
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_r; w += stride) {
@@ -518,13 +521,12 @@ __global__ void __launch_bounds__(WF_THREADS, 3) k_bdpt_vertex(WfArgs a, BdArgs 
                 const int vprev = (light ? BD_EYE_MAX : 0) + depth - 1;
                 V3 prev_pos = f4xyz(b.vb[(size_t)(vprev * 5) * b.cap + s]), prev_normal = f4xyz(b.vb[(size_t)(vprev * 5 + 1) * b.cap + s]);
                 V3 o = mk3(A.x, A.y, A.z), dir = mk3(A.w, B.x, B.y), beta = mk3(C.x, C.y, C.z);
-                if (light) st = bd_vertex<true>(a, b, bp, s, pix, frame, depth, o, dir, beta, B.z, prev_pos, prev_normal, prim, Hh.z, Hh.w, Hh.x);
-                else st = bd_vertex<false>(a, b, bp, s, pix, frame, depth, o, dir, beta, B.z, prev_pos, prev_normal, prim, Hh.z, Hh.w, Hh.x);
+                st = bd_vertex(light, a, b, bp, s, pix, frame, depth, o, dir, beta, B.z, prev_pos, prev_normal, prim, Hh.z, Hh.w, Hh.x);   // one shared copy of the code for both sub-paths
                 if (st.counted) b.depths[(light ? b.cap : 0) + s] = depth + 1;
                 if (depth + 1 >= (light ? BD_LIGHT_MAX : BD_EYE_MAX)) st.cont = false;         // the sub-path is full
             }
         }
-        int qn = warp_append(&a.ctr->nq[d + 1], st.cont);
+        int qn = block_append(&a.ctr->nq[d + 1], st.cont);
         if (st.cont) {
             a.pa[np_][qn] = make_float4(st.origin.x, st.origin.y, st.origin.z, st.dir.x);
             a.pb[np_][qn] = make_float4(st.dir.y, st.dir.z, st.pdfFwd, __uint_as_float(sw));
@@ -536,12 +538,12 @@ __global__ void __launch_bounds__(WF_THREADS, 3) k_bdpt_vertex(WfArgs a, BdArgs 
 // one thread per connection: geometry, then a shadow-queue entry  sa = (o.xyz, d.x)  sb = (d.y, d.z, target prim, item)
 __global__ void __launch_bounds__(WF_THREADS) k_bdpt_connect_gen(WfArgs a, BdArgs b) {
     const BatchParams bp = *a.bp;
-    const int n = (int)b.ctr[2], n_r = (n + 31) & ~31;
+    const int n = (int)b.ctr[2], n_r = (n + WF_THREADS - 1) / WF_THREADS * WF_THREADS;       // block-uniform trip count (block_append)
     const int stride = gridDim.x * blockDim.x;
     for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < n_r; it += stride) {
         BdConn c; c.need = false;
         if (it < n) { unsigned item = b.items[it]; bd_connect_geom(a, b, bp, item & 0x3ffffffu, (item >> 26) & 7, (int)(item >> 29), c); }
-        int q = warp_append(&a.ctr->nshadow[0], c.need);
+        int q = block_append(&a.ctr->nshadow[0], c.need);
         if (c.need) {
             a.sa[0][q] = make_float4(c.ro.x, c.ro.y, c.ro.z, c.rd.x);
             a.sb[0][q] = make_float4(c.rd.y, c.rd.z, __int_as_float(c.target), __int_as_float(it));
@@ -554,7 +556,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_bdpt_connect_gen(WfArgs a, BdArg
 // weight kernel runs with full warps instead of a third of the lanes.
 __global__ void __launch_bounds__(WF_THREADS, 3) k_bdpt_connect_eval(WfArgs a, BdArgs b) {
     const BatchParams bp = *a.bp;
-    const int n = (int)b.ctr[2], n_r = (n + 31) & ~31;
+    const int n = (int)b.ctr[2], n_r = (n + WF_THREADS - 1) / WF_THREADS * WF_THREADS;       // block-uniform trip count (block_append)
     const int stride = gridDim.x * blockDim.x;
     for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < n_r; it += stride) {
         bool defer = false; V3 radiance = mk3(0.f, 0.f, 0.f);
@@ -567,7 +569,7 @@ __global__ void __launch_bounds__(WF_THREADS, 3) k_bdpt_connect_eval(WfArgs a, B
             defer = bd_needs_mis(radiance) && (l + e != 2);
             if (!defer) bd_connect_write(a, b, s, e, l, c, radiance);
         }
-        int q = warp_append((int*)(b.ctr + 3), defer);
+        int q = block_append((int*)(b.ctr + 3), defer);
         if (defer) a.sa[0][q] = make_float4(radiance.x, radiance.y, radiance.z, __int_as_float(it));
     }
 }

@@ -76,6 +76,28 @@ __device__ __forceinline__ int warp_append(int* counter, bool pred) {
     return pred ? base + __popc(m & ((1u << lane) - 1u)) : -1;
 }
 
+// block-aggregated append: one atomic per CTA instead of one per warp (thousands of warps appending to ONE counter serialise in
+// the L2 atomic unit and every warp waits for its round trip).  All threads of the block must call it together (block-uniform
+// loops); returns the queue position for threads with pred, -1 otherwise.
+__device__ __forceinline__ int block_append(int* counter, bool pred) {
+    __shared__ int s_cnt[WF_THREADS / 32];
+    __shared__ int s_base;
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_cnt[warp] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < WF_THREADS / 32; ++w) { int c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
+        s_base = tot ? atomicAdd(counter, tot) : 0;
+    }
+    __syncthreads();
+    const int pos = s_base + s_cnt[warp] + __popc(m & ((1u << lane) - 1u));
+    __syncthreads();                                   // the shared slots are rewritten by the next call
+    return pred ? pos : -1;
+}
+
 // true when an earlier stage handed the remaining paths of this chain to the tail kernel (tail_from: 0 = no hand-over,
 // d >= 1 = k_tail owns the paths from depth d on)
 __device__ __forceinline__ bool tail_took_over(const WfArgs& a, int depth) {
@@ -92,7 +114,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_generate(WfArgs a) {
     const int nf = max(0, min(a.sub_frames, bp.n_frames - a.frame_off));
     const int total = nf * a.npix;
     const int stride = gridDim.x * blockDim.x;
-    const int total_r = (total + 31) & ~31;
+    const int total_r = (total + WF_THREADS - 1) / WF_THREADS * WF_THREADS;   // block-uniform trip count (block_append)
     for (int sl = blockIdx.x * blockDim.x + threadIdx.x; sl < total_r; sl += stride) {
         bool valid = false; int x = 0, y = 0, frame = 0, s = 0;
         if (sl < total) {
@@ -103,7 +125,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_generate(WfArgs a) {
             valid = slot_to_pixel(a, p, x, y);
             a.L[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); a.Lnee[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
-        int q = warp_append(&a.ctr->nq[0], valid);
+        int q = block_append(&a.ctr->nq[0], valid);
         if (valid) {
             unsigned pix = ((unsigned)x << 16) | (unsigned)y;
             float jx = 0.0f, jy = 0.0f;
@@ -549,7 +571,7 @@ __global__ void __launch_bounds__(WF_THREADS, SPEC ? 3 : WF_SHADE_MIN_BLOCKS) k_
     const int n = n0 + n1 + n2;
     const int pp = depth & 1, np_ = pp ^ 1;
     const int stride = gridDim.x * blockDim.x;
-    const int n_r = (n + 31) & ~31;
+    const int n_r = (n + WF_THREADS - 1) / WF_THREADS * WF_THREADS;          // block-uniform trip count (block_append)
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_r; w += stride) {
         ShadeOut o; o.cont = false; o.shadow = false;
         if (w < n) {
@@ -557,9 +579,9 @@ __global__ void __launch_bounds__(WF_THREADS, SPEC ? 3 : WF_SHADE_MIN_BLOCKS) k_
             int q = a.cls[(size_t)cl * a.cap + (w - (cl == 0 ? 0 : (cl == 1 ? n0 : n0 + n1)))];
             shade_any<SPEC>(a, bp, depth, cl, a.pa[pp][q], a.pb[pp][q], a.pc[pp][q], a.hit[q], o);
         }
-        int qn = warp_append(&a.ctr->nq[depth + 1], o.cont);
+        int qn = block_append(&a.ctr->nq[depth + 1], o.cont);
         if (o.cont) { a.pa[np_][qn] = o.nA; a.pb[np_][qn] = o.nB; a.pc[np_][qn] = o.nC; }
-        int qs = warp_append(&a.ctr->nshadow[depth], o.shadow);
+        int qs = block_append(&a.ctr->nshadow[depth], o.shadow);
         if (o.shadow) { a.sa[pp][qs] = o.sA; a.sb[pp][qs] = o.sB; a.sc[pp][qs] = o.sC; }
     }
     // last block out decides whether the next depth is small enough for the tail kernel (queue size is final now)
