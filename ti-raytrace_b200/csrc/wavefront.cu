@@ -201,14 +201,23 @@ __device__ __forceinline__ int feed_lanes(WarpFeed& f, int* cursor, int n, unsig
     return q;
 }
 
-// append the top `take` (<= 32) buffered (queue index | class << 30) entries to the material-sorted shade queues
+// append the top `take` (<= 32) buffered (queue index | class << 30) entries to the material-sorted shade queues.
+// The three class counters are bumped by ONE atomic instruction (lanes 0..2, one address each): a single round trip to the
+// L2 atomic unit per flush instead of three back-to-back ones.
 __device__ __forceinline__ void flush_retired(const WfArgs& a, int depth, const int* rbuf, int rcount, int take, int lane) {
     unsigned e = (lane < take) ? (unsigned)rbuf[rcount - take + lane] : 0u;
     int c = (lane < take) ? (int)(e >> 30) : -1, qq = (int)(e & 0x3fffffffu);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        int pos = warp_append(&a.ctr->ncls[depth][k], c == k);
-        if (c == k) a.cls[(size_t)k * a.cap + pos] = qq;
+    const unsigned m0 = __ballot_sync(0xffffffffu, c == 0), m1 = __ballot_sync(0xffffffffu, c == 1), m2 = __ballot_sync(0xffffffffu, c == 2);
+    int base = 0;
+    if (lane < 3) {
+        const unsigned mk = lane == 0 ? m0 : (lane == 1 ? m1 : m2);
+        if (mk) base = atomicAdd(&a.ctr->ncls[depth][lane], __popc(mk));
+    }
+    const int b0 = __shfl_sync(0xffffffffu, base, 0), b1 = __shfl_sync(0xffffffffu, base, 1), b2 = __shfl_sync(0xffffffffu, base, 2);
+    if (c >= 0) {
+        const unsigned mk = c == 0 ? m0 : (c == 1 ? m1 : m2);
+        const int pos = (c == 0 ? b0 : (c == 1 ? b1 : b2)) + __popc(mk & ((1u << lane) - 1u));
+        a.cls[(size_t)c * a.cap + pos] = qq;
     }
     __syncwarp();
 }
