@@ -211,6 +211,30 @@ def test_pt_rgb_batched_equals_framewise(gpu_ctx):
     assert np.array_equal(integ.hdr.to_numpy(), a)            # BVH in shared memory vs global: same result
 
 
+def test_async_render_deferred_stats_and_ring_overflow(gpu_ctx):
+    """tr_render_pt_rgb only enqueues; tr_stats_get folds the per-batch counter snapshots afterwards.  70 one-frame batches
+    overflow the 64-entry pinned ring (the rest takes the synchronous path): ray counts and film must equal the 70 frames
+    rendered in one batch, and a second render issued before any stats call must not disturb the first one's film"""
+    W = H = 64
+    scene, cam, integ = build_gpu_scene("cornell", W, H)
+    st_one = integ.render_frames(70)
+    a = integ.hdr.to_numpy()
+    gpu_ctx.film_clear(); cam.frame = 0; cam.frame_cpu[0] = 0
+    gpu_ctx.set_option("batch_frames", 1)
+    assert integ.render_frames(70, stats=False) is None
+    b = integ.hdr.to_numpy()                       # the download waits for the render
+    st_many = gpu_ctx.stats()
+    assert np.array_equal(a, b)
+    assert (st_many["rays_closest"], st_many["rays_shadow"], st_many["frames"]) == (st_one["rays_closest"], st_one["rays_shadow"], 70)
+    assert st_many["ms_total"] > 0.0
+    gpu_ctx.set_option("batch_frames", 0)
+    gpu_ctx.film_clear(); cam.frame = 0; cam.frame_cpu[0] = 0
+    integ.render_frames(35, stats=False); integ.render_frames(35, stats=False)      # back to back, no host wait in between
+    assert np.array_equal(integ.hdr.to_numpy(), a)
+    st_last = gpu_ctx.stats()
+    assert st_last["frames"] == 35 and 0 < st_last["rays_closest"] < st_one["rays_closest"]
+
+
 def test_pt_rgb_glass_env_sphere_light_matches_oracle(gpu_ctx, oracle_tables):
     """single_model as shipped: glass sphere.obj, sphere light, env map power 5, smooth normals"""
     W = H = 128
