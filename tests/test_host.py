@@ -157,3 +157,24 @@ def test_native_obj_reader_numbers_and_errors(tmp_path):
         bad = tmp_path / "bad.obj"; bad.write_text(body)
         with pytest.raises((ValueError, FileNotFoundError), match=msg):
             objio.read_obj(str(bad))
+
+
+def test_header_is_plain_c_and_usable_from_c(tmp_path):
+    """include/tiray.h compiles as C99 with -Wall -Werror, and a C program linked against libtiray.so drives the OBJ reader
+    and gets TR_ERR_NO_DEVICE (exit code 3) instead of a silent fallback when no GPU is present (0 on a GPU box)"""
+    import shutil, subprocess, _native
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "client")
+    libdir = os.path.dirname(_native.lib_path())
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cabi", "client.c"), "-o", exe, "-L", libdir, "-l:libtiray.so", "-Wl,-rpath," + libdir])
+    r = subprocess.run([exe, os.path.join(PKG, "model", "cornell_box.obj")], capture_output=True, text=True)
+    assert r.returncode in (0, 3), r.stderr
+    out = r.stdout.splitlines()
+    assert out[0].startswith("material 0 white tris 30 ") and out[3].startswith("material 3 light tris 2 ")
+    assert any(l.startswith("triangles 36 devices") for l in out)
+    assert ("context ok" in r.stdout) == (r.returncode == 0)
+    if r.returncode == 3:
+        assert "no device" in r.stdout
