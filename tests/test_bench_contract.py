@@ -1,0 +1,43 @@
+"""bench.py contract checks that need no GPU: the reference arm (the CPU restatement timed on the host cores) prints ONE JSON
+line with the keys the driver reads; the native arm refuses to run without a CUDA device instead of falling back."""
+import json
+import os
+import subprocess
+import sys
+
+from conftest import ROOT
+
+
+def _run(args, env=None):
+    e = dict(os.environ); e.update(env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True, env=e, cwd=ROOT)
+
+
+def test_reference_arm_json_line():
+    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "0"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, "stdout must carry exactly one JSON line"
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "Mrays/s" and d["unit"] == "Mrays/s" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 0 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["vs_baseline"] is None and d["dtype"] == "f32"
+    assert "cornell_box.py PT_RGB 512x512 64spp" in d["config"]["workload"] and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "spp" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_stay_silent():
+    """under torchrun only rank 0 runs and prints the reference arm; the other ranks exit 0 without work"""
+    r = _run(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"], env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_native_arm_needs_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a CUDA device is present")
+    r = _run(["--steps", "1", "--warmup", "0", "--no-cpu"])
+    assert r.returncode != 0 and r.stdout.strip() == ""          # no JSON line from a CPU fallback
