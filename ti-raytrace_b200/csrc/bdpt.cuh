@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_bdpt_generate(WfArgs a, BdArgs b
 }
 
 // one thread per traced segment of stage d, walking the material-sorted queues k_trace filled (terminal | Disney | glass)
-__global__ void __launch_bounds__(WF_THREADS, 3) k_bdpt_vertex(WfArgs a, BdArgs b, int d) {
+__global__ void __launch_bounds__(WF_THREADS, 4) k_bdpt_vertex(WfArgs a, BdArgs b, int d) {
     const BatchParams bp = *a.bp;
     const int n0 = a.ctr->ncls[d][0], n1 = a.ctr->ncls[d][1], n2 = a.ctr->ncls[d][2];
     const int n = n0 + n1 + n2, n_r = (n + WF_THREADS - 1) / WF_THREADS * WF_THREADS;       // block-uniform trip count (block_append)

@@ -98,6 +98,27 @@ __device__ __forceinline__ int block_append(int* counter, bool pred) {
     return pred ? pos : -1;
 }
 
+// two appends (to two queues) with one set of barriers: k_shade emits a continuation and a shadow ray per vertex
+__device__ __forceinline__ void block_append2(int* counter_a, bool pred_a, int* counter_b, bool pred_b, int& pos_a, int& pos_b) {
+    __shared__ int s_cnt2[2][WF_THREADS / 32];
+    __shared__ int s_base2[2];
+    const unsigned ma = __ballot_sync(0xffffffffu, pred_a), mb = __ballot_sync(0xffffffffu, pred_b);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_cnt2[0][warp] = __popc(ma); s_cnt2[1][warp] = __popc(mb); }
+    __syncthreads();
+    if (threadIdx.x < 2) {                                 // thread 0: queue a, thread 1: queue b -- one atomic instruction for both
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < WF_THREADS / 32; ++w) { int c = s_cnt2[threadIdx.x][w]; s_cnt2[threadIdx.x][w] = tot; tot += c; }
+        s_base2[threadIdx.x] = tot ? atomicAdd(threadIdx.x == 0 ? counter_a : counter_b, tot) : 0;
+    }
+    __syncthreads();
+    const unsigned lt = (1u << lane) - 1u;
+    pos_a = pred_a ? s_base2[0] + s_cnt2[0][warp] + __popc(ma & lt) : -1;
+    pos_b = pred_b ? s_base2[1] + s_cnt2[1][warp] + __popc(mb & lt) : -1;
+    __syncthreads();                                   // the shared slots are rewritten by the next call
+}
+
 // true when an earlier stage handed the remaining paths of this chain to the tail kernel (tail_from: 0 = no hand-over,
 // d >= 1 = k_tail owns the paths from depth d on)
 __device__ __forceinline__ bool tail_took_over(const WfArgs& a, int depth) {
@@ -588,9 +609,9 @@ __global__ void __launch_bounds__(WF_THREADS, SPEC ? 3 : WF_SHADE_MIN_BLOCKS) k_
             int q = a.cls[(size_t)cl * a.cap + (w - (cl == 0 ? 0 : (cl == 1 ? n0 : n0 + n1)))];
             shade_any<SPEC>(a, bp, depth, cl, a.pa[pp][q], a.pb[pp][q], a.pc[pp][q], a.hit[q], o);
         }
-        int qn = block_append(&a.ctr->nq[depth + 1], o.cont);
+        int qn, qs;
+        block_append2(&a.ctr->nq[depth + 1], o.cont, &a.ctr->nshadow[depth], o.shadow, qn, qs);
         if (o.cont) { a.pa[np_][qn] = o.nA; a.pb[np_][qn] = o.nB; a.pc[np_][qn] = o.nC; }
-        int qs = block_append(&a.ctr->nshadow[depth], o.shadow);
         if (o.shadow) { a.sa[pp][qs] = o.sA; a.sb[pp][qs] = o.sB; a.sc[pp][qs] = o.sC; }
     }
     // last block out decides whether the next depth is small enough for the tail kernel (queue size is final now)
