@@ -97,6 +97,7 @@ def measured_peak_gbs():
 def ncu_traffic(workload, kernel_prefix):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel, from the committed ncu capture of the same
     command line (profiles/r01_dram_traffic.json, written from `ncu --metrics dram__bytes_*` by tools/); None if absent"""
+    workload = {"teapot_mc": "teapot_mc16"}.get(workload, workload)      # 64 spp = four batches of the captured 16-frame batch: same launches
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))[workload]
         for k, v in t.items():
@@ -110,6 +111,7 @@ def ncu_traffic(workload, kernel_prefix):
 def ncu_issue(workload):
     """issue-slot utilisation etc. of the dominant kernel from the committed --set full capture (None if absent): the kernels are
     issue-bound, not DRAM-bound, which is why the effective-bandwidth fraction can exceed 1"""
+    workload = {"teapot_mc": "teapot_mc16"}.get(workload, workload)
     try:
         return json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))[workload].get("ncu_full")
     except Exception:
