@@ -243,3 +243,33 @@ def test_bdpt_partial_tiles_and_non_square(gpu_ctx, oracle_tables):
         acc += integ.hdr.to_numpy()
     gpu_ctx.set_shard(0, 1)
     assert np.allclose(acc, g, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("module", ["cornell_box", "veach_bdpt"])
+def test_reference_driver_loop(gpu_ctx, tmp_path, monkeypatch, module):
+    """Main.py's loop (Main.py:16-21: build_scene, then render() until it returns 0) over example.Example.render
+    (example/Example.py:38-59): one sample per call, tone map, frame counter, out.png at frame == sample_count; the film equals
+    the same number of samples rendered in one render_frames call"""
+    import importlib, cv2
+    from conftest import PKG
+    monkeypatch.chdir(PKG)
+    mod = importlib.import_module(module)
+    ex = mod.example(64, 64, 4)
+    ex.out_file = str(tmp_path / "out.png")
+    ex.build_scene()
+    calls = 0
+    while ex.render() == 1:
+        calls += 1
+        assert calls < 50
+    assert calls == 4 and ex.cam.frame == 5 and os.path.exists(ex.out_file)
+    img = cv2.imread(ex.out_file)
+    assert img.shape == (64, 64, 3) and img.mean() > 5
+    a = ex.integrator.hdr.to_numpy()
+    import _native
+    _native.context().film_clear(); ex.cam.frame = 0; ex.cam.frame_cpu[0] = 0      # ti.init() in the example made a fresh context
+    ex.integrator.render_frames(4)
+    b = ex.integrator.hdr.to_numpy()
+    if module == "cornell_box":
+        assert np.array_equal(a, b)
+    else:
+        assert np.allclose(a, b, rtol=1e-4, atol=1e-6)
