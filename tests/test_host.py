@@ -178,3 +178,19 @@ def test_header_is_plain_c_and_usable_from_c(tmp_path):
     assert ("context ok" in r.stdout) == (r.returncode == 0)
     if r.returncode == 3:
         assert "no device" in r.stdout
+
+
+def test_sass_shows_tma_staging_and_sm100a():
+    """the shipped binary is sm_100a code and the small-tree kernels stage the BVH with bulk async copies on an mbarrier
+    (cp.async.bulk = UBLKCP in SASS, B200_PROFILING.md) -- k_trace, k_shadow, k_tail and the lock-step BDPT kernels"""
+    import shutil, subprocess, _native
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("no cuobjdump")
+    lib = _native.lib_path()
+    elf = subprocess.run([cuobjdump, "-lelf", lib], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf and "sm_90" not in elf
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "_Z7k_traceILb1EEv6WfArgsi", lib], capture_output=True, text=True).stdout
+    assert sass.count("UBLKCP") == 2 and "SYNCS.ARRIVE.TRANS64" in sass and "SYNCS.PHASECHK.TRANS64.TRYWAIT" in sass
+    sass0 = subprocess.run([cuobjdump, "-sass", "-fun", "_Z7k_traceILb0EEv6WfArgsi", lib], capture_output=True, text=True).stdout
+    assert "UBLKCP" not in sass0 and "LDG" in sass0            # large trees are walked in global memory
