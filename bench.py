@@ -265,6 +265,7 @@ def run_native(args, wl):
             integ.setup_data_gpu()               # spectral tables H2D + white-point normalisation
         scene.setup_data_gpu()                   # tables H2D (pageable numpy) + env + LBVH build
         ta = time.perf_counter()
+        build_ms = ctx.stats()["ms_build"]       # device time of the LBVH build just done (nothing pending: no wait)
         if wl["normals"]:
             scene.process_normal()
         cam.dirty = True
@@ -298,7 +299,10 @@ def run_native(args, wl):
                       "l2": "L2 flushed (256 MiB write) between timed steps; per-step queue traffic also exceeds L2"},
            "wall_ms_per_step": wall / args.steps * 1e3, "clocks": clocks, "gpu_launches": launches,
            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                   "ms_per_step": e2e_t / max(1, min(args.steps, 3)) * 1e3}}
+                   "ms_per_step": e2e_t / max(1, min(args.steps, 3)) * 1e3},
+           "bvh_build": {"primitives": int(scene.primitive_count), "device_ms": build_ms,
+                         "mprims_per_s": scene.primitive_count / max(build_ms, 1e-6) / 1e3, "launches": 16,
+                         "note": "Morton + 4-pass radix sort + Karras + refit + flatten, inside the e2e region of every step (SURVEY 8d)"}}
 
     # ---- roofline of the dominant kernel (closest-hit trace) + cpu baseline: rank 0, N = 1 only
     if world == 1 and wl.get("bdpt"):

@@ -341,6 +341,7 @@ extern "C" int tr_bvh_build(tr_ctx* ctx) {
     const int n = ctx->np, nn = 2 * n - 1;
     cudaStream_t s = ctx->stream;
     int rc;
+    if ((rc = tr_stats_resolve(ctx))) return rc;      // an asynchronous render still owns the timing events used below
     if ((rc = tr_realloc(ctx, &ctx->d_morton_unsorted, (size_t)n * 2))) return rc;
     for (int k = 0; k < 2; ++k) { if ((rc = tr_realloc(ctx, &ctx->d_keys[k], (size_t)n))) return rc; if ((rc = tr_realloc(ctx, &ctx->d_vals[k], (size_t)n))) return rc; }
     if ((rc = tr_realloc(ctx, &ctx->d_left, (size_t)nn))) return rc;
