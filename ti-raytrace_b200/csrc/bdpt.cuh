@@ -199,6 +199,11 @@ __global__ void __launch_bounds__(WF_THREADS) k_bdpt_paths(WfArgs a, BdArgs b) {
     if (n_closest) atomicAdd(b.ctr, n_closest);
 }
 
+// A strategy of a sample is worth a queue item when both prefixes exist -- and, for l == 0 (the eye sub-path hit an emitter,
+// BDPT_RGB.py:447-451), only when e - 1 is the LAST eye vertex: eye_path stops at the first emitter it hits, so every shorter
+// l == 0 prefix ends on a surface and contributes exactly 0.  k_bdpt_film and the dump hook apply the same rule.
+__host__ __device__ __forceinline__ bool bd_strategy_live(int e, int l, int ed, int ld) { return e <= ed && l <= ld && (l != 0 || e == ed); }
+
 // Connection queue: item = sample | e << 26 | l << 29, emitted strategy-major per warp so that the connect kernel's warps
 // are (mostly) homogeneous in strategy type.  Loop bounds of BDPT_RGB.py:625-637.
 __global__ void __launch_bounds__(WF_THREADS) k_bdpt_items(WfArgs a, BdArgs b) {
@@ -215,7 +220,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_bdpt_items(WfArgs a, BdArgs b) {
             for (int l = 0; l <= BD_LIGHT_MAX; ++l) {
                 const int depth = l + e - 2;
                 if ((l == 1 && e == 1) || depth < 0 || depth > BD_MAX_DEPTH) continue;      // warp-uniform
-                total += __popc(__ballot_sync(0xffffffffu, e <= ed && l <= ld));
+                total += __popc(__ballot_sync(0xffffffffu, bd_strategy_live(e, l, ed, ld)));
             }
         int off = 0;
         if (lane == 0 && total > 0) off = atomicAdd((int*)(b.ctr + 2), total);
@@ -224,7 +229,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_bdpt_items(WfArgs a, BdArgs b) {
             for (int l = 0; l <= BD_LIGHT_MAX; ++l) {
                 const int depth = l + e - 2;
                 if ((l == 1 && e == 1) || depth < 0 || depth > BD_MAX_DEPTH) continue;
-                const bool valid = e <= ed && l <= ld;
+                const bool valid = bd_strategy_live(e, l, ed, ld);
                 const unsigned m = __ballot_sync(0xffffffffu, valid);
                 if (valid) b.items[off + __popc(m & ((1u << lane) - 1u))] = (unsigned)s | ((unsigned)e << 26) | ((unsigned)l << 29);
                 off += __popc(m);
@@ -607,7 +612,8 @@ __global__ void __launch_bounds__(WF_THREADS) k_bdpt_film(WfArgs a, BdArgs b) {
                 const size_t s = (size_t)f * a.npix + p;
                 const int ed = b.depths[s], ld = b.depths[b.cap + s];
                 for (int e = 2; e <= ed; ++e)
-                    for (int l = 0; l <= ld && l + e - 2 <= BD_MAX_DEPTH; ++l) rad = rad + f4xyz(b.contrib[(size_t)bd_row(e, l) * b.cap + s]);
+                    for (int l = 0; l <= ld && l + e - 2 <= BD_MAX_DEPTH; ++l)
+                        if (bd_strategy_live(e, l, ed, ld)) rad = rad + f4xyz(b.contrib[(size_t)bd_row(e, l) * b.cap + s]);     // the others are exactly 0
             }
             const float* sp = b.splat + ((size_t)f * a.W * a.H + g) * 3;
             rad = rad + mk3(sp[0], sp[1], sp[2]);
@@ -799,6 +805,7 @@ extern "C" int tr_test_bdpt_dump(tr_ctx* ctx, int n, const int32_t* px, const in
         float* co = contrib + (size_t)k * 7 * 7 * 4;
         for (int c = 0; c < 7 * 7 * 4; ++c) co[c] = 0.0f;
         for (int e = 2; e <= d[0]; ++e) for (int l = 0; l <= d[1] && l + e - 2 <= BD_MAX_DEPTH; ++l) {
+            if (!bd_strategy_live(e, l, d[0], d[1])) continue;          // never queued: identically zero
             float4 w; int row = (e - 2) * 6 - ((e - 2) * (e - 3)) / 2 + l;
             TR_CUDA(ctx, cudaMemcpy(&w, ctx->d_bd_contrib + (size_t)row * cap + s, 16, cudaMemcpyDeviceToHost));
             float* o = co + ((e - 1) * 7 + l) * 4; o[0] = w.x; o[1] = w.y; o[2] = w.z; o[3] = (float)(x * 65536 + y);
