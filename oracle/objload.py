@@ -151,6 +151,8 @@ def load_scene(paths, shapes=(), material_edit=None):
             row[1] = -1.0
             mat_index = len(mats); mats.append(row)
             fmt = m.vertex_format
+            if not m.vertices:
+                continue                                 # a material no face uses: num_vert == 0, only the material row exists (Scene.py:93-97,141)
             stride = {"T2F_V3F": 5, "T2F_N3F_V3F": 8, "N3F_V3F": 6, "V3F": 3}[fmt]
             buf = m.vertices
             for k in range(0, len(buf), stride):

@@ -194,3 +194,44 @@ def test_sass_shows_tma_staging_and_sm100a():
     assert sass.count("UBLKCP") == 2 and "SYNCS.ARRIVE.TRANS64" in sass and "SYNCS.PHASECHK.TRANS64.TRYWAIT" in sass
     sass0 = subprocess.run([cuobjdump, "-sass", "-fun", "_Z7k_traceILb0EEv6WfArgsi", lib], capture_output=True, text=True).stdout
     assert "UBLKCP" not in sass0 and "LDG" in sass0            # large trees are walked in global memory
+
+
+def test_random_obj_files_pack_like_the_oracle_loader(tmp_path, monkeypatch):
+    """12 random OBJ + MTL files (polygons of 3-6 corners, v / v/vt / v//vn / v/vt/vn per material, negative indices,
+    faces before any usemtl, usemtl of names the MTL does not define, emissive and transparent materials): the product
+    (native reader + Scene packing) and the oracle's Python loader produce the same tables bit for bit"""
+    import Scene
+    from oracle import objload
+    rng = np.random.RandomState(11)
+    for case in range(12):
+        nv, nn, nt = rng.randint(8, 60), rng.randint(1, 20), rng.randint(1, 20)
+        lines = ["mtllib m%d.mtl" % case]
+        lines += ["v %.6g %.6g %.6g" % tuple(rng.randn(3) * 10.0 ** rng.randint(-2, 3)) for _ in range(nv)]
+        lines += ["vn %.5f %.5f %.5f" % tuple(rng.randn(3)) for _ in range(nn)]
+        lines += ["vt %.4f %.4f" % tuple(rng.rand(2)) for _ in range(nt)]
+        mats = ["a", "b", "c", "ghost"]                       # "ghost" is not in the MTL
+        fmt_of = {}
+        order = [None] + [mats[k] for k in rng.randint(0, 4, 6)]   # first group: faces before any usemtl -> "default<k>"
+        for m in order:
+            if m is not None:
+                lines.append("usemtl " + m)
+            fmt = fmt_of.setdefault(m, rng.randint(0, 4))
+            for _ in range(rng.randint(1, 5)):
+                corners = []
+                for _c in range(rng.randint(3, 7)):
+                    neg = rng.rand() < 0.3
+                    a = -rng.randint(1, nv + 1) if neg else rng.randint(1, nv + 1)
+                    b = -rng.randint(1, nt + 1) if neg else rng.randint(1, nt + 1)
+                    c = -rng.randint(1, nn + 1) if neg else rng.randint(1, nn + 1)
+                    corners.append(("%d" % a, "%d/%d" % (a, b), "%d//%d" % (a, c), "%d/%d/%d" % (a, b, c))[fmt])
+                lines.append("f " + " ".join(corners))
+        (tmp_path / ("r%d.obj" % case)).write_text("\n".join(lines) + "\n")
+        (tmp_path / ("m%d.mtl" % case)).write_text(
+            "newmtl a\nKd 0.1 0.2 0.3\nd 1.0\nNs 10\nNi 1.2\n# comment\nnewmtl b\nKd 0.9 0.9 0.9\nKe 20 30 40\n\nnewmtl c\nKd 1 1 1\nTr 0.6\nNi 1.45\nNs 3.5\n")
+        path = str(tmp_path / ("r%d.obj" % case))
+        s = Scene.Scene(); s.add_obj(path); s.setup_data_cpu()
+        t = objload.load_scene([path])
+        assert np.array_equal(s.vertex_np, t.vertex), case
+        assert np.array_equal(s.primitive_np, t.primitive) and np.array_equal(s.material_np, t.material), case
+        assert np.array_equal(np.asarray(s.light_cpu, np.int32), t.light), case
+        assert np.array_equal(s.minboundarynp, t.bmin) and np.array_equal(s.maxboundarynp, t.bmax), case
