@@ -41,6 +41,18 @@ def test_camera_matches_oracle():
     view, view_inv, eye, fx, fy, cx, cy = oracle.camera_matrices(512, 512, (278.0, 274.4, -279.6), 768.5923)
     assert np.array_equal(cam.view_np[0], view) and np.array_equal(cam.view_inv_np[0], view_inv)
     assert np.array_equal(cam.eye_np[0], eye) and (cam.fx, cam.fy, cam.cx, cam.cy) == (fx, fy, cx, cy)
+    # orbit positions: yaw / pitch (pitch is clamped to +-1.57, Camera.py:71), non-square images
+    rng = np.random.RandomState(5)
+    for _ in range(20):
+        W, H = int(rng.randint(16, 900)), int(rng.randint(16, 900))
+        yaw, pitch, scale = float(rng.uniform(-3.2, 3.2)), float(rng.uniform(-2.0, 2.0)), float(rng.uniform(0.5, 2000.0))
+        tgt = tuple(float(x) for x in rng.randn(3) * 100.0)
+        c2 = Camera.Camera(W, H, 16)
+        c2.target[:] = tgt
+        c2.set_view_point(yaw, pitch, 0.0, scale)
+        view, view_inv, eye, fx, fy, cx, cy = oracle.camera_matrices(W, H, tgt, scale, yaw, pitch)
+        assert np.array_equal(c2.view_np[0], view) and np.array_equal(c2.view_inv_np[0], view_inv) and np.array_equal(c2.eye_np[0], eye)
+        assert (c2.fx, c2.fy, c2.cx, c2.cy) == (fx, fy, cx, cy)
     cam.update_frame(); assert cam.frame == 1 and cam.frame_cpu[0] == 1
     with pytest.raises(ZeroDivisionError):          # spp < 4 raises in the reference ctor
         Camera.Camera(8, 8, 1)
