@@ -247,3 +247,24 @@ def test_random_obj_files_pack_like_the_oracle_loader(tmp_path, monkeypatch):
         assert np.array_equal(s.primitive_np, t.primitive) and np.array_equal(s.material_np, t.material), case
         assert np.array_equal(np.asarray(s.light_cpu, np.int32), t.light), case
         assert np.array_equal(s.minboundarynp, t.bmin) and np.array_equal(s.maxboundarynp, t.bmax), case
+
+
+def test_texture_loader_matches_oracle(tmp_path, monkeypatch):
+    """Texture.load_image (texture/Texture.py:18-34): packed RGB i32, buf[x][H-1-row] -- product vs oracle, on the shipped
+    environment map and on a random non-square image"""
+    import cv2
+    import Scene  # noqa: F401  (puts texture/ on sys.path like the reference's Scene.py:3-4)
+    import Texture as TX
+    monkeypatch.chdir(PKG)
+    rng = np.random.RandomState(2)
+    img = rng.randint(0, 256, (37, 91, 3)).astype(np.uint8)
+    p = str(tmp_path / "t.png"); cv2.imwrite(p, img)
+    for path in ("image/env.png", "image/black.png", p):
+        t = TX.Texture(); t.load_image(path)
+        packed, w, h = oracle.load_env(path if os.path.isabs(path) else os.path.join(PKG, path))
+        assert (t.wid, t.hgt) == (w, h)
+        assert np.array_equal(np.asarray(t.np_img, np.int32).reshape(w, h), packed)
+    # layout: x major, y up; channels packed as R << 16 | G << 8 | B (cv2 reads BGR)
+    t = TX.Texture(); t.load_image(p)
+    b, g, r = (int(v) for v in img[36 - 5, 7])
+    assert int(np.asarray(t.np_img).reshape(91, 37)[7, 5]) == (r << 16) | (g << 8) | b
