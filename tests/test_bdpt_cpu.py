@@ -78,3 +78,38 @@ def test_oracle_bdpt_mask_shards_sum(oracle_tables):
     a, _ = s.render_bdpt_rgb(W, H, 0, 2, mask=m)
     b, _ = s.render_bdpt_rgb(W, H, 0, 2, mask=1 - m)
     assert np.allclose(a + b, full, rtol=1e-4, atol=1e-6)
+
+
+def test_cpp_oracle_matches_literal_python_transliteration(oracle_tables):
+    """connect_path + mis_weight restated a second time (oracle/bdpt_literal.py: dense Vertex arrays, field-by-field copy(),
+    the in-place save / overwrite / walk / restore of mis_weight, -1 indices wrapping into the padding slot) reproduce the C++
+    oracle's weighted contribution of every strategy and the splat pixel of the light-tracing ones: two independent
+    readings of BDPT_RGB.py:258-580 agree, on the Veach room and on the Cornell box"""
+    from oracle import bdpt_literal as BL, objload
+    from conftest import model
+    import ctypes as C
+    for name, fit, smooth, W in (("veach", 0.5, True, 40), ("cornell", 0.8, False, 32)):
+        H = W
+        if name == "veach":
+            s = veach_oracle(oracle_tables, W, H, fast=False); tables = s.t
+        else:
+            tables = oracle_tables("cornell"); s = oracle.OracleScene(tables).build()
+        cam = oracle.fit_camera(tables, W, H, fit)
+        s.set_camera(cam[1], cam[2], *cam[3:]); s.set_camera_view(cam[0], W, H)
+        rng_state = np.random.RandomState(4)
+        n_strat = n_weighted = 0
+        for frame in (0, 2):
+            for _ in range(60):
+                i, j = int(rng_state.randint(0, W)), int(rng_state.randint(0, H))
+                verts, depths, contrib = s.bdpt_pixel_dump(i, j, frame)
+
+                def rng(block, i=i, j=j, frame=frame):
+                    out = np.zeros(4, np.float32); s.lib.orc_rng(0, i * 65536 + j, frame, block, out); return out
+                px = BL.Pixel(s, tables, cam, W, H, verts, depths, i, j, frame)
+                for (e, l), (rgb, (u, v)) in px.all_strategies(rng).items():
+                    ref = contrib[e - 1, l]
+                    assert np.allclose(rgb, ref[:3], rtol=2e-5, atol=1e-12), (name, i, j, frame, e, l, rgb, ref)
+                    if e == 1:
+                        assert (u * 65536 + v if u >= 0 else -1) == int(ref[3]), (name, i, j, frame, l)
+                    n_strat += 1; n_weighted += bool(rgb[0] > 0 and rgb[1] > 0 and rgb[2] > 0 and l + e != 2)
+        assert n_strat > 500 and n_weighted > 50, (n_strat, n_weighted)
