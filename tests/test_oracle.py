@@ -124,3 +124,30 @@ def test_process_normal_smooths_sphere(oracle_tables):
     radial = pos / np.linalg.norm(pos, axis=1, keepdims=True)
     cosang = (radial * nrm).sum(1)
     assert np.isfinite(nrm).all() and cosang.min() > 0.99
+
+
+def test_cpp_oracle_pt_rgb_matches_literal_python_transliteration(oracle_tables):
+    """PathTrace.render restated a second time in plain Python (oracle/pt_literal.py: hit attributes, light sampling, Disney
+    sampling and evaluation, NEE with the power heuristic, throughput recursion, RNG block order) against the C++ oracle, pixel by
+    pixel on the Cornell box for an unjittered and two jittered frames.  numpy's float32 sin / cos differ from glibc's by ULPs:
+    rel 1e-4, and <= 1 % of the pixels may differ more (a path that changes a branch at a float boundary)"""
+    from oracle import pt_literal as PL
+    W = H = 24
+    for glass0, frames in ((False, (0, 1, 3)), (True, (0, 3))):       # second pass: the white walls / boxes become glass (ior 1.3, extinction 5)
+      t = oracle_tables("cornell", glass0=glass0)
+      s = oracle.OracleScene(t).build()
+      cam = oracle.fit_camera(t, W, H)
+      s.set_camera(cam[1], cam[2], *cam[3:])
+      tr = PL.Tracer(s, t, cam)
+      for frame in frames:
+          hdr, cnt = s.render_pt_rgb(W, H, frame, 1)
+          ref = hdr * np.float32(frame + 1)                # film started at 0: hdr = L / (frame + 1), exact for these frames
+          got = np.zeros_like(ref); nc = ns = 0
+          for i in range(W):
+              for j in range(H):
+                  got[i, j], (a, b) = tr.pixel(i, j, frame)
+                  nc += a; ns += b
+          bad = np.abs(got - ref).max(axis=2) > 1e-4 * np.maximum(1.0, np.abs(ref).max(axis=2))
+          assert bad.mean() <= 0.01, (frame, int(bad.sum()))
+          assert abs(nc - cnt["closest"]) <= 0.005 * cnt["closest"] and abs(ns - cnt["shadow"]) <= 0.005 * cnt["shadow"]
+          assert ref.max() > 1.0 and (ref.max(axis=2) > 0).mean() > (0.02 if glass0 else 0.5)
