@@ -1,22 +1,26 @@
 #!/usr/bin/env python
 """bench.py — headline metric of BASELINE.json: Mrays/s (and ms/spp) of PT_RGB.
 
-  python bench.py --gpus N --steps K --warmup W [--workload cornell|teapot_mc|teapot_mc16|spectral_box] [--impl native|reference]
+  python bench.py --gpus N --steps K --warmup W [--workload cornell|teapot_mc|teapot_mc16|spectral_box|veach_bdpt] [--impl native|reference]
 
 A step = one full pass of the hot path over one batch: clear the film, render `spp` samples per pixel
 (cornell: 512x512, 64 spp = BASELINE configs[1]; teapot_mc: 1024x1024, 64 spp = configs[2]; teapot_mc16: 16 spp;
-spectral_box: PT_Spec hero-wavelength 512x512, 64 spp = configs[3]) with the
-scene, BVH and camera resident in HBM, and (N > 1) one NCCL sum-reduce of the film.  rays = closest-hit
-traversals + shadow traversals actually executed (device queue counters).
+spectral_box: PT_Spec hero-wavelength 512x512, 64 spp = configs[3]; veach_bdpt: BDPT_RGB = configs[4]) with the
+scene, BVH and camera resident in HBM, and (N > 1) one NCCL sum-reduce of the film (tr_film_reduce: ncclReduce enqueued by
+the library on the render stream).  rays = closest-hit traversals + shadow traversals actually executed (device queue
+counters).
 
   value      whole-job Mrays/s, timed with CUDA events on the stream the kernels run on, max over ranks
   e2e        the same metric through the public Python API with HOST buffers: scene tables H2D + LBVH
-             build + render + tone map + film D2H inside the timed region
+             build + render + film reduce + tone map + film D2H inside the timed region
   roofline   the closest-hit trace kernel: algorithmic bytes (48 B/ray + 32 B per internal-node
              visit + 68 B per leaf test, visit counts from the counters build of the same kernel) / mean
-             kernel time (CUDA events around every launch of it) vs the measured HBM copy bandwidth
+             kernel time (CUDA events around every launch of it) vs the measured HBM copy bandwidth;
+             roofline.kernels adds the shade and shadow kernels by the same rules (224 / 176 / 112 B per vertex)
+  workloads  the default run (cornell) also carries a `workloads.teapot_mc` sub-record: the 130 720-triangle scene of
+             BASELINE configs[2] measured the same way in the same process, at every N
   cpu_baseline / --impl reference: the reference algorithm restated on the CPU (oracle/, -O3 -ffast-math,
-             OpenMP on all host cores) on a bounded sample of the same workload (Taichi is not installable).
+             OpenMP on ALL host cores, also under torchrun) on the same workload (Taichi is not installable).
 """
 import argparse
 import json
@@ -46,6 +50,13 @@ WORKLOADS = {
                        desc="veach_bdpt.py BDPT_RGB 512x512 32spp MAX_DEPTH 5 (BASELINE configs[4])", normals=True, bdpt=True, fit=0.5),
 }
 MAX_DEPTH = 15
+L2_NOTE = "GPU arm: L2 flushed (256 MiB write) between timed steps; per-step queue traffic also exceeds L2"
+
+
+def workload_config(wl):
+    """the `config` object: identical in the native and the reference arm (same workload, same samples per step)"""
+    return {"workload": wl["desc"], "resolution": "%dx%d" % (wl["W"], wl["H"]), "spp_per_step": wl["spp"],
+            "max_depth": wl.get("max_depth", 5 if wl.get("bdpt") else MAX_DEPTH), "l2": L2_NOTE}
 
 
 # --------------------------------------------------------------------------------------------- helpers
@@ -94,17 +105,23 @@ def measured_peak_gbs():
         return 6650.0, "fallback"
 
 
+def _traffic_table():
+    for name in ("r02_dram_traffic.json", "r01_dram_traffic.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", name))), name
+        except Exception:
+            pass
+    return {}, None
+
+
 def ncu_traffic(workload, kernel_prefix):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel, from the committed ncu capture of the same
-    command line (profiles/r01_dram_traffic.json, written from `ncu --metrics dram__bytes_*` by tools/); None if absent"""
+    command line (profiles/r0N_dram_traffic.json, written from `ncu --metrics dram__bytes_*` by tools/); None if absent"""
     workload = {"teapot_mc": "teapot_mc16"}.get(workload, workload)      # 64 spp = four batches of the captured 16-frame batch: same launches
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))[workload]
-        for k, v in t.items():
-            if k.startswith(kernel_prefix):
-                return v["dram_bytes_per_launch_all"]
-    except Exception:
-        pass
+    t, _ = _traffic_table()
+    for k, v in t.get(workload, {}).items():
+        if k.startswith(kernel_prefix) and isinstance(v, dict):
+            return v.get("dram_bytes_per_launch_all")
     return None
 
 
@@ -112,10 +129,15 @@ def ncu_issue(workload):
     """issue-slot utilisation etc. of the dominant kernel from the committed --set full capture (None if absent): the kernels are
     issue-bound, not DRAM-bound, which is why the effective-bandwidth fraction can exceed 1"""
     workload = {"teapot_mc": "teapot_mc16"}.get(workload, workload)
+    t, _ = _traffic_table()
+    return t.get(workload, {}).get("ncu_full")
+
+
+def host_threads():
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))[workload].get("ncu_full")
+        return len(os.sched_getaffinity(0))
     except Exception:
-        return None
+        return os.cpu_count() or 1
 
 
 def oracle_tables(wl):
@@ -124,9 +146,17 @@ def oracle_tables(wl):
     return objload.load_scene([os.path.join(PKG, "model", f) for f in wl["files"]], shapes=shapes)
 
 
-def cpu_reference_run(wl, spp, frame_begin=0):
-    """the reference algorithm on the host cores (oracle, fast build): returns (Mrays/s, rays, seconds, threads)"""
+_cpu_scenes = {}
+
+
+def cpu_scene(wl):
+    """oracle-side scene of a workload (fast build), built once per process"""
+    key = wl["module"]
+    if key in _cpu_scenes:
+        return _cpu_scenes[key]
     from oracle import oracle
+    # torchrun exports OMP_NUM_THREADS=1: the CPU baseline is defined on ALL host cores of the box
+    oracle.lib(True).orc_set_num_threads(host_threads())
     t = oracle_tables(wl)
     if wl.get("spectral"):
         for k in range(3):                          # example/spectral_box.py:22-27
@@ -141,6 +171,16 @@ def cpu_reference_run(wl, spp, frame_begin=0):
     if wl.get("spectral"):
         from oracle import spectral
         spectral.attach(s, PKG)
+    _cpu_scenes[key] = s
+    return s
+
+
+def cpu_reference_run(wl, spp, frame_begin=0):
+    """the reference algorithm on the host cores (oracle, fast build): returns (Mrays/s, rays, seconds, threads, counters)"""
+    from oracle import oracle
+    s = cpu_scene(wl)
+    if wl.get("spectral"):
+        from oracle import spectral
         t0 = time.perf_counter()
         _, cnt = spectral.render_pt_spec(s, wl["W"], wl["H"], frame_begin, spp, wl["max_depth"], 0)
     elif wl.get("bdpt"):
@@ -155,25 +195,38 @@ def cpu_reference_run(wl, spp, frame_begin=0):
 
 
 # --------------------------------------------------------------------------------------------- reference arm
+def reference_measure(wl, steps, warmup, spp):
+    for _ in range(warmup):
+        cpu_reference_run(wl, 1)
+    rays = 0; secs = 0.0; cores = 1
+    for _ in range(steps):
+        _, r, dt, cores, _ = cpu_reference_run(wl, spp)
+        rays += r; secs += dt
+    v = rays / secs / 1e6
+    sample = "%dx%d, %d spp per step (of %d), %d steps, all %d host threads, oracle/liboracle_fast.so" % (wl["W"], wl["H"], spp, wl["spp"], steps, cores)
+    return {"value": v, "unit": "Mrays/s", "ms_per_step": secs / steps * 1e3, "ms_per_spp": secs / steps / spp * 1e3, "rays_per_step": rays // steps,
+            "config": workload_config(wl), "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
 def run_reference(args, wl):
+    """the reference's own CPU path (restated: Taichi is not installable) on all host cores of the box, full workload per
+    step.  Rank 0 alone runs and prints; the other ranks of a torchrun launch exit 0 without work."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_spp = 4 if args.workload in ("cornell", "spectral_box") else 1      # veach_bdpt: 1 spp = 1.2 M traversals, ~0.5 s
-    for _ in range(args.warmup):
-        cpu_reference_run(wl, 1)
-    rays = 0; secs = 0.0; cores = 1
-    for k in range(args.steps):
-        _, r, dt, cores, _ = cpu_reference_run(wl, sample_spp)
-        rays += r; secs += dt
-    v = rays / secs / 1e6
-    sample = "%dx%d, %d spp per step (of %d), all %d host threads, oracle/liboracle_fast.so" % (wl["W"], wl["H"], sample_spp, wl["spp"], cores)
-    out = {"impl": "reference", "metric": "Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "ms_per_spp": secs / args.steps / sample_spp * 1e3,
-           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "reference assets (model/*.obj), seed 0",
-           "config": {"workload": wl["desc"], "sample": sample},
-           "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
-           "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    # the stated config: every step renders the workload's full spp (the BDPT workload is bounded to 4 of its 32 spp: ~10 s per step)
+    spp = 4 if wl.get("bdpt") else wl["spp"]
+    m = reference_measure(wl, args.steps, args.warmup, spp)
+    out = {"impl": "reference", "metric": "Mrays/s", "value": m["value"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "ms_per_spp": m["ms_per_spp"],
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "reference assets (model/*.obj), counter-based RNG seed 0",
+           "config": m["config"], "rays_per_step": m["rays_per_step"], "cpu_baseline": m["cpu_baseline"], "e2e": m["e2e"]}
+    if args.workload == "cornell" and not args.no_sub:
+        # the 130 720-triangle scene next to it: a bounded sample (16 of 64 spp, 2 steps) so the arm stays within minutes
+        sub = WORKLOADS["teapot_mc"]
+        sm = reference_measure(sub, max(1, min(args.steps, 2)), min(args.warmup, 1), 16)
+        out["workloads"] = {"teapot_mc": sm}
     print(json.dumps(out))
 
 
@@ -188,84 +241,105 @@ def build_example(wl):
     return ex
 
 
-def run_native(args, wl):
-    import numpy as np
+class Dist:
+    """torch.distributed as plumbing: barrier, max / sum over ranks, gather of the per-rank records"""
+
+    def __init__(self, world, local):
+        self.world, self.local = world, local
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+
+    def reduce(self, values, op):
+        if self.world == 1:
+            return list(values)
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor(list(values), dtype=torch.float64, device="cuda:%d" % self.local)
+        dist.all_reduce(t, op={"max": dist.ReduceOp.MAX, "sum": dist.ReduceOp.SUM}[op])
+        return t.tolist()
+
+    def gather(self, values):
+        if self.world == 1:
+            return [list(values)]
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor(list(values), dtype=torch.float64, device="cuda:%d" % self.local)
+        out = [torch.zeros_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t)
+        return [o.tolist() for o in out]
+
+
+def measure_native(args, name, steps, warmup, rank, world, local, D, detail=True):
+    """one workload on this rank's context: device-timed steps, e2e through the host-buffer API, and (N = 1, detail) the
+    roofline of the trace / shade / shadow kernels plus the CPU baseline.  Returns the record (same on every rank)."""
     import torch
     import _native
     import parallel
-    rank, world, local = parallel.init_process_group("nccl" if args.gpus > 1 else None)
-    if world != args.gpus and args.gpus > 1:
-        raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torchrun)" % (args.gpus, world))
-    torch.cuda.set_device(local)
-    import torch.distributed as dist
-    ex = build_example(wl)                      # ti.init() -> context on LOCAL_RANK
+    import UtilsFunc as UF
+    wl = WORKLOADS[name]
+    ex = build_example(wl)                      # ti.init() -> fresh context on LOCAL_RANK
     ctx = _native.context()
-    ctx.set_shard(rank, world)
     stream = torch.cuda.Stream(device=local)
     ctx.stream_set(stream.cuda_stream)
-    integ, cam = ex.integrator, ex.cam
+    parallel.comm_init(ctx)                     # library-owned NCCL communicator + tile shard of this rank
+    integ, cam, scene = ex.integrator, ex.cam, ex.scene
     spp = wl["spp"]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:%d" % local)     # > 126 MB L2
-    film = parallel.film_tensor(ctx)            # torch view of the device film (zero copy), made once
 
     def one_step():
         ctx.film_clear(); cam.frame = 0; cam.frame_cpu[0] = 0
         integ.render_frames(spp, stats=False)           # asynchronous: the film reduce is enqueued right behind the last kernel
-        if world > 1:
-            with torch.cuda.stream(stream):
-                parallel.reduce_film(film, dst=0)
-        return ctx.stats()
+        ctx.film_reduce()                               # ncclReduce on the render stream (no-op for one rank)
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         one_step()
     torch.cuda.synchronize(local)
-    if world > 1:
-        dist.barrier()
+    D.barrier()
     sampler = ClockSampler(local); sampler.start()
     rays = 0; launches = 0; ms = 0.0
     t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         with torch.cuda.stream(stream):
             flush.zero_()                        # L2 flush between timed iterations (outside the timed events)
         torch.cuda.synchronize(local)
-        if world > 1:
-            dist.barrier()
+        D.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
             e0.record(stream)
-            st = one_step()
+            one_step()
             e1.record(stream)
         torch.cuda.synchronize(local)
         ms += e0.elapsed_time(e1)
+        st = ctx.stats()
         rays += int(st["rays_closest"]) + int(st["rays_shadow"]); launches += int(st["kernel_launches"])
     wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
-    if world > 1:
-        tm = torch.tensor([ms], dtype=torch.float64, device="cuda:%d" % local); dist.all_reduce(tm, op=dist.ReduceOp.MAX); ms = float(tm.item())
-        tr = torch.tensor([rays, launches], dtype=torch.int64, device="cuda:%d" % local); dist.all_reduce(tr, op=dist.ReduceOp.SUM)
-        rays, launches = int(tr[0].item()), int(tr[1].item())
-    value = rays / (ms * 1e-3) / 1e6
+    per_rank = D.gather([ms / steps, rays / steps])
+    ms_max = D.reduce([ms], "max")[0]
+    rays_all, launches_all = D.reduce([rays, launches], "sum")
+    rays_all, launches_all = int(rays_all), int(launches_all)
+    value = rays_all / (ms_max * 1e-3) / 1e6
     paths_in_flight = int(st["paths_in_flight"])
 
-    # ---- e2e: public API, host buffers, H2D + build + render + tone map + D2H inside the timed region
-    import UtilsFunc as UF
-    scene = ex.scene
+    # ---- e2e: public API, host buffers, H2D + build + render + reduce + tone map + D2H inside the timed region
     h2d = scene.vertex_np.nbytes + scene.primitive_np.nbytes + scene.material_np.nbytes + scene.env.np_img.nbytes + 64 + 64 + 12
     if wl.get("spectral"):                       # sensor, rgb2spec table, four spectra, sky state
         h2d += integ.data_np.nbytes + integ.rgb2spec.table_data_np.nbytes + integ.rgb2spec.table_scale_np.nbytes + 113 * 4
         h2d += sum(sp.data_np.nbytes for sp in (integ.d65, integ.white, integ.red, integ.green))
-    d2h = 2 * wl["W"] * wl["H"] * 12
-    e2e_rays = 0; e2e_t = 0.0
-    for k in range(max(1, min(args.steps, 3)) + 1):
+    d2h = 2 * wl["W"] * wl["H"] * 12 if rank == 0 else 0          # only the root presents (and downloads) the image
+    n_e2e = max(1, min(steps, 3))
+    e2e_rays = 0; e2e_t = 0.0; build_ms = 0.0; checksum = 0.0
+    for k in range(n_e2e + 1):
         torch.cuda.synchronize(local)
-        if world > 1:
-            dist.barrier()
+        D.barrier()
         t0 = time.perf_counter()
         if wl.get("spectral"):
             integ.setup_data_gpu()               # spectral tables H2D + white-point normalisation
-        scene.setup_data_gpu()                   # tables H2D (pageable numpy) + env + LBVH build
+        scene.setup_data_gpu()                   # tables H2D (through pinned staging) + env + LBVH build
         ta = time.perf_counter()
-        build_ms = ctx.stats()["ms_build"]       # device time of the LBVH build just done (nothing pending: no wait)
         if wl["normals"]:
             scene.process_normal()
         cam.dirty = True
@@ -273,90 +347,138 @@ def run_native(args, wl):
         tb = time.perf_counter()
         integ.render_frames(spp, stats=False)
         tc = time.perf_counter()
-        if world > 1:
-            with torch.cuda.stream(stream):
-                parallel.reduce_film(parallel.film_tensor(ctx), dst=0)
-        UF.tone_map(0.5, integ.hdr, integ.rgb_film)
-        hdr_host, rgb_host = ctx.film_download(True, True)
+        ctx.film_reduce()
+        if rank == 0:
+            UF.tone_map(0.5, integ.hdr, integ.rgb_film)
+            hdr_host, rgb_host = ctx.film_download(True, True, view=True)      # DMA into the context's pinned host buffers
+            checksum = float(hdr_host[::37, ::41].sum())                      # the host reads the result
         torch.cuda.synchronize(local)
         dt = time.perf_counter() - t0
         st2 = ctx.stats()
+        build_ms = st2["ms_build"]
         if args.verbose and rank == 0:
-            print("e2e pass %d: upload+build %.2f ms, normals %.2f, render enqueue %.2f (device %.2f), reduce+tonemap+download (incl. waiting for the render) %.2f" %
-                  (k, (ta - t0) * 1e3, (tb - ta) * 1e3, (tc - tb) * 1e3, st2["ms_total"], (t0 + dt - tc) * 1e3), file=sys.stderr)
+            print("e2e pass %d (%s): upload+build %.2f ms, normals %.2f, render enqueue %.2f (device %.2f), reduce+tonemap+download (incl. waiting for the render) %.2f" %
+                  (k, name, (ta - t0) * 1e3, (tb - ta) * 1e3, (tc - tb) * 1e3, st2["ms_total"], (t0 + dt - tc) * 1e3), file=sys.stderr)
         if k > 0:                                # first pass is warm-up (graph re-capture after the rebuild)
             e2e_t += dt; e2e_rays += int(st2["rays_closest"]) + int(st2["rays_shadow"])
-    if world > 1:
-        tm = torch.tensor([e2e_t], dtype=torch.float64, device="cuda:%d" % local); dist.all_reduce(tm, op=dist.ReduceOp.MAX); e2e_t = float(tm.item())
-        tr = torch.tensor([e2e_rays], dtype=torch.int64, device="cuda:%d" % local); dist.all_reduce(tr, op=dist.ReduceOp.SUM); e2e_rays = int(tr.item())
+    e2e_t = D.reduce([e2e_t], "max")[0]
+    e2e_rays = int(D.reduce([e2e_rays], "sum")[0])
+    h2d_all, d2h_all = (int(v) for v in D.reduce([h2d, d2h], "sum"))
     e2e_value = e2e_rays / e2e_t / 1e6
 
-    out = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms / args.steps, "ms_per_spp": ms / args.steps / spp, "higher_is_better": True, "scaling": "strong",
+    cfg = workload_config(wl)
+    cfg.update({"paths_in_flight": paths_in_flight,
+                "tile_shard": "32x32 tiles, rank=(tx+3ty)%N, 1 ncclReduce per step (tr_film_reduce)" if world > 1 else "none"})
+    out = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+           "ms_per_step": ms_max / steps, "ms_per_spp": ms_max / steps / spp, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f32", "data": "reference assets (model/*.obj), counter-based RNG seed 0",
-           "config": {"workload": wl["desc"], "rays_per_step": rays // args.steps, "paths_in_flight": paths_in_flight,
-                      "tile_shard": "32x32 tiles, rank=(tx+3ty)%N, 1 NCCL reduce per step" if world > 1 else "none",
-                      "l2": "L2 flushed (256 MiB write) between timed steps; per-step queue traffic also exceeds L2"},
-           "wall_ms_per_step": wall / args.steps * 1e3, "clocks": clocks, "gpu_launches": launches,
-           "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                   "ms_per_step": e2e_t / max(1, min(args.steps, 3)) * 1e3},
+           "config": cfg, "rays_per_step": rays_all // steps,
+           "per_rank": [{"rank": r, "ms_per_step": v[0], "rays_per_step": int(v[1])} for r, v in enumerate(per_rank)],
+           "wall_ms_per_step": wall / steps * 1e3, "clocks": clocks, "gpu_launches": launches_all,
+           "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
+                   "ms_per_step": e2e_t / n_e2e * 1e3, "film_checksum": checksum},
            "bvh_build": {"primitives": int(scene.primitive_count), "device_ms": build_ms,
-                         "mprims_per_s": scene.primitive_count / max(build_ms, 1e-6) / 1e3, "launches": 16,
+                         "mprims_per_s": scene.primitive_count / max(build_ms, 1e-6) / 1e3,
                          "note": "Morton + 4-pass radix sort + Karras + refit + flatten, inside the e2e region of every step (SURVEY 8d)"}}
 
-    # ---- roofline of the dominant kernel (closest-hit trace) + cpu baseline: rank 0, N = 1 only
-    if world == 1 and wl.get("bdpt"):
-        bdpt_roofline(out, args, wl, ex, ctx, local, spp)
-    elif world == 1:
-        ctx.set_option("stage_timing", 1)
-        ctx.film_clear(); cam.frame = 0; cam.frame_cpu[0] = 0
-        stt = integ.render_frames(spp)
-        ctx.set_option("stage_timing", 0)
-        n_batches = (spp * wl["W"] * wl["H"] + paths_in_flight - 1) // paths_in_flight
-        n_trace_launches = n_batches * integ.max_depth
-        # visit counts of the same traversal policy from the counters flavour of the library: the same host classes
-        # drive a second context
-        cctx = _native.Context(local, "libtiray_counters.so")
-        main_ctx, _native._ctx = _native._ctx, cctx
-        try:
-            integ.setup_data_cpu(); integ.setup_data_gpu(); scene.setup_data_gpu()
-            if wl["normals"]:
-                scene.process_normal()
-            cam.dirty = True; cam.frame = 0; cam.frame_cpu[0] = 0
-            integ.render_frames(spp)
-            cs = cctx.stats()
-        finally:
-            _native._ctx = main_ctx
-            cam.dirty = True
-        cctx.close()
-        algo_bytes = 48 * cs["rays_closest"] + 32 * cs["node_visits"] + 68 * cs["leaf_tests"]
-        trace_s = stt["ms_trace"] * 1e-3
-        peak, how = measured_peak_gbs()
-        achieved = algo_bytes / trace_s / 1e9
-        out["roofline"] = {"kernel": "k_trace (closest hit)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                           "frac": achieved / peak, "traffic": ncu_traffic(args.workload, "k_trace"), "peak_source": how,
-                           "traffic_note": "ncu dram__bytes_read+write per launch (profiles/r01_dram_traffic.json): far below the algorithmic bytes because the BVH is cache resident",
-                           "ncu": ncu_issue(args.workload),
-                           "launches_per_step": n_trace_launches, "avg_launch_ms": stt["ms_trace"] / n_trace_launches,
-                           "algorithmic_bytes_per_step": int(algo_bytes), "bytes_per_ray": algo_bytes / max(1, cs["rays_closest"]),
-                           "node_visits_per_ray": cs["node_visits"] / max(1, cs["rays_closest"]),
-                           "leaf_tests_per_ray": cs["leaf_tests"] / max(1, cs["rays_closest"]),
-                           "compulsory_dram_bytes_per_ray": 48,
-                           "stage_ms_per_step": {"trace": stt["ms_trace"], "shade": stt["ms_shade"], "shadow": stt["ms_shadow"], "total": stt["ms_total"]},
-                           "note": "effective bandwidth: the BVH is SMEM/L2 resident, compulsory DRAM traffic is the 48 B/ray queue stream"}
-        if not args.no_cpu:
-            sample_spp = 64 if args.workload in ("cornell", "spectral_box") else 16     # a few seconds on 16 threads, ~15 s on 4
-            cpu_reference_run(wl, 1)                                   # warm the pages / OpenMP pool
-            v, r, dt, cores, _ = cpu_reference_run(wl, sample_spp)
-            out["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                                   "sample": "%dx%d, %d of %d spp, %.1f s, reference-algorithm CPU restatement (Taichi unavailable)" % (wl["W"], wl["H"], sample_spp, spp, dt)}
+    # ---- roofline of the trace / shade / shadow kernels + cpu baseline: rank 0, N = 1 only
+    if world == 1 and detail and wl.get("bdpt"):
+        bdpt_roofline(out, args, name, wl, ex, ctx, local, spp)
+    elif world == 1 and detail:
+        pt_roofline(out, args, name, wl, ex, ctx, local, spp, paths_in_flight)
+    ctx.comm_destroy()
+    return out
+
+
+def pt_roofline(out, args, name, wl, ex, ctx, local, spp, paths_in_flight):
+    import _native
+    integ, cam, scene = ex.integrator, ex.cam, ex.scene
+    ctx.set_option("stage_timing", 1)
+    ctx.film_clear(); cam.frame = 0; cam.frame_cpu[0] = 0
+    stt = integ.render_frames(spp)
+    ctx.set_option("stage_timing", 0)
+    n_batches = (spp * wl["W"] * wl["H"] + paths_in_flight - 1) // paths_in_flight
+    n_stage_launches = n_batches * integ.max_depth
+    # visit counts of the same traversal policy from the counters flavour of the library: the same host classes
+    # drive a second context
+    cctx = _native.Context(local, "libtiray_counters.so")
+    main_ctx, _native._ctx = _native._ctx, cctx
+    try:
+        integ.setup_data_cpu(); integ.setup_data_gpu(); scene.setup_data_gpu()
+        if wl["normals"]:
+            scene.process_normal()
+        cam.dirty = True; cam.frame = 0; cam.frame_cpu[0] = 0
+        integ.render_frames(spp)
+        cs = cctx.stats()
+    finally:
+        _native._ctx = main_ctx
+        cam.dirty = True
+    cctx.close()
+    peak, how = measured_peak_gbs()
+    # SURVEY 8d accounting.  trace: 48 B/ray stream + 32 B per internal-node visit + 68 B per leaf test
+    algo_bytes = 48 * cs["rays_closest"] + 32 * cs["node_visits"] + 68 * cs["leaf_tests"]
+    achieved = algo_bytes / (stt["ms_trace"] * 1e-3) / 1e9
+    # shade: 176 B stream per Disney / glass vertex, + 48 B when a NEE sample is emitted (= 224), 112 B per terminal vertex
+    n_vert = cs["rays_closest"]; n_term = min(cs["shade_terminal"], n_vert)
+    shade_bytes = 176 * (n_vert - n_term) + 112 * n_term + 48 * cs["rays_shadow"]
+    shade_ach = shade_bytes / max(stt["ms_shade"] * 1e-3, 1e-9) / 1e9
+    # shadow: 48 B queue record + 32 / 68 B per node visit / leaf test (+ the 16 B target leaf fetch is one of the leaf tests)
+    shadow_bytes = 48 * cs["rays_shadow"] + 32 * cs["node_visits_shadow"] + 68 * cs["leaf_tests_shadow"]
+    shadow_ach = shadow_bytes / max(stt["ms_shadow"] * 1e-3, 1e-9) / 1e9
+    out["roofline"] = {"kernel": "k_trace (closest hit)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                       "frac": achieved / peak, "traffic": ncu_traffic(name, "k_trace"), "peak_source": how,
+                       "traffic_note": "ncu dram__bytes_read+write per launch (profiles/r0N_dram_traffic.json): far below the algorithmic bytes because the BVH is cache resident",
+                       "ncu": ncu_issue(name),
+                       "launches_per_step": n_stage_launches, "avg_launch_ms": stt["ms_trace"] / n_stage_launches,
+                       "algorithmic_bytes_per_step": int(algo_bytes), "bytes_per_ray": algo_bytes / max(1, cs["rays_closest"]),
+                       "node_visits_per_ray": cs["node_visits"] / max(1, cs["rays_closest"]),
+                       "leaf_tests_per_ray": cs["leaf_tests"] / max(1, cs["rays_closest"]),
+                       "compulsory_dram_bytes_per_ray": 48,
+                       "stage_ms_per_step": {"trace": stt["ms_trace"], "shade": stt["ms_shade"], "shadow": stt["ms_shadow"], "total": stt["ms_total"]},
+                       "note": "effective bandwidth: the BVH is SMEM/L2 resident, compulsory DRAM traffic is the 48 B/ray queue stream",
+                       "kernels": {
+                           "k_shade": {"bound": "hbm", "achieved": shade_ach, "peak": peak, "unit": "GB/s", "frac": shade_ach / peak,
+                                       "traffic": ncu_traffic(name, "k_shade"), "launches_per_step": n_stage_launches,
+                                       "avg_launch_ms": stt["ms_shade"] / n_stage_launches, "algorithmic_bytes_per_step": int(shade_bytes),
+                                       "bytes_per_vertex": shade_bytes / max(1, n_vert), "vertices_per_step": int(n_vert), "terminal_vertices": int(n_term),
+                                       "note": "SURVEY 8d: 176 B stream per Disney / glass vertex (+48 B with a NEE sample = 224), 112 B per terminal vertex"},
+                           "k_shadow": {"bound": "hbm", "achieved": shadow_ach, "peak": peak, "unit": "GB/s", "frac": shadow_ach / peak,
+                                        "traffic": ncu_traffic(name, "k_shadow"), "launches_per_step": n_stage_launches,
+                                        "avg_launch_ms": stt["ms_shadow"] / n_stage_launches, "algorithmic_bytes_per_step": int(shadow_bytes),
+                                        "bytes_per_ray": shadow_bytes / max(1, cs["rays_shadow"]),
+                                        "node_visits_per_ray": cs["node_visits_shadow"] / max(1, cs["rays_shadow"]),
+                                        "leaf_tests_per_ray": cs["leaf_tests_shadow"] / max(1, cs["rays_shadow"]),
+                                        "note": "48 B queue record + 32 B per node visit + 68 B per leaf test; effective bandwidth (tree on chip)"}}}
+    if not args.no_cpu:
+        sample_spp = 64 if name in ("cornell", "spectral_box") else 16     # a few seconds on 16 threads, ~15 s on 4
+        cpu_reference_run(wl, 1)                                   # warm the pages / OpenMP pool
+        v, r, dt, cores, _ = cpu_reference_run(wl, sample_spp)
+        out["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                               "sample": "%dx%d, %d of %d spp, %.1f s, reference-algorithm CPU restatement (Taichi unavailable)" % (wl["W"], wl["H"], sample_spp, spp, dt)}
+
+
+def run_native(args):
+    import torch
+    import parallel
+    rank, world, local = parallel.init_process_group("nccl" if args.gpus > 1 else None)
+    if world != args.gpus and args.gpus > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torchrun)" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    D = Dist(world, local)
+    out = measure_native(args, args.workload, args.steps, args.warmup, rank, world, local, D)
+    if args.workload == "cornell" and not args.no_sub:
+        # BASELINE configs[2] (the scene the >= 6x scaling target is defined on) in the same process, at every N
+        sub = measure_native(args, "teapot_mc", max(1, min(args.steps, 5)), max(3, min(args.warmup, 3)), rank, world, local, D)
+        out["workloads"] = {"teapot_mc": sub}
+        out["gpu_launches_all_workloads"] = out["gpu_launches"] + sub["gpu_launches"]
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
+        import torch.distributed as dist
         dist.barrier(); dist.destroy_process_group()
 
 
-def bdpt_roofline(out, args, wl, ex, ctx, local, spp):
+def bdpt_roofline(out, args, name, wl, ex, ctx, local, spp):
     """roofline of the dominant BDPT kernel + cpu baseline.  The two traversal kernels dominate the step: the persistent
     closest-hit kernel k_trace (6 launches per batch: 48 B ray / hit stream + 32 B per internal-node visit + 68 B per leaf
     test) and the connection query kernel k_shadow<QUERY> (1 launch per batch: 32 B queue entry + 4 B result + the
@@ -392,13 +514,13 @@ def bdpt_roofline(out, args, wl, ex, ctx, local, spp):
           "node_visits_per_ray": cs["node_visits"] / max(1, cs["rays_closest"]), "leaf_tests_per_ray": cs["leaf_tests"] / max(1, cs["rays_closest"])}
     top, other = (kq, kt) if ms_kshadow >= ms_ktrace else (kt, kq)
     out["roofline"] = dict(top, bound="hbm", peak=peak, unit="GB/s", frac=top["achieved"] / peak,
-                           traffic=ncu_traffic(args.workload, "k_trace" if top is kt else "k_shadow"), peak_source=how, ncu=ncu_issue(args.workload),
+                           traffic=ncu_traffic(name, "k_trace" if top is kt else "k_shadow"), peak_source=how, ncu=ncu_issue(name),
                            second_kernel=dict(other, frac=other["achieved"] / peak),
                            stage_ms_per_step={"sub-paths (generate + 6 x (trace, vertex))": stt["ms_trace"], "of which k_trace": ms_ktrace,
                                               "connections (gen + query + eval)": stt["ms_shadow"], "of which k_shadow<QUERY>": ms_kshadow,
                                               "items + film": stt["ms_shade"], "total": stt["ms_total"]},
-                           note="effective bandwidth: the 11.5 k-triangle BVH (1.5 MB of 64-byte nodes + 0.55 MB of leaf records) is L1/L2 "
-                                "resident; compulsory DRAM traffic is the ray / vertex / item / contribution streams")
+                           note="effective bandwidth: the 11.5 k-triangle BVH is L1/L2 resident; compulsory DRAM traffic is the ray / vertex / item / "
+                                "contribution streams")
     if not args.no_cpu:
         cpu_reference_run(wl, 1)
         v, r, dt, cores, _ = cpu_reference_run(wl, 8)
@@ -414,13 +536,13 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="cornell", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sub", action="store_true", help="skip the workloads.teapot_mc sub-record of the default run")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
     if args.impl == "reference":
-        run_reference(args, wl)
+        run_reference(args, WORKLOADS[args.workload])
     else:
-        run_native(args, wl)
+        run_native(args)
 
 
 if __name__ == "__main__":

@@ -28,7 +28,8 @@ typedef enum tr_status {
     TR_ERR_INVALID = -2,       /* bad argument / call order */
     TR_ERR_AABB = -3,          /* "aabb gen error": refit did not reach n-1 nodes (accel/LBvh.py:215-216) */
     TR_ERR_NO_DEVICE = -4,     /* no CUDA device: there is no CPU fallback */
-    TR_ERR_STACK = -5          /* "overflow, need larger stack" (Scene.py:741-742) */
+    TR_ERR_STACK = -5,         /* "overflow, need larger stack" (Scene.py:741-742): the tree is deeper than the traversal stack */
+    TR_ERR_COMM = -6           /* NCCL error / libnccl.so.2 not loadable (text in tr_last_error) */
 } tr_status;
 
 /* Counters and timings of the last tr_render_pt_rgb batch (device counters, CUDA events). */
@@ -49,6 +50,8 @@ typedef struct tr_stats {
     uint64_t leaf_tests_shadow;
     int32_t  chains;           /* independent wavefront chains per batch */
     int32_t  pad_;
+    uint64_t shade_terminal;   /* shaded vertices that were terminal (miss or emitter hit): the rest of rays_closest were
+                                  Disney / glass vertices (roofline accounting of the shade kernel) */
 } tr_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -109,12 +112,31 @@ int tr_film_create(tr_ctx* ctx, int W, int H);
 int tr_film_clear(tr_ctx* ctx);
 int tr_film_download(tr_ctx* ctx, float* hdr /* W*H*3 or NULL */, float* rgb /* W*H*3 or NULL */);
 int tr_film_upload(tr_ctx* ctx, const float* hdr /* W*H*3 */);
-/* device pointer of hdr (W*H*3 f32) for zero-copy interop (NCCL reduce through torch.distributed) */
+/* the same download without the last host copy: the film is DMA'd into pinned host buffers owned by the context and their
+ * addresses are returned (valid until the next download / tr_film_create; NULL for a film that was not requested).  This is what
+ * `.to_numpy()` of the Python classes hands out when asked for a view (example/Example.py:44 reads the film every frame). */
+int tr_film_download_pinned(tr_ctx* ctx, int want_hdr, int want_rgb, const float** hdr, const float** rgb);
+/* device pointer of hdr (W*H*3 f32) for zero-copy interop */
 int tr_film_device_ptr(tr_ctx* ctx, void** hdr_dev, void** rgb_dev);
 
 /* pixel-tile sharding: this context renders the 32x32 tiles t with (tx + 3*ty) % nranks == rank;
  * pixels of other ranks stay 0 in hdr so that a SUM over ranks gives the image. Default (0,1). */
 int tr_set_shard(tr_ctx* ctx, int rank, int nranks);
+
+/* ---- multi-GPU (the reference is single-device) ----------------------------------------------------------
+ * One context (= one process or thread) per GPU.  Rank 0 obtains an id with tr_comm_unique_id and hands the 128 bytes to the
+ * other ranks by any host channel (torch.distributed / MPI broadcast, a file, a socket); every rank then calls tr_comm_init,
+ * which creates the NCCL communicator and shards the film (tr_set_shard(rank, nranks)).  tr_film_reduce enqueues ONE
+ * ncclReduce (sum, f32, W*H*3) of the per-rank partial films on the context's stream, right behind whatever was rendered:
+ * rank 0 (all_ranks != 0: every rank, ncclAllReduce) then presents the full image through tr_tonemap / tr_film_download*.
+ * The partial films themselves are left untouched, so rendering more frames and reducing again never double-counts; any
+ * render, clear or upload of the film makes the context present its own partial film again.  nranks == 1 is a no-op.
+ * libnccl.so.2 is loaded at run time on the first call (TR_ERR_COMM if absent). */
+#define TR_COMM_ID_BYTES 128
+int tr_comm_unique_id(void* id_out /* TR_COMM_ID_BYTES */);
+int tr_comm_init(tr_ctx* ctx, int rank, int nranks, const void* unique_id /* TR_COMM_ID_BYTES, may be NULL when nranks == 1 */);
+int tr_film_reduce(tr_ctx* ctx, int all_ranks);
+int tr_comm_destroy(tr_ctx* ctx);
 
 /* ---- integrators ------------------------------------------------------------------------ */
 /* replaces PT_RGB.PathTrace.render (integrator/PT_RGB.py:44-136) for frames

@@ -55,6 +55,7 @@ def _load(fast):
     lib.orc_rng.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _f32p]
     lib.orc_philox_raw.argtypes = [C.c_uint32] * 6 + [_u32p]
     lib.orc_slabs.argtypes = [_f32p, _f32p, _f32p, _f32p]
+    lib.orc_set_num_threads.argtypes = [C.c_int]
     lib.orc_camera_view_set.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int]
     lib.orc_render_bdpt_rgb.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, _f32p, C.c_void_p, _u64p]
     lib.orc_bdpt_pixel_dump.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, _f32p, _i32p, _f32p]

@@ -1035,6 +1035,12 @@ int orc_num_threads() {
     return 1;
 #endif
 }
+// bench.py's reference arm: torchrun exports OMP_NUM_THREADS=1, the CPU baseline is defined on ALL host cores
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#endif
+}
 int orc_slabs(const float* o, const float* d, const float* mn, const float* mx) { return slabs(v3(o[0], o[1], o[2]), v3(d[0], d[1], d[2]), mn, mx); }
 
 #include "spec_api.inc"

@@ -14,7 +14,8 @@ def _run(args, env=None):
 
 
 def test_reference_arm_json_line():
-    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "0"])
+    # torchrun exports OMP_NUM_THREADS=1 to its ranks: the arm must still use every host core
+    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "0"], env={"OMP_NUM_THREADS": "1"})
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, "stdout must carry exactly one JSON line"
@@ -26,6 +27,10 @@ def test_reference_arm_json_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "spp" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert cb["cores"] == len(os.sched_getaffinity(0)) and "all %d host threads" % cb["cores"] in cb["sample"]
+    assert d["config"]["spp_per_step"] == 64 and "64 spp per step (of 64)" in cb["sample"]        # the stated config, not a sample of it
+    sub = d["workloads"]["teapot_mc"]                                                            # BASELINE configs[2] next to it
+    assert "130720 tris" in sub["config"]["workload"] and sub["value"] > 0 and sub["cpu_baseline"]["cores"] == cb["cores"]
 
 
 def test_reference_arm_other_ranks_stay_silent():

@@ -40,15 +40,24 @@ def _worker(rank, world, port, all_ranks, bdpt=False):
         assert foreign.any(), "no splat crossed a tile boundary: the test would not exercise the sum"
     else:
         part, _ = s.render_pt_rgb(W, H, 0, 2, seed=3, mask=parallel.tile_mask(W, H, rank, world))
-    film = torch.from_numpy(part)
-    parallel.reduce_film(film, dst=0, all_ranks=all_ranks)
-    if rank == 0 or all_ranks:
+    film = torch.from_numpy(part.copy())
+    out = parallel.reduce_film(film, dst=0, all_ranks=all_ranks)
+    assert np.array_equal(film.numpy(), part), "the reduce must leave the rank's partial film untouched"
+    assert (out is not None) == (rank == 0 or all_ranks)
+    if out is not None:
         if bdpt:
             full, _ = s.render_bdpt_rgb(W, H, 0, 2, seed=3)
-            assert np.allclose(film.numpy(), full, rtol=1e-4, atol=1e-6)
+            assert np.allclose(out.numpy(), full, rtol=1e-4, atol=1e-6)
         else:
             full, _ = s.render_pt_rgb(W, H, 0, 2, seed=3)
-            assert np.array_equal(film.numpy(), full)
+            assert np.array_equal(out.numpy(), full)
+    if not bdpt:
+        # progressive use: two more frames accumulated into the SAME partial film, reduced again -> no double counting
+        part2, _ = s.render_pt_rgb(W, H, 2, 2, seed=3, hdr=part.copy(), mask=parallel.tile_mask(W, H, rank, world))
+        out2 = parallel.reduce_film(torch.from_numpy(part2), dst=0, all_ranks=all_ranks)
+        if out2 is not None:
+            full2, _ = s.render_pt_rgb(W, H, 0, 4, seed=3)
+            assert np.array_equal(out2.numpy(), full2)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -21,7 +21,7 @@ class Stats(C.Structure):
                 ("ms_trace", C.c_float), ("ms_shade", C.c_float), ("ms_shadow", C.c_float), ("ms_build", C.c_float),
                 ("frames", C.c_int32), ("paths_in_flight", C.c_int32),
                 ("node_visits_shadow", C.c_uint64), ("leaf_tests_shadow", C.c_uint64),
-                ("chains", C.c_int32), ("pad_", C.c_int32)]
+                ("chains", C.c_int32), ("pad_", C.c_int32), ("shade_terminal", C.c_uint64)]
 
 
 # every symbol include/tiray.h declares: name -> (restype, argtypes)
@@ -52,7 +52,12 @@ SIGNATURES = {
     "tr_film_clear": (C.c_int, [_vp]),
     "tr_film_download": (C.c_int, [_vp, _vp, _vp]),
     "tr_film_upload": (C.c_int, [_vp, _vp]),
+    "tr_film_download_pinned": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp)]),
     "tr_film_device_ptr": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
+    "tr_comm_unique_id": (C.c_int, [_vp]),
+    "tr_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "tr_film_reduce": (C.c_int, [_vp, C.c_int]),
+    "tr_comm_destroy": (C.c_int, [_vp]),
     "tr_set_shard": (C.c_int, [_vp, C.c_int, C.c_int]),
     "tr_render_pt_rgb": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_uint64]),
     "tr_render_pt_spec": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_uint64]),
@@ -106,6 +111,8 @@ def load_library(name=None):
 
 
 def _ptr(a):
+    """address of a numpy array for a void* argument.  The CALLER must keep `a` alive across the foreign call: pass a named
+    local, never a temporary expression (numpy's small-block cache would hand the freed buffer to the next argument)."""
     return None if a is None else a.ctypes.data
 
 
@@ -149,9 +156,11 @@ class Context:
         v = _f(vertex); p = np.ascontiguousarray(prim, np.int32); m = _f(material)
         s = _f(shape) if shape is not None and len(shape) else None
         l = np.ascontiguousarray(light, np.int32) if light is not None and len(light) else None
+        lo = _f(bmin).reshape(-1); hi = _f(bmax).reshape(-1)            # named locals: alive until the call returns
+        assert lo.size == 3 and hi.size == 3
         self._ck(self.lib.tr_scene_upload(self.h, _ptr(v), v.shape[0], _ptr(p), p.shape[0], _ptr(m), m.shape[0],
                                           _ptr(s), 0 if s is None else s.shape[0], _ptr(l), 0 if l is None else l.shape[0],
-                                          _ptr(_f(bmin).reshape(-1)), _ptr(_f(bmax).reshape(-1))), "tr_scene_upload")
+                                          _ptr(lo), _ptr(hi)), "tr_scene_upload")
         self.n_prims, self.n_verts = p.shape[0], v.shape[0]
 
     def material_upload(self, material):
@@ -186,8 +195,9 @@ class Context:
 
     # ---- camera / film
     def camera_set(self, view, view_inv, eye, fx, fy, cx, cy):
-        self._ck(self.lib.tr_camera_set(self.h, _ptr(_f(view).reshape(-1)), _ptr(_f(view_inv).reshape(-1)),
-                                        _ptr(_f(eye).reshape(-1)), fx, fy, cx, cy), "tr_camera_set")
+        v = None if view is None else _f(view).reshape(-1); vi = _f(view_inv).reshape(-1); e = _f(eye).reshape(-1)
+        assert (v is None or v.size == 16) and vi.size == 16 and e.size == 3
+        self._ck(self.lib.tr_camera_set(self.h, _ptr(v), _ptr(vi), _ptr(e), fx, fy, cx, cy), "tr_camera_set")
 
     def film_create(self, W, H):
         self._ck(self.lib.tr_film_create(self.h, int(W), int(H)), "tr_film_create"); self.W, self.H = int(W), int(H)
@@ -195,9 +205,17 @@ class Context:
     def film_clear(self):
         self._ck(self.lib.tr_film_clear(self.h), "tr_film_clear")
 
-    def film_download(self, hdr=True, rgb=False):
-        a = np.zeros((self.W, self.H, 3), np.float32) if hdr else None
-        b = np.zeros((self.W, self.H, 3), np.float32) if rgb else None
+    def film_download(self, hdr=True, rgb=False, view=False):
+        """(hdr, rgb) as (W,H,3) f32 arrays.  view=True returns zero-copy views of the context's pinned download buffers (valid
+        until the next download) instead of fresh arrays: the film is DMA'd once and not copied again on the host."""
+        if view:
+            a, b = _vp(), _vp()
+            self._ck(self.lib.tr_film_download_pinned(self.h, int(hdr), int(rgb), C.byref(a), C.byref(b)), "tr_film_download_pinned")
+            shape = (self.W, self.H, 3)
+            mk = lambda p: np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=shape) if p.value else None
+            return mk(a), mk(b)
+        a = np.empty((self.W, self.H, 3), np.float32) if hdr else None
+        b = np.empty((self.W, self.H, 3), np.float32) if rgb else None
         self._ck(self.lib.tr_film_download(self.h, _ptr(a), _ptr(b)), "tr_film_download")
         return a, b
 
@@ -212,6 +230,24 @@ class Context:
 
     def set_shard(self, rank, nranks):
         self._ck(self.lib.tr_set_shard(self.h, int(rank), int(nranks)), "tr_set_shard")
+
+    # ---- multi-GPU: NCCL communicator owned by the library (one context per GPU / process)
+    def comm_unique_id(self):
+        buf = np.zeros(128, np.uint8)
+        self._ck(self.lib.tr_comm_unique_id(_ptr(buf)), "tr_comm_unique_id")
+        return buf
+
+    def comm_init(self, rank, nranks, unique_id=None):
+        uid = None if unique_id is None else np.ascontiguousarray(unique_id, np.uint8)
+        assert uid is None or uid.size == 128
+        self._ck(self.lib.tr_comm_init(self.h, int(rank), int(nranks), _ptr(uid)), "tr_comm_init")
+
+    def film_reduce(self, all_ranks=False):
+        """one ncclReduce (sum) of the per-rank partial films, enqueued on the context's stream; rank 0 then presents the image"""
+        self._ck(self.lib.tr_film_reduce(self.h, int(all_ranks)), "tr_film_reduce")
+
+    def comm_destroy(self):
+        self._ck(self.lib.tr_comm_destroy(self.h), "tr_comm_destroy")
 
     # ---- integrators
     def render_pt_rgb(self, frame_begin, n_frames, max_depth=15, seed=0):

@@ -399,8 +399,8 @@ extern "C" int tr_bvh_build(tr_ctx* ctx) {
     k_next8<<<cdiv(nn * 8, 256), 256, 0, s>>>(n, ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_axis, ctx->d_pre, ctx->d_nodes, ctx->d_nodesx);
     TR_CHECK_LAUNCH(ctx);
     TR_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
-    int status[16];
-    TR_CUDA(ctx, cudaMemcpyAsync(status, ctx->d_build_status, sizeof(status), cudaMemcpyDeviceToHost, s));
+    int* status = ctx->h_build_status;                   // pinned: a true asynchronous copy, one wait for build + copy
+    TR_CUDA(ctx, cudaMemcpyAsync(status, ctx->d_build_status, 16 * sizeof(int), cudaMemcpyDeviceToHost, s));
     TR_CUDA(ctx, cudaStreamSynchronize(s));
     float ms = 0.0f; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->stats.ms_build = ms;
     if (status[0] != n - 1)

@@ -73,6 +73,7 @@ struct tr_ctx {
     int*   d_leafcount = nullptr; int* d_flag = nullptr; int* d_pre = nullptr;
     int*   d_build_status = nullptr;     // [0] = refit-completed internal nodes
     TrNode* d_nodes = nullptr; TrLeaf* d_leaves = nullptr; int* d_leaf_of_prim = nullptr;
+    struct TrNode2* d_nodes2 = nullptr; float4* d_small_img = nullptr;
     int* d_axis = nullptr; TrNodeX* d_nodesx = nullptr;    // split axis per internal node; 64-byte nodes with 8 octant-ordered escape links
     TrShade* d_shade = nullptr; bool shade_ready = false;
     int*   d_hist = nullptr; size_t hist_cap = 0;
@@ -81,6 +82,14 @@ struct tr_ctx {
     TrCamera cam; bool cam_set = false;
     int W = 0, H = 0;
     float* d_hdr = nullptr; float* d_rgb = nullptr;
+    // multi-GPU: tr_film_reduce sums the per-rank partial films (d_hdr stays a pure partial) into d_hdr_sum on the root; while
+    // present_sum is set, tone map and download read the sum.  Any render / clear / upload of the film resets it.
+    float* d_hdr_sum = nullptr; bool present_sum = false;
+    void* nccl_comm = nullptr; int comm_rank = 0, comm_nranks = 1;
+    // pinned host memory: upload staging (bump allocator), film download target, LBVH build status
+    char* h_stage = nullptr; size_t stage_cap = 0, stage_used = 0; bool stage_busy = false; cudaEvent_t ev_stage = nullptr;
+    float* h_film = nullptr; size_t film_host_cap = 0;
+    int* h_build_status = nullptr;
     // first-hit buffers (Debug integrator)
     float* d_fh = nullptr;      // W*H*16 floats: t, prim, u, v, pos3, gn3, n3, dir3
     bool fh_ready = false;
@@ -124,9 +133,12 @@ struct tr_ctx {
     int opt_smem_bvh = 1;
     int opt_chains = 2;
     int opt_shadow_overlap = 1;
-    int opt_tail_max = 16384;
+    int opt_tail_max = -1;          // hand-over threshold of k_tail: -1 = auto (a fraction of the chain's paths), 0 = never
     int opt_tail_chunk = 8;
     int opt_bdpt_wavefront = 1;     // 0: lock-step BDPT pipeline (cross-check)
+    int opt_top_nodes = 0;          // large trees: this many breadth-first top nodes are staged into shared memory per CTA (0 = off)
+    int opt_pdl = 1;                // programmatic dependent launch between the stages of a chain
+    int opt_replicas = 1;           // small trees: bank-conflict-free 8-replica shared-memory image
     size_t opt_max_paths = (size_t)20 << 20;   // path slots per batch (188 B each): more paths in flight amortise the per-stage tails
 
     // cuda graph cache for the batch pipeline
@@ -146,6 +158,9 @@ struct tr_ctx {
 };
 
 int tr_fail(tr_ctx* ctx, int code, const char* fmt, ...);
+static inline float* tr_present_hdr(tr_ctx* ctx) { return (ctx->present_sum && ctx->d_hdr_sum) ? ctx->d_hdr_sum : ctx->d_hdr; }
+void tr_comm_release(tr_ctx* ctx);                                              // comm.cu
+int tr_stage_h2d(tr_ctx* ctx, void* dst, const void* src, size_t bytes);        // api.cu: asynchronous upload through pinned staging
 #define TR_CUDA(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
     return tr_fail(ctx, TR_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
 #define TR_CHECK_LAUNCH(ctx) TR_CUDA(ctx, cudaGetLastError())

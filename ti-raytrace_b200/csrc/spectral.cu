@@ -14,8 +14,7 @@ extern "C" int tr_spec_sensor_upload(tr_ctx* ctx, const float* xyz, int n, float
     int rc; if ((rc = tr_realloc(ctx, &ctx->d_sensor, (size_t)n))) return rc;
     std::vector<float4> h((size_t)n);
     for (int i = 0; i < n; ++i) h[i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.0f);
-    TR_CUDA(ctx, cudaMemcpyAsync(ctx->d_sensor, h.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-    TR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = tr_stage_h2d(ctx, ctx->d_sensor, h.data(), (size_t)n * sizeof(float4)))) return rc;
     ctx->spec.sensor = ctx->d_sensor; ctx->spec.s_size = n; ctx->spec.s_lmin = lmin; ctx->spec.s_lmax = lmax;
     ctx->spec.s_lrange = (lmax - lmin) / (float)(n - 1);          // integrator/PT_Spec.py:74
     ctx->gen++;
@@ -27,8 +26,7 @@ extern "C" int tr_spec_spectrum_upload(tr_ctx* ctx, int which, const float* data
         return tr_fail(ctx, TR_ERR_INVALID, "tr_spec_spectrum_upload: bad table %d (n=%d, %g..%g nm)", which, n, lmin, lmax);
     TR_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc; if ((rc = tr_realloc(ctx, &ctx->d_spectrum[which], (size_t)n))) return rc;
-    TR_CUDA(ctx, cudaMemcpyAsync(ctx->d_spectrum[which], data, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
-    TR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = tr_stage_h2d(ctx, ctx->d_spectrum[which], data, (size_t)n * 4))) return rc;
     SpecTable& t = ctx->spec.sp[which];
     t.data = ctx->d_spectrum[which]; t.size = n; t.lmin = lmin; t.lmax = lmax; t.lrange = (lmax - lmin) / (float)(n - 1);   // spectrum/Spectrum.py:33
     ctx->gen++;
@@ -50,9 +48,8 @@ extern "C" int tr_spec_rgb2spec_upload(tr_ctx* ctx, const float* scale, const fl
     int rc;
     if ((rc = tr_realloc(ctx, &ctx->d_rs_scale, (size_t)res))) return rc;
     if ((rc = tr_realloc(ctx, &ctx->d_rs_data, n))) return rc;
-    TR_CUDA(ctx, cudaMemcpyAsync(ctx->d_rs_scale, scale, (size_t)res * 4, cudaMemcpyHostToDevice, ctx->stream));
-    TR_CUDA(ctx, cudaMemcpyAsync(ctx->d_rs_data, data, n * 4, cudaMemcpyHostToDevice, ctx->stream));
-    TR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = tr_stage_h2d(ctx, ctx->d_rs_scale, scale, (size_t)res * 4))) return rc;
+    if ((rc = tr_stage_h2d(ctx, ctx->d_rs_data, data, n * 4))) return rc;
     ctx->rs_res = res; ctx->matspec_ready = false; ctx->gen++;
     return TR_OK;
 }
@@ -63,8 +60,7 @@ extern "C" int tr_spec_sky_upload(tr_ctx* ctx, const float* configs, const float
     int rc; if ((rc = tr_realloc(ctx, &ctx->d_sky, (size_t)TR_SKY_FLOATS))) return rc;
     float h[TR_SKY_FLOATS];
     memcpy(h, configs, 99 * 4); memcpy(h + 99, radiances, 11 * 4); memcpy(h + 110, sun_dir, 12);
-    TR_CUDA(ctx, cudaMemcpyAsync(ctx->d_sky, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
-    TR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = tr_stage_h2d(ctx, ctx->d_sky, h, sizeof(h)))) return rc;
     ctx->spec.sky = ctx->d_sky; ctx->spec.sky_on = 1; ctx->gen++;
     return TR_OK;
 }

@@ -1118,6 +1118,7 @@ static int render_wavefront(tr_ctx* ctx, int frame_begin, int n_frames, int max_
     TR_CUDA(ctx, cudaSetDevice(ctx->device));
     WfArgs a; int rc;
     if ((rc = tr_stats_resolve(ctx))) return rc;                        // an earlier asynchronous render still owns ev0 / ev1 / the ring
+    ctx->present_sum = false;                                           // the partial film changes: a reduced copy is stale
     if (!ctx->h_ring) TR_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_ring, sizeof(TrCounters) * TR_MAX_CHAINS * TR_RING_BATCHES, cudaHostAllocDefault));
     if ((rc = fill_args(ctx, a, SPEC))) return rc;
     if (a.npix == 0) { memset(&ctx->stats, 0, sizeof(ctx->stats)); ctx->stats.frames = n_frames; return TR_OK; }    // this rank owns no tile
@@ -1150,7 +1151,7 @@ static int render_wavefront(tr_ctx* ctx, int frame_begin, int n_frames, int max_
         ctx->stage_ev.resize(4 * TR_MAX_DEPTH_CAP);
         for (auto& e : ctx->stage_ev) TR_CUDA(ctx, cudaEventCreate(&e));
     }
-    uint64_t launches = 0, rays_c = 0, rays_s = 0, vis[4] = {0, 0, 0, 0};
+    uint64_t launches = 0, rays_c = 0, rays_s = 0, vis[4] = {0, 0, 0, 0}, n_term = 0;
     float ms_trace = 0.0f, ms_shade = 0.0f, ms_shadow = 0.0f;
     TR_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
     for (int f0 = 0; f0 < n_frames; f0 += F) {
@@ -1194,7 +1195,7 @@ static int render_wavefront(tr_ctx* ctx, int frame_begin, int n_frames, int max_
         TR_CUDA(ctx, cudaStreamSynchronize(s));
         for (int j = 0; j < K; ++j) {
             const int tf = ctx->h_ctr[j].tail_from;
-            for (int d = 0; d < max_depth; ++d) { if (tf == 0 || d != tf) rays_c += (uint64_t)ctx->h_ctr[j].nq[d]; rays_s += (uint64_t)ctx->h_ctr[j].nshadow[d]; }
+            for (int d = 0; d < max_depth; ++d) { if (tf == 0 || d != tf) rays_c += (uint64_t)ctx->h_ctr[j].nq[d]; rays_s += (uint64_t)ctx->h_ctr[j].nshadow[d]; n_term += (uint64_t)ctx->h_ctr[j].ncls[d][0]; }
             rays_c += ctx->h_ctr[j].tail_rays[0]; rays_s += ctx->h_ctr[j].tail_rays[1];
             for (int k = 0; k < 4; ++k) vis[k] += ctx->h_ctr[j].visits[k];
         }
@@ -1205,7 +1206,7 @@ static int render_wavefront(tr_ctx* ctx, int frame_begin, int n_frames, int max_
         }
     }
     TR_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
-    ctx->stats.rays_closest = rays_c; ctx->stats.rays_shadow = rays_s;
+    ctx->stats.rays_closest = rays_c; ctx->stats.rays_shadow = rays_s; ctx->stats.shade_terminal = n_term;
     ctx->stats.node_visits = vis[0]; ctx->stats.leaf_tests = vis[1]; ctx->stats.node_visits_shadow = vis[2]; ctx->stats.leaf_tests_shadow = vis[3];
     ctx->stats.kernel_launches = launches; ctx->stats.ms_total = 0.0f; ctx->stats.frames = n_frames; ctx->stats.paths_in_flight = (int)((size_t)F * a.npix); ctx->stats.chains = K;
     ctx->stats.ms_trace = ms_trace; ctx->stats.ms_shade = ms_shade; ctx->stats.ms_shadow = ms_shadow;
@@ -1219,16 +1220,16 @@ int tr_stats_resolve(tr_ctx* ctx) {
     if (!ctx->stats_pending) return TR_OK;
     TR_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
     ctx->stats_pending = false;
-    uint64_t rays_c = 0, rays_s = 0, vis[4] = {0, 0, 0, 0};
+    uint64_t rays_c = 0, rays_s = 0, vis[4] = {0, 0, 0, 0}, n_term = 0;
     for (int b = 0; b < ctx->ring_batches; ++b) for (int j = 0; j < ctx->ring_K; ++j) {
         const TrCounters& c = ctx->h_ring[(size_t)b * TR_MAX_CHAINS + j];
         const int tf = c.tail_from;
-        for (int d = 0; d < ctx->ring_depth; ++d) { if (tf == 0 || d != tf) rays_c += (uint64_t)c.nq[d]; rays_s += (uint64_t)c.nshadow[d]; }
+        for (int d = 0; d < ctx->ring_depth; ++d) { if (tf == 0 || d != tf) rays_c += (uint64_t)c.nq[d]; rays_s += (uint64_t)c.nshadow[d]; n_term += (uint64_t)c.ncls[d][0]; }
         rays_c += c.tail_rays[0]; rays_s += c.tail_rays[1];
         for (int k = 0; k < 4; ++k) vis[k] += c.visits[k];
     }
     ctx->ring_batches = 0;
-    ctx->stats.rays_closest += rays_c; ctx->stats.rays_shadow += rays_s;
+    ctx->stats.rays_closest += rays_c; ctx->stats.rays_shadow += rays_s; ctx->stats.shade_terminal += n_term;
     ctx->stats.node_visits += vis[0]; ctx->stats.leaf_tests += vis[1]; ctx->stats.node_visits_shadow += vis[2]; ctx->stats.leaf_tests_shadow += vis[3];
     float ms = 0.0f; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->stats.ms_total = ms;
@@ -1286,7 +1287,7 @@ extern "C" int tr_tonemap(tr_ctx* ctx, float exposure) {
     if (!ctx || !ctx->d_hdr) return tr_fail(ctx, TR_ERR_INVALID, "tr_tonemap: no film");
     TR_CUDA(ctx, cudaSetDevice(ctx->device));
     int n = ctx->W * ctx->H * 3;
-    k_tonemap<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->d_hdr, ctx->d_rgb, n, exposure);
+    k_tonemap<<<cdiv(n, 256), 256, 0, ctx->stream>>>(tr_present_hdr(ctx), ctx->d_rgb, n, exposure);
     TR_CHECK_LAUNCH(ctx);
     return TR_OK;
 }

@@ -57,23 +57,40 @@ def film_tensor(ctx):
 
 
 def reduce_film(film, dst=0, all_ranks=False):
-    """Sum the per-rank partial films. `film` is a torch tensor (device film alias on GPUs, CPU tensor
-    under gloo). In place; after the call rank `dst` (or every rank) holds the full image."""
+    """Sum per-rank partial films held in torch tensors (CPU tensors under gloo: the host-logic tests; the GPU path is
+    comm_init() + ctx.film_reduce() below).  OUT OF PLACE: `film` stays this rank's pure partial, so rendering more frames and
+    reducing again never double-counts history.  Returns the summed image on rank `dst` (on every rank with all_ranks), None
+    elsewhere."""
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return film
+    out = film.clone()
     if all_ranks:
-        dist.all_reduce(film, op=dist.ReduceOp.SUM)
-    else:
-        dist.reduce(film, dst=dst, op=dist.ReduceOp.SUM)
-    return film
+        dist.all_reduce(out, op=dist.ReduceOp.SUM)
+        return out
+    dist.reduce(out, dst=dst, op=dist.ReduceOp.SUM)
+    return out if dist.get_rank() == dst else None
 
 
-def reduce_device_film(ctx, dst=0, all_ranks=False):
-    """One NCCL reduce of the device film over NVLink, ordered after the context's render stream."""
+def comm_init(ctx):
+    """Create the library-owned NCCL communicator of this rank's context (tr_comm_init): rank 0 makes the unique id, the 128
+    bytes travel over the torch.distributed process group (plumbing only), every rank joins.  Also shards the film."""
     import torch
-    ctx.synchronize()
-    t = film_tensor(ctx)
-    reduce_film(t, dst, all_ranks)
-    torch.cuda.synchronize(t.device)
-    return t
+    import torch.distributed as dist
+    rank, world, local = env_rank()
+    if world == 1 or not dist.is_initialized():
+        ctx.comm_init(0, 1, None)
+        return
+    uid = ctx.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)
+    t = torch.from_numpy(uid)
+    if dist.get_backend() == "nccl":
+        t = t.cuda(local)
+    dist.broadcast(t, src=0)
+    ctx.comm_init(rank, world, t.cpu().numpy())
+
+
+def reduce_device_film(ctx, all_ranks=False):
+    """One ncclReduce of the device film over NVLink, enqueued on the context's render stream (tr_film_reduce): no host round
+    trip between the last render kernel and the reduce.  Rank 0 (every rank with all_ranks) then presents the summed image
+    through tone_map / film_download."""
+    ctx.film_reduce(all_ranks)
