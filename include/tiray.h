@@ -168,8 +168,10 @@ int tr_first_hit_download(tr_ctx* ctx, float* t, int32_t* prim, float* uv /*2*/,
 /* replaces UF.tone_map (UtilsFunc.py:583-586): rgb = srgb(ACES(hdr * exposure)) */
 int tr_tonemap(tr_ctx* ctx, float exposure);
 int tr_stats_get(tr_ctx* ctx, tr_stats* out);
-/* tuning: "batch_frames" (0 = auto), "max_paths", "chains" (parallel wavefront chains per batch),
- * "stage_timing", "graph" (CUDA-graph replay), "smem_bvh" (TMA staging of small BVHs) */
+/* tuning: "batch_frames" (0 = auto), "max_paths", "chains" (parallel wavefront chains per batch), "stage_timing", "graph"
+ * (CUDA-graph replay), "smem_bvh" (TMA staging of small trees into shared memory), "replicas" (their bank-conflict-free
+ * 8-way replicated image), "top_nodes" (large trees: breadth-first top nodes staged per CTA, 0 = off), "tail_max", "tail_chunk",
+ * "shadow_overlap", "pdl", "bdpt_wavefront".  Out-of-range values are rejected with TR_ERR_INVALID. */
 int tr_set_option(tr_ctx* ctx, const char* name, int value);
 
 /* ---- spectral tables: replace the from_numpy calls of PT_Spec.setup_data_gpu (integrator/PT_Spec.py:89-98) ---------
@@ -198,9 +200,15 @@ int tr_test_glass_sample(tr_ctx* ctx, int n, const float* dir, const float* N, f
                          const float* u /* n */, float* out /* n x 4 */);
 int tr_test_offset_ray(tr_ctx* ctx, int n, const float* p, const float* nrm, float* out /* n x 3 */);
 int tr_test_rng(tr_ctx* ctx, uint64_t seed, uint32_t pixel, uint32_t frame, uint32_t block, float* out4);
-/* arbitrary rays through the traversal kernels; shadow != 0 uses the nearest-hit shadow query */
+/* arbitrary rays through the simple one-lane-per-ray walk (the Debug integrator's); shadow != 0 adds the shadow-query cross-check */
 int tr_test_trace(tr_ctx* ctx, int n, const float* o, const float* d, int shadow,
                   float* t, int32_t* prim, float* uv /* n x 2 or NULL */);
+/* the same rays through the PRODUCTION kernels, as queue records, in the tree mode the renderer would use (options "smem_bvh",
+ * "replicas", "top_nodes" apply): kernel 0 = tr_test_trace; 1 = persistent closest-hit kernel k_trace; 2 = persistent shadow kernel
+ * k_shadow (target[k] = primitive ray k must see: prim[k] = target[k] and t[k] = 1 when the target is the nearest hit, else -2 / 0);
+ * 3 = the tail megakernel k_tail (first walk of each path). */
+int tr_test_trace_kernel(tr_ctx* ctx, int kernel, int n, const float* o, const float* d, const int32_t* target /* kernel 2 */, int shadow,
+                         float* t, int32_t* prim, float* uv /* n x 2 or NULL */);
 
 /* BDPT internals of the last tr_render_bdpt_rgb batch (its first frame) for n pixels: verts n x 13 x 20 f32 (eye 0..6, light
  * 0..5; pos3 normal3 snormal3 beta3 wo3 fpdf rpdf type+16*delta prim mat, zero beyond the sub-path depth), depths n x 2 i32,

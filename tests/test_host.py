@@ -202,10 +202,18 @@ def test_sass_shows_tma_staging_and_sm100a():
     lib = _native.lib_path()
     elf = subprocess.run([cuobjdump, "-lelf", lib], capture_output=True, text=True).stdout
     assert "sm_100a" in elf and "sm_90" not in elf
-    sass = subprocess.run([cuobjdump, "-sass", "-fun", "_Z7k_traceILb1EEv6WfArgsi", lib], capture_output=True, text=True).stdout
-    assert sass.count("UBLKCP") == 2 and "SYNCS.ARRIVE.TRANS64" in sass and "SYNCS.PHASECHK.TRANS64.TRYWAIT" in sass
-    sass0 = subprocess.run([cuobjdump, "-sass", "-fun", "_Z7k_traceILb0EEv6WfArgsi", lib], capture_output=True, text=True).stdout
+    def sass_of(fn):
+        return subprocess.run([cuobjdump, "-sass", "-fun", fn, lib], capture_output=True, text=True).stdout
+    # tree modes (csrc/trace.cuh): 0 replicated shared-memory image (one bulk copy), 1 plain shared-memory tree (nodes + leaves: two),
+    # 3 global memory + staged top nodes (one), 2 global memory only (none); all staged modes wait on the mbarrier
+    for mode, copies in ((0, 1), (1, 2), (3, 1)):
+        for fn in ("_Z7k_traceILi%dEEv6WfArgsi" % mode, "_Z8k_shadowILi%dELb0EEv6WfArgsi" % mode, "_Z6k_tailILi%dELb0EEv6WfArgsi" % mode):
+            sass = sass_of(fn)
+            assert sass.count("UBLKCP") == copies, (fn, sass.count("UBLKCP"))
+            assert "SYNCS.ARRIVE.TRANS64" in sass and "SYNCS.PHASECHK.TRANS64.TRYWAIT" in sass, fn
+    sass0 = sass_of("_Z7k_traceILi2EEv6WfArgsi")
     assert "UBLKCP" not in sass0 and "LDG" in sass0            # large trees are walked in global memory
+    assert "LDS" in sass0 and "STS" in sass0                   # ... with the traversal stack in shared memory
 
 
 def test_random_obj_files_pack_like_the_oracle_loader(tmp_path, monkeypatch):

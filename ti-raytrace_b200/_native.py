@@ -75,6 +75,7 @@ SIGNATURES = {
     "tr_test_offset_ray": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
     "tr_test_rng": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _vp]),
     "tr_test_trace": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "tr_test_trace_kernel": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp]),
     "tr_spec_sensor_upload": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_float]),
     "tr_spec_spectrum_upload": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_float, C.c_float]),
     "tr_spec_spectrum_download": (C.c_int, [_vp, C.c_int, _vp]),
@@ -354,10 +355,14 @@ class Context:
     def test_rng(self, seed, pixel, frame, block):
         out = np.zeros(4, np.float32); self._ck(self.lib.tr_test_rng(self.h, seed, pixel, frame, block, _ptr(out)), "hook"); return out
 
-    def test_trace(self, o, d, shadow=False):
+    def test_trace(self, o, d, shadow=False, kernel=0, target=None):
+        """rays through the traversal code: kernel 0 the simple walk, 1 the production k_trace, 2 the production k_shadow
+        (target = primitive every ray must see), 3 the production k_tail"""
         o, d = _f(o, (-1, 3)), _f(d, (-1, 3)); n = o.shape[0]
+        tg = None if target is None else np.ascontiguousarray(target, np.int32)
         t = np.zeros(n, np.float32); prim = np.zeros(n, np.int32); uv = np.zeros((n, 2), np.float32)
-        self._ck(self.lib.tr_test_trace(self.h, n, _ptr(o), _ptr(d), int(shadow), _ptr(t), _ptr(prim), _ptr(uv)), "tr_test_trace")
+        self._ck(self.lib.tr_test_trace_kernel(self.h, int(kernel), n, _ptr(o), _ptr(d), _ptr(tg), int(shadow), _ptr(t), _ptr(prim), _ptr(uv)),
+                 "tr_test_trace_kernel")
         return t, prim, uv
 
 

@@ -80,11 +80,11 @@ void tr_ctx_destroy(tr_ctx* ctx) {
                     ctx->d_build_status, ctx->d_nodes, ctx->d_leaves, ctx->d_leaf_of_prim, ctx->d_shade, ctx->d_hist, ctx->d_hdr, ctx->d_rgb,
                     ctx->d_fh, ctx->d_tiles, ctx->d_path[0][0], ctx->d_path[0][1], ctx->d_path[0][2], ctx->d_path[1][0],
                     ctx->d_path[1][1], ctx->d_path[1][2], ctx->d_hit, ctx->d_cls, ctx->d_shq[0][0], ctx->d_shq[0][1],
-                    ctx->d_shq[0][2], ctx->d_shq[1][0], ctx->d_shq[1][1], ctx->d_shq[1][2], ctx->d_Lnee, ctx->d_L, ctx->d_ctr, ctx->d_batch_params, ctx->d_matlin, ctx->d_axis, ctx->d_nodesx, ctx->d_smooth,
+                    ctx->d_shq[0][2], ctx->d_shq[1][0], ctx->d_shq[1][1], ctx->d_shq[1][2], ctx->d_Lnee, ctx->d_L, ctx->d_ctr, ctx->d_batch_params, ctx->d_matlin, ctx->d_smooth,
                     ctx->d_sensor, ctx->d_spectrum[0], ctx->d_spectrum[1], ctx->d_spectrum[2], ctx->d_spectrum[3], ctx->d_rs_scale, ctx->d_rs_data,
                     ctx->d_sky, ctx->d_matspec, ctx->d_white_point,
                     ctx->d_bd_vb, ctx->d_bd_depths, ctx->d_bd_contrib, ctx->d_bd_splat, ctx->d_bd_items, ctx->d_bd_tile_slot, ctx->d_bd_ctr,
-                    ctx->d_bd_sq[0], ctx->d_bd_sq[1], ctx->d_bd_vis, ctx->d_hdr_sum, ctx->d_nodes2, ctx->d_small_img};
+                    ctx->d_bd_sq[0], ctx->d_bd_sq[1], ctx->d_bd_vis, ctx->d_hdr_sum, ctx->d_nodes2, ctx->d_small_img, ctx->d_first, ctx->d_sneed, ctx->d_irank, ctx->d_top};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -320,8 +320,8 @@ int tr_set_option(tr_ctx* ctx, const char* name, int value) {
     const Opt opts[] = {
         {"batch_frames", &ctx->opt_batch_frames, 0, 1 << 20}, {"stage_timing", &ctx->opt_stage_timing, 0, 1}, {"graph", &ctx->opt_graph, 0, 1},
         {"smem_bvh", &ctx->opt_smem_bvh, 0, 1}, {"chains", &ctx->opt_chains, 1, TR_MAX_CHAINS}, {"shadow_overlap", &ctx->opt_shadow_overlap, 0, 1},
-        {"tail_max", &ctx->opt_tail_max, -1, 1 << 24}, {"tail_chunk", &ctx->opt_tail_chunk, 1, 32}, {"bdpt_wavefront", &ctx->opt_bdpt_wavefront, 0, 1},
-        {"top_nodes", &ctx->opt_top_nodes, 0, 1 << 16}, {"pdl", &ctx->opt_pdl, 0, 1}, {"replicas", &ctx->opt_replicas, 0, 1},
+        {"tail_max", &ctx->opt_tail_max, -1, 1 << 30}, {"tail_chunk", &ctx->opt_tail_chunk, 1, 32}, {"bdpt_wavefront", &ctx->opt_bdpt_wavefront, 0, 1},
+        {"top_nodes", &ctx->opt_top_nodes, 0, 1 << 16}, {"pdl", &ctx->opt_pdl, 0, 1}, {"replicas", &ctx->opt_replicas, 0, 1}, {"stack_smem", &ctx->opt_stack_smem, 1, 64},
     };
     bool found = false;
     for (const Opt& o : opts) if (!strcmp(name, o.name)) {

@@ -152,9 +152,9 @@ __device__ __forceinline__ void bd_vertex0(const WfArgs& a, const BdArgs& b, con
 // The two loops differ where the reference differs: the eye path stores the emitter vertex it hits and measures `to`
 // from the offset ray origin with a clamped distance; the light path stops in front of emitters, measures from the
 // stored previous position, and multiplies fpdf in a different order.
-template <bool SMEM, bool LIGHT>
-__device__ __forceinline__ void bdpt_subpath(const WfArgs& a, const BdArgs& b, const BatchParams& bp, const TrNode* nodes, const TrLeaf* leaves,
-                                             const TrNodeX* nodesx, size_t s, bool active, unsigned pix, unsigned frame, int x, int y,
+template <bool LIGHT>
+__device__ __forceinline__ void bdpt_subpath(const WfArgs& a, const BdArgs& b, const BatchParams& bp, const TreeView& tv,
+                                             size_t s, bool active, unsigned pix, unsigned frame, int x, int y,
                                              unsigned long long& n_closest) {
     const int maxd = LIGHT ? BD_LIGHT_MAX : BD_EYE_MAX;
     V3 origin = mk3(0.f, 0.f, 0.f), dir = mk3(1.f, 1.f, 1.f), beta = mk3(1.f, 1.f, 1.f), prev_pos = origin, prev_normal = dir;
@@ -165,7 +165,7 @@ __device__ __forceinline__ void bdpt_subpath(const WfArgs& a, const BdArgs& b, c
     for (int it = 1; it < maxd; ++it) {
         if (__ballot_sync(0xffffffffu, alive) == 0u) break;
         RayPre r = make_ray(origin, dir);
-        HitRec h = trace_closest<SMEM>(nodes, leaves, nodesx, a.nnodes, r, alive, a.ctr->visits);
+        HitRec h = trace_closest(tv, a.root, r, alive, a.ctr->visits);
         if (!alive) continue;
         ++n_closest;
         if (h.prim < 0) { alive = false; continue; }
@@ -177,10 +177,14 @@ __device__ __forceinline__ void bdpt_subpath(const WfArgs& a, const BdArgs& b, c
     if (active) b.depths[(LIGHT ? b.cap : 0) + s] = depth;
 }
 
-template <bool SMEM>
+// global-memory view of the tree for the simple (one lane = one ray) walks of the lock-step cross-check pipeline
+__device__ __forceinline__ TreeView global_tree(const WfArgs& a) {
+    TreeView tv; tv.snodes = tv.sleaves = nullptr; tv.gnodes = a.nodes2; tv.gleaves = a.leaves4; tv.top = 0;
+    return tv;
+}
+
 __global__ void __launch_bounds__(WF_THREADS) k_bdpt_paths(WfArgs a, BdArgs b) {
-    const TrNode* nodes; const TrLeaf* leaves; const TrNodeX* nodesx;
-    bvh_view<SMEM>(a, nodes, leaves, nodesx);
+    const TreeView tv = global_tree(a);
     const BatchParams bp = *a.bp;
     const int nsamp = bp.n_frames * a.npix, nsamp_r = (nsamp + 31) & ~31;
     const int lane = threadIdx.x & 31;
@@ -193,8 +197,8 @@ __global__ void __launch_bounds__(WF_THREADS) k_bdpt_paths(WfArgs a, BdArgs b) {
         if (s < nsamp) { int f = s / a.npix, p = s - f * a.npix; frame = (unsigned)(bp.frame_begin + f); active = slot_to_pixel(a, p, x, y); }
         const unsigned pix = ((unsigned)x << 16) | (unsigned)y;
         if (s < nsamp && !active) b.depths[(light ? b.cap : 0) + s] = 0;
-        if (light) bdpt_subpath<SMEM, true>(a, b, bp, nodes, leaves, nodesx, (size_t)s, active, pix, frame, x, y, n_closest);
-        else bdpt_subpath<SMEM, false>(a, b, bp, nodes, leaves, nodesx, (size_t)s, active, pix, frame, x, y, n_closest);
+        if (light) bdpt_subpath<true>(a, b, bp, tv, (size_t)s, active, pix, frame, x, y, n_closest);
+        else bdpt_subpath<false>(a, b, bp, tv, (size_t)s, active, pix, frame, x, y, n_closest);
     }
     if (n_closest) atomicAdd(b.ctr, n_closest);
 }
@@ -451,10 +455,8 @@ __device__ __forceinline__ void bd_connect_finish(const WfArgs& a, const BdArgs&
 }
 
 // lock-step pipeline: one lane per (sample, e, l), the warp walks the BVH together
-template <bool SMEM>
 __global__ void __launch_bounds__(WF_THREADS) k_bdpt_connect(WfArgs a, BdArgs b) {
-    const TrNode* nodes; const TrLeaf* leaves; const TrNodeX* nodesx;
-    bvh_view<SMEM>(a, nodes, leaves, nodesx);
+    const TreeView tv = global_tree(a);
     const BatchParams bp = *a.bp;
     const int n = (int)b.ctr[2], n_r = (n + 31) & ~31;
     const int lane = threadIdx.x & 31;
@@ -471,7 +473,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_bdpt_connect(WfArgs a, BdArgs b)
         if (__ballot_sync(0xffffffffu, c.need) != 0u) {
             RayPre r = make_ray(c.need ? c.ro : mk3(0.f, 0.f, 0.f), c.need ? c.rd : mk3(1.f, 1.f, 1.f));
             int tleaf = c.need ? __ldg(a.leaf_of_prim + c.target) : 0;
-            vis = trace_shadow_visible<SMEM>(nodes, leaves, nodesx, a.nnodes, r, c.need, tleaf, a.ctr->visits + 2, &tt);
+            vis = trace_shadow_visible(tv, a.root, r, c.need, tleaf, a.ctr->visits + 2, &tt);
             if (c.need) ++n_shadow;
         }
         if (active) bd_connect_finish(a, b, s, e, l, c, vis, tt);
@@ -663,18 +665,10 @@ static int render_bdpt(tr_ctx* ctx, int frame_begin, int n_frames, uint64_t seed
     b.tile_slot = ctx->d_bd_tile_slot; b.ctr = ctx->d_bd_ctr; b.cap = ctx->bd_cap; memcpy(b.view, ctx->view, 64);
     LaunchCfg cfg; memset(&cfg, 0, sizeof(cfg)); if ((rc = launch_cfg(ctx, a, cfg))) return rc;
     int bp_ = 1, bc_ = 1, bq_ = 1;
-    if (cfg.use_smem) {
-        TR_CUDA(ctx, cudaFuncSetAttribute(k_bdpt_paths<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-        TR_CUDA(ctx, cudaFuncSetAttribute(k_bdpt_connect<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-        TR_CUDA(ctx, cudaFuncSetAttribute(k_shadow<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-        TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bp_, k_bdpt_paths<true>, WF_THREADS, cfg.smem));
-        TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bc_, k_bdpt_connect<true>, WF_THREADS, cfg.smem));
-        TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bq_, k_shadow<true, true>, WF_THREADS, cfg.smem));
-    } else {
-        TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bp_, k_bdpt_paths<false>, WF_THREADS, 0));
-        TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bc_, k_bdpt_connect<false>, WF_THREADS, 0));
-        TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bq_, k_shadow<false, true>, WF_THREADS, 0));
-    }
+    TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bp_, k_bdpt_paths, WF_THREADS, 0));
+    TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bc_, k_bdpt_connect, WF_THREADS, 0));
+    TR_MODE_SWITCH(cfg.mode, { if (!rc) rc = kernel_blocks(ctx, k_shadow<M, true>, cfg.smem, bq_); });
+    if (rc) return rc;
     if (bp_ < 1) bp_ = 1; if (bc_ < 1) bc_ = 1; if (bq_ < 1) bq_ = 1;
     cudaStream_t s = ctx->stream;
     uint64_t launches = 0, rays_c = 0, rays_s = 0, vis[4] = {0, 0, 0, 0};
@@ -699,8 +693,7 @@ static int render_bdpt(tr_ctx* ctx, int frame_begin, int n_frames, uint64_t seed
             k_bdpt_generate<<<cfg.grid_simple, WF_THREADS, 0, s>>>(a, b); ++launches;
             for (int d = 0; d < BD_EYE_MAX - 1; ++d) {
                 if (ev) cudaEventRecord(ev[8 + 2 * d], s);
-                if (cfg.use_smem) k_trace<true><<<cfg.grid_trace, WF_THREADS, cfg.smem, s>>>(a, d);
-                else k_trace<false><<<cfg.grid_trace, WF_THREADS, 0, s>>>(a, d);
+                TR_MODE_SWITCH(cfg.mode, (k_trace<M><<<cfg.grid_trace, WF_THREADS, cfg.smem, s>>>(a, d)));
                 if (ev) cudaEventRecord(ev[9 + 2 * d], s);
                 k_bdpt_vertex<<<cfg.grid_simple, WF_THREADS, 0, s>>>(a, b, d);
                 launches += 2;
@@ -710,21 +703,18 @@ static int render_bdpt(tr_ctx* ctx, int frame_begin, int n_frames, uint64_t seed
             if (ev) cudaEventRecord(ev[2], s);
             k_bdpt_connect_gen<<<cfg.grid_simple, WF_THREADS, 0, s>>>(a, b);
             if (ev) cudaEventRecord(ev[5], s);
-            if (cfg.use_smem) k_shadow<true, true><<<ctx->num_sms * bq_, WF_THREADS, cfg.smem, s>>>(a, 0);
-            else k_shadow<false, true><<<ctx->num_sms * bq_, WF_THREADS, 0, s>>>(a, 0);
+            TR_MODE_SWITCH(cfg.mode, (k_shadow<M, true><<<ctx->num_sms * bq_, WF_THREADS, cfg.smem, s>>>(a, 0)));
             if (ev) cudaEventRecord(ev[6], s);
             k_bdpt_connect_eval<<<cfg.grid_simple, WF_THREADS, 0, s>>>(a, b);
             k_bdpt_mis<<<cfg.grid_simple, WF_THREADS, 0, s>>>(a, b);
             if (ev) cudaEventRecord(ev[3], s);
             launches += 5;
         } else if (a.npix > 0) {
-            if (cfg.use_smem) k_bdpt_paths<true><<<ctx->num_sms * bp_, WF_THREADS, cfg.smem, s>>>(a, b);
-            else k_bdpt_paths<false><<<ctx->num_sms * bp_, WF_THREADS, 0, s>>>(a, b);
+            k_bdpt_paths<<<ctx->num_sms * bp_, WF_THREADS, 0, s>>>(a, b);
             if (ev) cudaEventRecord(ev[1], s);
             k_bdpt_items<<<cfg.grid_simple, WF_THREADS, 0, s>>>(a, b);
             if (ev) cudaEventRecord(ev[2], s);
-            if (cfg.use_smem) k_bdpt_connect<true><<<ctx->num_sms * bc_, WF_THREADS, cfg.smem, s>>>(a, b);
-            else k_bdpt_connect<false><<<ctx->num_sms * bc_, WF_THREADS, 0, s>>>(a, b);
+            k_bdpt_connect<<<ctx->num_sms * bc_, WF_THREADS, 0, s>>>(a, b);
             if (ev) cudaEventRecord(ev[3], s);
             launches += 3;
         }

@@ -165,7 +165,7 @@ __device__ __forceinline__ int find_split(const int* __restrict__ code, int firs
 }
 
 __global__ void k_karras(const int* __restrict__ code, int n, int* __restrict__ left, int* __restrict__ right, int* __restrict__ parent,
-                         int* __restrict__ axis) {
+                         int* __restrict__ first) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     int r0, r1; determine_range(code, n, i, r0, r1);
@@ -175,10 +175,7 @@ __global__ void k_karras(const int* __restrict__ code, int n, int* __restrict__ 
     if (max(r0, r1) == split + 1) r += n - 1;
     left[i] = l; right[i] = r;
     parent[l] = i; parent[r] = i;
-    // split axis of this node = axis of the highest Morton bit in which its range differs (bit 0 = x, 1 = y, 2 = z;
-    // the left child holds the smaller coordinate). 3 = no axis (run of identical codes). Only used to ORDER the walk.
-    int x = code[min(r0, r1)] ^ code[max(r0, r1)];
-    axis[i] = (x > 0) ? ((31 - __clz(x)) % 3) : 3;
+    first[i] = min(r0, r1);                            // sorted position of the node's first leaf
 }
 
 // ------------------------------------------------------------------ leaf boxes + atomic bottom-up refit
@@ -186,7 +183,7 @@ __global__ void k_karras(const int* __restrict__ code, int n, int* __restrict__ 
 // The fixed point is identical: boxes are exact min/max unions.
 __global__ void k_refit(const float* __restrict__ vertex, const int* __restrict__ prim, const float* __restrict__ shape,
                         const int* __restrict__ sorted_prim, int n, const int* __restrict__ left, const int* __restrict__ right,
-                        const int* __restrict__ parent, float* boxes, int* leafcount, int* flag, int* status) {
+                        const int* __restrict__ parent, float* boxes, int* leafcount, int* flag, int* status, int* sneed) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     int node = n - 1 + k;
@@ -208,6 +205,7 @@ __global__ void k_refit(const float* __restrict__ vertex, const int* __restrict_
     float* bx = boxes + (size_t)node * 6;
     bx[0] = mn.x; bx[1] = mn.y; bx[2] = mn.z; bx[3] = mx.x; bx[4] = mx.y; bx[5] = mx.z;
     leafcount[node] = 1;
+    sneed[node] = 0;
     __threadfence();
     int cur = parent[node];
     while (cur >= 0) {
@@ -223,6 +221,12 @@ __global__ void k_refit(const float* __restrict__ vertex, const int* __restrict_
 #pragma unroll
         for (int q = 0; q < 6; ++q) c[q] = o[q];
         leafcount[cur] = __ldcg(leafcount + l) + __ldcg(leafcount + r);
+        // traversal-stack entries the sub-tree needs (trace.cuh: a leaf child is taken before an internal one, the other child
+        // is pushed): two internal children 1 + max, one leaf child max(1, S(internal child)), two leaves 1
+        const int sl = __ldcg(sneed + l), sr = __ldcg(sneed + r);
+        const int need = (l < n - 1 && r < n - 1) ? 1 + max(sl, sr) : max(1, max(sl, sr));
+        sneed[cur] = need;
+        if (cur == 0) status[1] = need;
         atomicAdd(status, 1);
         __threadfence();
         cur = parent[cur];
@@ -235,8 +239,7 @@ __global__ void k_refit(const float* __restrict__ vertex, const int* __restrict_
 __global__ void k_flatten(const float* __restrict__ vertex, const int* __restrict__ prim, const float* __restrict__ shape,
                           const int* __restrict__ sorted_prim, int n, const int* __restrict__ left, const int* __restrict__ right,
                           const int* __restrict__ parent, const float* __restrict__ boxes, const int* __restrict__ leafcount,
-                          int* __restrict__ pre_out, TrNode* __restrict__ nodes, TrLeaf* __restrict__ leaves,
-                          int* __restrict__ leaf_of_prim, float leaf_guard, const int* __restrict__ axis) {
+                          int* __restrict__ pre_out, TrNode* __restrict__ nodes, TrLeaf* __restrict__ leaves, int* __restrict__ leaf_of_prim) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int nn = 2 * n - 1;
     if (x >= nn) return;
@@ -247,18 +250,16 @@ __global__ void k_flatten(const float* __restrict__ vertex, const int* __restric
         c = p;
     }
     pre_out[x] = pre;
-    const float* b = boxes + (size_t)x * 6;
-    int lc = leafcount[x];
-    bool leaf = x >= n - 1;
-    int link = leaf ? -((x - (n - 1)) + 1) : ((pre + 2 * leafcount[left[x]]) | (axis[x] << 29));
-    // traversal copy of the box: leaf boxes are grown by a guard band (the reference never tests a leaf's
-    // own box; the band keeps the cull strictly weaker than the triangle test).  The reference-layout
-    // views (tr_bvh_download) come from `boxes`, untouched.
-    float g = leaf ? leaf_guard : 0.0f;
-    TrNode nd;
-    nd.lo = make_float4(b[0] - g, b[1] - g, b[2] - g, __int_as_float(pre + 2 * lc - 1));
-    nd.hi = make_float4(b[3] + g, b[4] + g, b[5] + g, __int_as_float(link));
-    nodes[pre] = nd;
+    const bool leaf = x >= n - 1;
+    {   // the reference's pre-order node (exact boxes), for process_normal's point queries
+        const float* b = boxes + (size_t)x * 6;
+        const int lc = leafcount[x];
+        const int link = leaf ? -((x - (n - 1)) + 1) : (pre + 2 * leafcount[left[x]]);
+        TrNode nd;
+        nd.lo = make_float4(b[0], b[1], b[2], __int_as_float(pre + 2 * lc - 1));
+        nd.hi = make_float4(b[3], b[4], b[5], __int_as_float(link));
+        nodes[pre] = nd;
+    }
     if (leaf) {
         int k = x - (n - 1), pi = sorted_prim[k];
         int type = prim[pi * 3], vi = prim[pi * 3 + 1], mat = prim[pi * 3 + 2];
@@ -282,27 +283,113 @@ __global__ void k_flatten(const float* __restrict__ vertex, const int* __restric
     }
 }
 
-// ------------------------------------------------------------------ ordered threading
-// nodesx[pre(x)].next[o] = node to visit after the sub-tree of x when the walk enters, at every internal node, the child
-// on the near side of a ray with direction-sign octant o (bit a set <=> d[a] < 0) first.  Stackless front-to-back
-// order: 8 escape links per node instead of one.
-__global__ void k_next8(int n, const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ parent,
-                        const int* __restrict__ axis, const int* __restrict__ pre, const TrNode* __restrict__ nodes,
-                        TrNodeX* __restrict__ nodesx) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int nn = 2 * n - 1;
-    if (t >= nn * 8) return;
-    int x = t >> 3, o = t & 7;
-    int c = x, p, res = nn;
-    while ((p = parent[c]) >= 0) {
-        int l = left[p], r = right[p];
-        int first = ((o >> axis[p]) & 1) ? r : l;          // axis 3: bit 3 of o is 0 -> left first
-        if (c == first) { res = pre[first == l ? r : l]; break; }
-        c = p;
+// ------------------------------------------------------------------ render-kernel nodes (TrNode2)
+// Breadth-first top of the tree: the first min(TR_TOP_MAX, n-1) internal nodes in level order (one block, level by level with
+// a block scan, so the order is deterministic).  top[i] = build-order id of the i-th node.
+__global__ void __launch_bounds__(1024) k_top_bfs(int n, const int* __restrict__ left, const int* __restrict__ right, int* __restrict__ top,
+                                                   int* __restrict__ status) {
+    __shared__ int q[TR_TOP_MAX];
+    __shared__ int scan[1024];
+    __shared__ int s_cnt;
+    const int t = threadIdx.x, nint = n - 1;
+    if (t == 0) { q[0] = 0; s_cnt = 1; }
+    __syncthreads();
+    int lvl_begin = 0, lvl_end = 1;
+    while (lvl_begin < lvl_end && lvl_end < TR_TOP_MAX && lvl_end < nint) {
+        int c0 = -1, c1 = -1;
+        if (lvl_begin + t < lvl_end) {
+            const int x = q[lvl_begin + t];
+            const int l = left[x], r = right[x];
+            if (l < nint) c0 = l;
+            if (r < nint) c1 = r;
+        }
+        const int mine = (c0 >= 0) + (c1 >= 0);
+        scan[t] = mine;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {             // inclusive Hillis-Steele scan
+            int v = (t >= off) ? scan[t - off] : 0;
+            __syncthreads();
+            scan[t] += v;
+            __syncthreads();
+        }
+        int pos = lvl_end + scan[t] - mine;
+        if (c0 >= 0) { if (pos < TR_TOP_MAX) q[pos] = c0; ++pos; }
+        if (c1 >= 0) { if (pos < TR_TOP_MAX) q[pos] = c1; }
+        const int total = scan[1023];
+        __syncthreads();
+        lvl_begin = lvl_end; lvl_end = min(lvl_end + total, TR_TOP_MAX);
     }
-    const int px = pre[x];
-    nodesx[px].next[o] = res;
-    if (o == 0) { nodesx[px].lo = nodes[px].lo; nodesx[px].hi = nodes[px].hi; }
+    const int cnt = min(lvl_end, nint);
+    if (t < cnt) top[t] = q[t];
+    if (t == 0) status[2] = cnt;
+}
+
+// position of internal node x (build id) in the TrNode2 array: breadth-first position for the top nodes, otherwise
+// cnt + (pre-order rank among internal nodes) - (top nodes with a smaller rank).
+__device__ __forceinline__ int node2_index(int x, const int* __restrict__ irank, const int* __restrict__ top_sorted_rank, const int* __restrict__ top_pos, int cnt) {
+    const int rk = irank[x];
+    int lo = 0, hi = cnt;                      // lower_bound over the top nodes' ranks
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (top_sorted_rank[mid] < rk) lo = mid + 1; else hi = mid; }
+    if (lo < cnt && top_sorted_rank[lo] == rk) return top_pos[lo];
+    return cnt + rk - lo;
+}
+
+// pre-order rank among the internal nodes = pre(x) - (leaves before x in pre-order) = pre(x) - first leaf of x
+__global__ void k_irank(int n, const int* __restrict__ pre, const int* __restrict__ first, int* __restrict__ irank) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x < n - 1) irank[x] = pre[x] - first[x];
+}
+// rank-sorted view of the top list (ranks ascending + breadth-first position of each)
+__global__ void k_top_ranks(int cnt_max, const int* __restrict__ status, const int* __restrict__ top, const int* __restrict__ irank,
+                            int* __restrict__ sorted_rank, int* __restrict__ pos_of) {
+    // single block of 1024: bitonic sort of (rank << 11 | bfs position)
+    __shared__ long long key[1024];
+    const int t = threadIdx.x, cnt = status[2];
+    key[t] = (t < cnt) ? (((long long)irank[top[t]] << 11) | t) : 0x7fffffffffffffffLL;
+    __syncthreads();
+    for (int k = 2; k <= 1024; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int ixj = t ^ j;
+            if (ixj > t) {
+                const bool up = (t & k) == 0;
+                const long long a = key[t], b = key[ixj];
+                if ((a > b) == up) { key[t] = b; key[ixj] = a; }
+            }
+            __syncthreads();
+        }
+    if (t < cnt) { sorted_rank[t] = (int)(key[t] >> 11); pos_of[t] = (int)(key[t] & 2047); }
+    (void)cnt_max;
+}
+
+__global__ void k_nodes2(int n, const int* __restrict__ left, const int* __restrict__ right, const float* __restrict__ boxes,
+                         const int* __restrict__ irank, const int* __restrict__ sorted_rank, const int* __restrict__ pos_of,
+                         const int* __restrict__ status, float leaf_guard, TrNode2* __restrict__ out) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n - 1) return;
+    const int cnt = status[2], nint = n - 1;
+    const int l = left[x], r = right[x];
+    const int link0 = l >= nint ? -((l - nint) + 1) : node2_index(l, irank, sorted_rank, pos_of, cnt);
+    const int link1 = r >= nint ? -((r - nint) + 1) : node2_index(r, irank, sorted_rank, pos_of, cnt);
+    // leaf boxes carry the guard band (the reference never tests a leaf's own box; the band keeps the cull strictly weaker
+    // than the triangle test), internal boxes are the exact unions the reference tests
+    const float g0 = l >= nint ? leaf_guard : 0.0f, g1 = r >= nint ? leaf_guard : 0.0f;
+    const float* b0 = boxes + (size_t)l * 6; const float* b1 = boxes + (size_t)r * 6;
+    TrNode2 nd;
+    nd.a = make_float4(b0[0] - g0, b0[1] - g0, b0[2] - g0, __int_as_float(link0));
+    nd.b = make_float4(b0[3] + g0, b0[4] + g0, b0[5] + g0, __int_as_float(link1));
+    nd.c = make_float4(b1[0] - g1, b1[1] - g1, b1[2] - g1, 0.0f);
+    nd.d = make_float4(b1[3] + g1, b1[4] + g1, b1[5] + g1, 0.0f);
+    out[node2_index(x, irank, sorted_rank, pos_of, cnt)] = nd;
+}
+
+// 8-way replicated shared-memory image of a small tree: row (4 i + w) = word w of node i, row (4 nint + 3 k + w) = word w of
+// leaf k, every row = the 16-byte word eight times (128 B): lane l reads column l & 7 (trace.cuh, TM_REP)
+__global__ void k_small_img(int nint, int nleaves, const float4* __restrict__ nodes2, const float4* __restrict__ leaves, float4* __restrict__ img) {
+    const int rows = nint * 4 + nleaves * 3;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows * 8) return;
+    const int row = t >> 3;
+    img[t] = row < nint * 4 ? nodes2[row] : leaves[row - nint * 4];
 }
 
 // ------------------------------------------------------------------ reference-layout views
@@ -354,8 +441,14 @@ extern "C" int tr_bvh_build(tr_ctx* ctx) {
     if ((rc = tr_realloc(ctx, &ctx->d_nodes, (size_t)nn))) return rc;
     if ((rc = tr_realloc(ctx, &ctx->d_leaves, (size_t)n))) return rc;
     if ((rc = tr_realloc(ctx, &ctx->d_leaf_of_prim, (size_t)n))) return rc;
-    if ((rc = tr_realloc(ctx, &ctx->d_axis, (size_t)nn))) return rc;
-    if ((rc = tr_realloc(ctx, &ctx->d_nodesx, (size_t)nn))) return rc;
+    if ((rc = tr_realloc(ctx, &ctx->d_first, (size_t)nn))) return rc;
+    if ((rc = tr_realloc(ctx, &ctx->d_sneed, (size_t)nn))) return rc;
+    if ((rc = tr_realloc(ctx, &ctx->d_irank, (size_t)nn))) return rc;
+    if ((rc = tr_realloc(ctx, &ctx->d_top, (size_t)3 * TR_TOP_MAX))) return rc;          // top ids | their ranks sorted | breadth-first position of each
+    if ((rc = tr_realloc(ctx, &ctx->d_nodes2, (size_t)(n > 1 ? n - 1 : 1)))) return rc;
+    const size_t img_rows = (size_t)(n - 1) * 4 + (size_t)n * 3;
+    const bool small = img_rows * 128 <= TR_SMALL_IMG_MAX;
+    if (small && (rc = tr_realloc(ctx, &ctx->d_small_img, img_rows * 8))) return rc;
     const int nblocks = cdiv(n, SORT_CHUNK);
     if ((rc = tr_realloc(ctx, &ctx->d_hist, (size_t)RADIX * nblocks))) return rc;
 
@@ -385,26 +478,41 @@ extern "C" int tr_bvh_build(tr_ctx* ctx) {
             TR_CHECK_LAUNCH(ctx);
             cur ^= 1;
         }
-        k_karras<<<cdiv(n - 1, 256), 256, 0, s>>>(ctx->d_keys[cur], n, ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_axis);
+        k_karras<<<cdiv(n - 1, 256), 256, 0, s>>>(ctx->d_keys[cur], n, ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_first);
         TR_CHECK_LAUNCH(ctx);
     }
     ctx->sorted_buf = cur;
     k_refit<<<cdiv(n, 256), 256, 0, s>>>(ctx->d_vertex, ctx->d_prim, ctx->d_shape, ctx->d_vals[cur], n, ctx->d_left, ctx->d_right,
-                                        ctx->d_parent, ctx->d_boxes, ctx->d_leafcount, ctx->d_flag, ctx->d_build_status);
+                                        ctx->d_parent, ctx->d_boxes, ctx->d_leafcount, ctx->d_flag, ctx->d_build_status, ctx->d_sneed);
     TR_CHECK_LAUNCH(ctx);
     k_flatten<<<cdiv(nn, 256), 256, 0, s>>>(ctx->d_vertex, ctx->d_prim, ctx->d_shape, ctx->d_vals[cur], n, ctx->d_left, ctx->d_right,
-                                           ctx->d_parent, ctx->d_boxes, ctx->d_leafcount, ctx->d_pre, ctx->d_nodes, ctx->d_leaves,
-                                           ctx->d_leaf_of_prim, leaf_guard, ctx->d_axis);
+                                           ctx->d_parent, ctx->d_boxes, ctx->d_leafcount, ctx->d_pre, ctx->d_nodes, ctx->d_leaves, ctx->d_leaf_of_prim);
     TR_CHECK_LAUNCH(ctx);
-    k_next8<<<cdiv(nn * 8, 256), 256, 0, s>>>(n, ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_axis, ctx->d_pre, ctx->d_nodes, ctx->d_nodesx);
-    TR_CHECK_LAUNCH(ctx);
+    if (n > 1) {
+        int* top = ctx->d_top; int* srank = top + TR_TOP_MAX; int* spos = top + 2 * TR_TOP_MAX;
+        k_irank<<<cdiv(n - 1, 256), 256, 0, s>>>(n, ctx->d_pre, ctx->d_first, ctx->d_irank);
+        k_top_bfs<<<1, 1024, 0, s>>>(n, ctx->d_left, ctx->d_right, top, ctx->d_build_status);
+        k_top_ranks<<<1, 1024, 0, s>>>(TR_TOP_MAX, ctx->d_build_status, top, ctx->d_irank, srank, spos);
+        k_nodes2<<<cdiv(n - 1, 256), 256, 0, s>>>(n, ctx->d_left, ctx->d_right, ctx->d_boxes, ctx->d_irank, srank, spos, ctx->d_build_status,
+                                                 leaf_guard, ctx->d_nodes2);
+        TR_CHECK_LAUNCH(ctx);
+    }
+    if (small) {
+        k_small_img<<<cdiv((int)img_rows * 8, 256), 256, 0, s>>>(n - 1, n, (const float4*)ctx->d_nodes2, (const float4*)ctx->d_leaves, ctx->d_small_img);
+        TR_CHECK_LAUNCH(ctx);
+    } else if (ctx->d_small_img) { cudaFree(ctx->d_small_img); ctx->capacity.erase((void*)ctx->d_small_img); ctx->d_small_img = nullptr; }
+    TR_CUDA(ctx, cudaMemcpyAsync(ctx->h_build_status + 8, ctx->d_boxes, 6 * sizeof(float), cudaMemcpyDeviceToHost, s));   // root box (node 0; the single leaf when n == 1)
     TR_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
     int* status = ctx->h_build_status;                   // pinned: a true asynchronous copy, one wait for build + copy
-    TR_CUDA(ctx, cudaMemcpyAsync(status, ctx->d_build_status, 16 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    TR_CUDA(ctx, cudaMemcpyAsync(status, ctx->d_build_status, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));      // [8..13] hold the root box
     TR_CUDA(ctx, cudaStreamSynchronize(s));
     float ms = 0.0f; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->stats.ms_build = ms;
     if (status[0] != n - 1)
         return tr_fail(ctx, TR_ERR_AABB, "aabb gen error: %d of %d internal nodes refitted", status[0], n - 1);
+    ctx->stack_need = n > 1 ? status[1] : 1; ctx->top_count = n > 1 ? status[2] : 0;
+    memcpy(ctx->root_box, status + 8, 6 * sizeof(float));
+    if (ctx->stack_need > TR_STACK_MAX)
+        return tr_fail(ctx, TR_ERR_STACK, "overflow, need larger stack: the tree needs %d traversal-stack entries (limit %d)", ctx->stack_need, TR_STACK_MAX);
     ctx->bvh_ready = true; ctx->shade_ready = false; ctx->fh_ready = false;
     ctx->gen++;
     return TR_OK;

@@ -13,14 +13,20 @@
 #define TR_MAX_CHAINS 8           // independent wavefront chains per batch (parallel graph branches)
 #define TR_TILE 32                // framebuffer tile edge used for sharding and ray coherence
 
-// Traversal node, 32 B, left-first pre-order (left child = idx+1), threaded with an escape index.
-//   lo = (min.x, min.y, min.z, as_float(escape))      escape = idx + subtree size
-//   hi = (max.x, max.y, max.z, as_float(link))        link >= 0: pre-order index of the right child | split axis << 29
-//                                                     link <  0: leaf, sorted position k = -link-1
+// Pre-order node of the reference's flattened tree, 32 B (left child = idx+1): lo = (min.xyz, as_float(escape = idx + subtree size)),
+// hi = (max.xyz, as_float(link)), link >= 0: pre-order index of the right child, link < 0: leaf with sorted position -link-1.
+// Walked by process_normal's point queries (normals.cu), which must visit candidates in the reference's order.
 struct TrNode { float4 lo, hi; };
-// Node of the ordered (front-to-back) walk used for trees that live in global memory: the same box words plus the 8
-// direction-octant escape links, 64 B = one half cache line per visit.
-struct TrNodeX { float4 lo, hi; int next[8]; };
+// Traversal node of the render kernels, 64 B, one per INTERNAL node: the boxes of both children, so one dependent load serves two
+// slab tests.  a = (lo0.xyz, as_float(link0)), b = (hi0.xyz, as_float(link1)), c = (lo1.xyz, 0), d = (hi1.xyz, 0); child 0 = left.
+//   link >= 0: index of an internal node in this array; link < 0: leaf, sorted position k = -link-1 (its box carries the guard band).
+// Order: the first top_count nodes are the breadth-first top of the tree (the part TM_GTOP stages into shared memory), the rest
+// follows in pre-order.
+struct TrNode2 { float4 a, b, c, d; };
+#define TR_STACK_SMEM 24                     // traversal-stack entries per lane kept in shared memory
+#define TR_STACK_MAX 120                     // + local-memory overflow: the deepest stack a tree may need (else TR_ERR_STACK at build)
+#define TR_TOP_MAX 1024                      // breadth-first top nodes kept contiguous at the front of the TrNode2 array
+#define TR_SMALL_IMG_MAX (40 * 1024)         // largest replicated shared-memory image (see trace.cuh)
 // Leaf record, 48 B, in sorted (Morton) order:
 //   a = (v0.xyz, as_float(prim id)), b = (E1.xyz, as_float(kind)), c = (E2.xyz, as_float(material id))   kind 0: triangle
 //   a = (centre.xyz, prim id),       b = (radius, 0, 0, kind)                         kind 1: sphere
@@ -73,8 +79,9 @@ struct tr_ctx {
     int*   d_leafcount = nullptr; int* d_flag = nullptr; int* d_pre = nullptr;
     int*   d_build_status = nullptr;     // [0] = refit-completed internal nodes
     TrNode* d_nodes = nullptr; TrLeaf* d_leaves = nullptr; int* d_leaf_of_prim = nullptr;
-    struct TrNode2* d_nodes2 = nullptr; float4* d_small_img = nullptr;
-    int* d_axis = nullptr; TrNodeX* d_nodesx = nullptr;    // split axis per internal node; 64-byte nodes with 8 octant-ordered escape links
+    TrNode2* d_nodes2 = nullptr; float4* d_small_img = nullptr;         // render-kernel nodes; 8-way replicated image of a small tree
+    int* d_first = nullptr; int* d_sneed = nullptr; int* d_irank = nullptr; int* d_top = nullptr;   // build scratch: first leaf, stack need, node order
+    float root_box[6] = {0, 0, 0, 0, 0, 0}; int stack_need = 1, top_count = 0;
     TrShade* d_shade = nullptr; bool shade_ready = false;
     int*   d_hist = nullptr; size_t hist_cap = 0;
 
@@ -139,6 +146,7 @@ struct tr_ctx {
     int opt_top_nodes = 0;          // large trees: this many breadth-first top nodes are staged into shared memory per CTA (0 = off)
     int opt_pdl = 1;                // programmatic dependent launch between the stages of a chain
     int opt_replicas = 1;           // small trees: bank-conflict-free 8-replica shared-memory image
+    int opt_stack_smem = TR_STACK_SMEM;   // traversal-stack entries per lane kept in shared memory (the rest overflows to local memory)
     size_t opt_max_paths = (size_t)20 << 20;   // path slots per batch (188 B each): more paths in flight amortise the per-stage tails
 
     // cuda graph cache for the batch pipeline

@@ -61,7 +61,7 @@ __global__ void k_smooth_normals(const float* __restrict__ vertex, const int* __
             }
         } else {
             if (v.x >= lo.x && v.y >= lo.y && v.z >= lo.z && v.x <= hi.x && v.y <= hi.y && v.z <= hi.z) {
-                stack[++sp] = ni + 1; stack[++sp] = link & 0x1fffffff;
+                stack[++sp] = ni + 1; stack[++sp] = link;
             }
         }
     }

@@ -1,20 +1,32 @@
-// trace.cuh — stackless (threaded pre-order) LBVH traversal + Moller-Trumbore, device side.
+// trace.cuh — LBVH traversal + Moller-Trumbore, device side.
 //
-// Replaces Scene.closet_hit / closet_hit_shadow (Scene.py:671-744), which walk the same pre-order
-// node array with an explicit per-pixel stack in global memory, unordered and unpruned.  Here the
-// walk follows escape links (no stack; one link per node for small trees in shared memory, eight
-// direction-octant links per node for a front-to-back walk of large trees), prunes sub-trees whose slab
-// entry lies beyond the best hit (with a relative guard band so exact/near ties are still tested) and keeps
-// the reference's result: the reference pops the right child first and accepts strict t < best, so among
-// equal-t hits the leaf with the LARGEST sorted position wins; closer() applies exactly that rule.
+// Replaces Scene.closet_hit / closet_hit_shadow (Scene.py:671-744), which walk the pre-order node array with an explicit
+// per-pixel stack in GLOBAL memory (integrator/PT_RGB.py:37), unordered and unpruned, one 36-byte node per dependent load.
+// Here:
+//   * traversal nodes (TrNode2, 64 B) hold the boxes of BOTH children of an internal node, so one dependent load serves two
+//     slab tests and the chain of dependent loads per ray is halved;
+//   * the per-lane stack lives in SHARED memory ([entry][thread]: conflict free), with a local-memory overflow region that
+//     only degenerate trees touch; a leaf child is always taken before an internal one, so chains of duplicate Morton codes
+//     (the reference's duplicate rule builds them) need one entry, and the build rejects trees that need more than
+//     TR_STACK_MAX entries with the reference's "overflow, need larger stack" (Scene.py:741-742);
+//   * of two hit children the one whose slab entry is nearer is visited first, and sub-trees whose slab entry lies beyond the
+//     best hit (relative guard band, so exact / near ties are still tested) are pruned;
+//   * small trees are staged whole into shared memory by TMA (cp.async.bulk) as a bank-conflict-free image: every 16-byte
+//     word is replicated 8 times in a 128-byte row and lane l reads column l & 7, so the 8 lanes of a quarter-warp (the unit
+//     a 128-bit shared load is served in) always touch 8 different bank quads whatever nodes they are at; medium trees are
+//     staged once (plain); of large trees the breadth-first top is staged, the rest is read from global memory.
+// The result is the reference's: the slab arithmetic (UtilsFunc.py:494-523) and Moller-Trumbore (Scene.py:603-638) are
+// restated operation by operation, every internal node's box is tested before its children are entered, and among equal-t
+// hits the reference's winner is kept explicitly (it pops the right child first and accepts strict t < best, so the LARGEST
+// sorted leaf position wins; closer() applies exactly that rule), which makes the visiting order free.
 #pragma once
 #include "ctx.h"
 #include "common.cuh"
 
 #define TR_PRUNE_GUARD 1.0001f
+#define TR_DONE 0x7fffffff          // link value of a lane whose walk is finished (also what an empty stack pops)
 
 struct RayPre {
-    int oct;               // direction-sign octant: bit a set <=> d[a] < 0 (selects the front-to-back threading)
     V3 o, d;
     float ix, iy, iz;      // 1/d per axis (UtilsFunc.py:510), unused when the axis is "parallel"
     bool px, py, pz;       // |d| < 1e-6 (UtilsFunc.py:506)
@@ -22,13 +34,12 @@ struct RayPre {
 
 __device__ __forceinline__ RayPre make_ray(V3 o, V3 d) {
     RayPre r; r.o = o; r.d = d;
-    r.oct = (d.x < 0.0f ? 1 : 0) | (d.y < 0.0f ? 2 : 0) | (d.z < 0.0f ? 4 : 0);
     r.px = fabsf(d.x) < 0.000001f; r.py = fabsf(d.y) < 0.000001f; r.pz = fabsf(d.z) < 0.000001f;
     r.ix = 1.0f / d.x; r.iy = 1.0f / d.y; r.iz = 1.0f / d.z;
     return r;
 }
 
-// UtilsFunc.py:494-523, plus tmin returned for pruning
+// UtilsFunc.py:494-523, plus tmin returned for ordering / pruning
 __device__ __forceinline__ bool slabs(const RayPre& r, float4 lo, float4 hi, float& tmin_out) {
     bool ret = true; float tmin = 0.0f, tmax = TR_INF;
     if (r.px) { if (r.o.x < lo.x || r.o.x > hi.x) ret = false; }
@@ -39,6 +50,20 @@ __device__ __forceinline__ bool slabs(const RayPre& r, float4 lo, float4 hi, flo
     else { float t1 = (lo.z - r.o.z) * r.iz, t2 = (hi.z - r.o.z) * r.iz; tmin = fmaxf(tmin, fminf(t1, t2)); tmax = fminf(tmax, fmaxf(t1, t2)); }
     tmin_out = tmin;
     return ret && !(tmin > tmax);
+}
+// Fast slab test for rays without a "parallel" axis (the common case): same arithmetic, no flags.
+__device__ __forceinline__ bool slabs_fast(const RayPre& r, float4 lo, float4 hi, float& tmin_out) {
+    float t1 = (lo.x - r.o.x) * r.ix, t2 = (hi.x - r.o.x) * r.ix;
+    float tmin = fmaxf(0.0f, fminf(t1, t2)), tmax = fminf(TR_INF, fmaxf(t1, t2));
+    t1 = (lo.y - r.o.y) * r.iy; t2 = (hi.y - r.o.y) * r.iy;
+    tmin = fmaxf(tmin, fminf(t1, t2)); tmax = fminf(tmax, fmaxf(t1, t2));
+    t1 = (lo.z - r.o.z) * r.iz; t2 = (hi.z - r.o.z) * r.iz;
+    tmin = fmaxf(tmin, fminf(t1, t2)); tmax = fminf(tmax, fmaxf(t1, t2));
+    tmin_out = tmin;
+    return !(tmin > tmax);
+}
+__device__ __forceinline__ bool slab_any(const RayPre& r, bool anypar, float4 lo, float4 hi, float& tmin) {
+    return anypar ? slabs(r, lo, hi, tmin) : slabs_fast(r, lo, hi, tmin);
 }
 
 // Scene.py:603-638 with E1/E2 precomputed at build time (same single-rounding subtractions)
@@ -88,180 +113,203 @@ __device__ __forceinline__ float intersect_leaf(const RayPre& r, float4 la, floa
     return t;
 }
 
-// hint the next node's line into L1 while the slab test of the current node is still in flight
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
 struct HitRec { float t, u, v; int prim; int mat; int leaf; };
+__device__ __forceinline__ void hit_reset(HitRec& h) { h.t = TR_INF; h.u = h.v = 0.0f; h.prim = -1; h.mat = 0; h.leaf = -1; }
 
-// next node of the walk. ORDERED (trees read from global memory): near child first on a box hit, octant escape link
-// (TrNodeX::next) otherwise = stackless front-to-back order, which halves the node visits on the 130 k-triangle scene.
-// Unordered (small trees staged in shared memory, where every box overlaps every ray and order buys nothing):
-// left child first, single escape link stored in the node.
-template <bool ORDERED>
-__device__ __forceinline__ int next_node(int idx, int link, bool hit, int esc, int oct) {
-    int first = idx + 1;
-    if (ORDERED) first = ((oct >> (link >> 29)) & 1) ? (link & 0x1fffffff) : idx + 1;
-    return (hit && link >= 0) ? first : esc;
-}
 // the reference pops the right child first and accepts strict t < best: among equal-t hits the LARGEST sorted leaf wins
 __device__ __forceinline__ bool closer(float t, int k, float best_t, int best_k) {
     return t > 0.0f && t < TR_INF && (t < best_t || (t == best_t && k > best_k));
 }
 
-#ifdef TR_COUNTERS
-#define TR_COUNT_NODE() (++cnt_nodes)
-#define TR_COUNT_LEAF() (++cnt_leaves)
-#else
-#define TR_COUNT_NODE()
-#define TR_COUNT_LEAF()
-#endif
+// ---- tree views ----------------------------------------------------------------------------------------------------------
+// How a kernel reads the tree (template parameter MODE of the traversal kernels):
+enum { TM_REP = 0,      // whole tree in shared memory as the 8-way replicated, bank-conflict-free image
+       TM_SMEM = 1,     // whole tree in shared memory, plain
+       TM_GLOBAL = 2,   // tree in global memory (L1 / L2)
+       TM_GTOP = 3 };   // global memory, the first `top` nodes (breadth-first top of the tree) staged in shared memory
 
-// Fast slab test for rays without a "parallel" axis (the common case): same arithmetic, no flags.
-__device__ __forceinline__ bool slabs_fast(const RayPre& r, float4 lo, float4 hi, float& tmin_out) {
-    float t1 = (lo.x - r.o.x) * r.ix, t2 = (hi.x - r.o.x) * r.ix;
-    float tmin = fmaxf(0.0f, fminf(t1, t2)), tmax = fminf(TR_INF, fmaxf(t1, t2));
-    t1 = (lo.y - r.o.y) * r.iy; t2 = (hi.y - r.o.y) * r.iy;
-    tmin = fmaxf(tmin, fminf(t1, t2)); tmax = fminf(tmax, fmaxf(t1, t2));
-    t1 = (lo.z - r.o.z) * r.iz; t2 = (hi.z - r.o.z) * r.iz;
-    tmin = fmaxf(tmin, fminf(t1, t2)); tmax = fminf(tmax, fmaxf(t1, t2));
-    tmin_out = tmin;
-    return !(tmin > tmax);
+struct TreeView {
+    const float4* snodes;    // shared-memory nodes (REP image / plain / staged top)
+    const float4* sleaves;   // shared-memory leaves (REP / SMEM)
+    const float4* gnodes;    // global TrNode2 array (4 float4 per node)
+    const float4* gleaves;   // global TrLeaf array (3 float4 per leaf)
+    int top;                 // TM_GTOP: nodes [0, top) are in snodes
+};
+
+template <int MODE>
+__device__ __forceinline__ void node_fetch(const TreeView& tv, int idx, int lane8, float4& A, float4& B, float4& C, float4& D) {
+    if (MODE == TM_REP) { const float4* p = tv.snodes + idx * 32 + lane8; A = p[0]; B = p[8]; C = p[16]; D = p[24]; }
+    else if (MODE == TM_SMEM) { const float4* p = tv.snodes + idx * 4; A = p[0]; B = p[1]; C = p[2]; D = p[3]; }
+    else if (MODE == TM_GLOBAL) { const float4* p = tv.gnodes + (size_t)idx * 4; A = __ldg(p); B = __ldg(p + 1); C = __ldg(p + 2); D = __ldg(p + 3); }
+    else { const float4* p = (idx < tv.top ? tv.snodes : tv.gnodes) + (size_t)idx * 4; A = p[0]; B = p[1]; C = p[2]; D = p[3]; }   // generic loads
+}
+template <int MODE>
+__device__ __forceinline__ void leaf_fetch(const TreeView& tv, int k, int lane8, float4& la, float4& lb, float4& lc) {
+    if (MODE == TM_REP) { const float4* p = tv.sleaves + k * 24 + lane8; la = p[0]; lb = p[8]; lc = p[16]; }
+    else if (MODE == TM_SMEM) { const float4* p = tv.sleaves + k * 3; la = p[0]; lb = p[1]; lc = p[2]; }
+    else { const float4* p = tv.gleaves + (size_t)k * 3; la = __ldg(p); lb = __ldg(p + 1); lc = __ldg(p + 2); }
 }
 
-// Warp-cooperative traversal schedule.
-// Every node visit is the same instruction stream for internal nodes and leaves: one slab test on the
-// node's box (leaf nodes carry their triangle's box, grown by a guard band at build time so that a
-// Moller-Trumbore hit can never be culled by it; the reference tests every leaf under a hit parent).  A lane
-// that reaches a leaf whose box is hit parks the leaf in `pend`; the Moller-Trumbore block then runs for the
-// parked lanes once per round of node steps.  TR_LEAF_BATCH > 1 would delay it until that many lanes are
-// parked; measured on B200 (sweep 1..24, one and two parked slots per lane): 1 is fastest on both scenes.
-// Hits are compared with closer(): the reference's tie rule made explicit, so the visiting order is free.
-#ifndef TR_LEAF_BATCH
-#define TR_LEAF_BATCH 1
+// ---- per-lane traversal stack -------------------------------------------------------------------------------------------
+// Entries [0, cap) live in shared memory at s[entry * stride] (s already points at this thread's column), the rest in a
+// per-thread local-memory array.  cap = min(stack entries the tree needs, TR_STACK_SMEM): the overflow region is reached only
+// by trees whose need exceeds TR_STACK_SMEM; the build guarantees need <= TR_STACK_MAX.
+struct LaneStack {
+    int* s; int stride, cap, sp;
+    int ovf[TR_STACK_MAX];
+    __device__ __forceinline__ void init(int* base, int stride_, int cap_) { s = base; stride = stride_; cap = cap_; sp = 0; }
+    __device__ __forceinline__ void push(int v) {
+        if (sp < cap) s[sp * stride] = v; else if (sp - cap < TR_STACK_MAX) ovf[sp - cap] = v;
+        ++sp;
+    }
+    __device__ __forceinline__ int pop() {
+        if (sp == 0) return TR_DONE;
+        --sp;
+        return sp < cap ? s[sp * stride] : (sp - cap < TR_STACK_MAX ? ovf[sp - cap] : TR_DONE);
+    }
+};
+
+#ifdef TR_COUNTERS
+#define TR_COUNT(x) (++(x))
+#else
+#define TR_COUNT(x)
 #endif
 
-// Closest hit (Scene.py:702-744 semantics).  nodes/leaves may point to shared or global memory.
-// Warp-synchronous: all 32 lanes must call it together; lanes without a ray pass active = false.
-template <bool SMEM>
-__device__ __forceinline__ HitRec trace_closest(const TrNode* __restrict__ nodes, const TrLeaf* __restrict__ leaves,
-                                                 const TrNodeX* __restrict__ nodesx, int nnodes,
-                                                 const RayPre& r, bool active, unsigned long long* cnt) {
-    HitRec h; h.t = TR_INF; h.u = 0.0f; h.v = 0.0f; h.prim = -1; h.mat = 0; h.leaf = -1;
+// link of the first node of a ray's walk: the root box is tested like the reference tests it at its first pop; a tree of
+// one primitive is a single leaf, which the reference intersects without any box test
+struct TreeRoot { float4 lo, hi; int link; };
+__device__ __forceinline__ int root_enter(const TreeRoot& rt, const RayPre& r, bool anypar) {
+    if (rt.link < 0) return rt.link;
+    float tmin;
+    return slab_any(r, anypar, rt.lo, rt.hi, tmin) ? rt.link : TR_DONE;
+}
+
+// One node step of a lane: fetch internal node `cur` (both child boxes), test them, choose the next link.
+//   link >= 0: internal node index; link < 0: leaf with sorted position -link-1; TR_DONE: walk finished.
+//   bound: best hit so far (closest hit) or the distance of the target (shadow query): children whose slab entry lies beyond
+//   bound x guard are pruned.  SHADOW: the target's own leaf (tlink) is never entered; reaching it sets `found`.
+// Order: a leaf child before an internal one (keeps the stack at one entry along chains), else the nearer slab entry first.
+template <int MODE, bool SHADOW>
+__device__ __forceinline__ int node_step(const TreeView& tv, const RayPre& r, bool anypar, float bound, int tlink, bool& found,
+                                         LaneStack& st, int cur, int lane8) {
+    float4 A, B, C, D;
+    node_fetch<MODE>(tv, cur, lane8, A, B, C, D);
+    const int l0 = __float_as_int(A.w), l1 = __float_as_int(B.w);
+    float t0, t1;
+    bool h0 = slab_any(r, anypar, A, B, t0) && !(t0 > bound * TR_PRUNE_GUARD);
+    bool h1 = slab_any(r, anypar, C, D, t1) && !(t1 > bound * TR_PRUNE_GUARD);
+    if (SHADOW) {
+        if (l0 == tlink) { found = true; h0 = false; }
+        if (l1 == tlink) { found = true; h1 = false; }
+    }
+    if (h0 && h1) {
+        const bool first1 = (l1 < 0 && l0 >= 0) || (((l0 < 0) == (l1 < 0)) && t1 < t0);
+        st.push(first1 ? l0 : l1);
+        return first1 ? l1 : l0;
+    }
+    return h0 ? l0 : (h1 ? l1 : st.pop());
+}
+
+// ---- simple (non-persistent) walks: Debug integrator, test hooks, lock-step BDPT cross-check -----------------------------
+// One lane = one ray from start to end; the stack is local memory only (cap 0).  Same node_step / closer as the persistent
+// kernels, global-memory tree.
+__device__ __forceinline__ HitRec trace_closest(const TreeView& tv, const TreeRoot& rt, const RayPre& r, bool active, unsigned long long* cnt) {
+    HitRec h; hit_reset(h);
 #ifdef TR_COUNTERS
     unsigned cnt_nodes = 0, cnt_leaves = 0;
 #endif
     const bool anypar = r.px || r.py || r.pz;
-    int idx = active ? 0 : nnodes, pend = -1;
-    while (true) {
-        if (pend < 0 && idx < nnodes) {
-            float4 lo, hi; int esc;
-            if (SMEM) { lo = nodes[idx].lo; hi = nodes[idx].hi; esc = __float_as_int(lo.w); }
-            else { lo = nodesx[idx].lo; hi = nodesx[idx].hi; esc = nodesx[idx].next[r.oct]; }
-            int link = __float_as_int(hi.w);
-            float tmin;
-            bool hit = (anypar ? slabs(r, lo, hi, tmin) : slabs_fast(r, lo, hi, tmin)) && !(tmin > h.t * TR_PRUNE_GUARD);
-            if (link < 0) { if (hit) pend = -link - 1; } else { TR_COUNT_NODE(); }
-            idx = next_node<!SMEM>(idx, link, hit, esc, r.oct);
-        }
-        const unsigned parked = __ballot_sync(0xffffffffu, pend >= 0);
-        const unsigned walking = __ballot_sync(0xffffffffu, pend < 0 && idx < nnodes);
-        if (parked == 0u && walking == 0u) break;
-        if (__popc(parked) >= TR_LEAF_BATCH || walking == 0u) {
-            if (pend >= 0) {
-                TR_COUNT_LEAF();
-                const TrLeaf* lf = leaves + pend;
-                float4 la = lf->a, lb = lf->b, lc = lf->c;
-                float u, v, t = intersect_leaf(r, la, lb, lc, u, v);
-                if (closer(t, pend, h.t, h.leaf)) { h.t = t; h.u = u; h.v = v; h.prim = __float_as_int(la.w); h.mat = __float_as_int(lc.w); h.leaf = pend; }
-                pend = -1;
-            }
+    LaneStack st; st.init(nullptr, 0, 0);
+    bool found = false;
+    int cur = active ? root_enter(rt, r, anypar) : TR_DONE;
+    while (cur != TR_DONE) {
+        if (cur >= 0) { TR_COUNT(cnt_nodes); cur = node_step<TM_GLOBAL, false>(tv, r, anypar, h.t, 0, found, st, cur, 0); }
+        else {
+            TR_COUNT(cnt_leaves);
+            const int k = -cur - 1;
+            float4 la, lb, lc; leaf_fetch<TM_GLOBAL>(tv, k, 0, la, lb, lc);
+            float u, v, t = intersect_leaf(r, la, lb, lc, u, v);
+            if (closer(t, k, h.t, h.leaf)) { h.t = t; h.u = u; h.v = v; h.prim = __float_as_int(la.w); h.mat = __float_as_int(lc.w); h.leaf = k; }
+            cur = st.pop();
         }
     }
 #ifdef TR_COUNTERS
-    if (cnt && active) { atomicAdd(cnt, (unsigned long long)cnt_nodes); atomicAdd(cnt + 1, (unsigned long long)cnt_leaves); }
+    if (cnt && active) { atomicAdd(cnt, 2ull * cnt_nodes); atomicAdd(cnt + 1, (unsigned long long)cnt_leaves); }     // 2 boxes (2 x 32 B) per node visit
 #endif
     return h;
 }
 
-// Shadow query.  The reference (integrator/PT_RGB.py:104-105, Scene.py:671-699) finds the nearest
-// hit of the light->surface ray and tests `shadow_prim == prim_id`.  Equivalent early-exit form:
-// intersect the target primitive first (t_t), then walk the tree (bounded by t_t) looking for ANY other
-// primitive that would have won the reference's comparison (t < t_t, or t == t_t at a later leaf
-// position); the target only counts if the walk reaches its leaf (every ancestor passes the slab test).
-// Warp-synchronous like trace_closest.
-template <bool SMEM>
-__device__ __forceinline__ bool trace_shadow_visible(const TrNode* __restrict__ nodes, const TrLeaf* __restrict__ leaves,
-                                                     const TrNodeX* __restrict__ nodesx, int nnodes,
-                                                     const RayPre& r, bool active, int target_leaf, unsigned long long* cnt,
-                                                     float* tt_out = nullptr) {
+// Shadow query.  The reference (integrator/PT_RGB.py:104-105, Scene.py:671-699) finds the nearest hit of the light->surface
+// ray and tests `shadow_prim == prim_id`.  Equivalent early-exit form: intersect the target primitive first (t_t), then walk
+// the tree (bounded by t_t) looking for ANY other primitive that would have won the reference's comparison (t < t_t, or
+// t == t_t at a later leaf position); the target only counts if the walk reaches its leaf (every ancestor passes the slab test).
+__device__ __forceinline__ bool blocks_target(float t, int k, float tt, int tleaf) {
+    return t > 0.0f && t < TR_INF && (t < tt || (t == tt && k > tleaf));
+}
+// start of a shadow walk: distance of the target, visibility so far, first link
+__device__ __forceinline__ int shadow_enter(const TreeView& tv, const TreeRoot& rt, const RayPre& r, bool anypar, int tleaf,
+                                            float4 la, float4 lb, float4 lc, float& tt, bool& visible, bool& found) {
+    float u, v; tt = intersect_leaf(r, la, lb, lc, u, v);
+    visible = (tt > 0.0f && tt < TR_INF); found = false;
+    if (!visible) return TR_DONE;
+    int cur = root_enter(rt, r, anypar);
+    if (cur == -tleaf - 1) { found = true; cur = TR_DONE; }          // single-leaf tree: the root is the target
+    return cur;
+}
+__device__ __forceinline__ bool trace_shadow_visible(const TreeView& tv, const TreeRoot& rt, const RayPre& r, bool active, int target_leaf,
+                                                     unsigned long long* cnt, float* tt_out = nullptr) {
 #ifdef TR_COUNTERS
     unsigned cnt_nodes = 0, cnt_leaves = 0;
 #endif
-    bool visible = false, found = false;
-    float tt = TR_INF;
-    if (active) {
-        const TrLeaf* lf = leaves + target_leaf;
-        float u, v; tt = intersect_leaf(r, lf->a, lf->b, lf->c, u, v);
-        TR_COUNT_LEAF();
-        visible = (tt > 0.0f && tt < TR_INF);
-    }
     const bool anypar = r.px || r.py || r.pz;
-    int idx = visible ? 0 : nnodes, pend = -1;
-    while (true) {
-        if (pend < 0 && idx < nnodes) {
-            float4 lo, hi; int esc;
-            if (SMEM) { lo = nodes[idx].lo; hi = nodes[idx].hi; esc = __float_as_int(lo.w); }
-            else { lo = nodesx[idx].lo; hi = nodesx[idx].hi; esc = nodesx[idx].next[r.oct]; }
-            int link = __float_as_int(hi.w);
-            float tmin;
-            bool hit = (anypar ? slabs(r, lo, hi, tmin) : slabs_fast(r, lo, hi, tmin)) && !(tmin > tt * TR_PRUNE_GUARD);
-            if (link < 0) {
-                int k = -link - 1;
-                if (k == target_leaf) found = true; else if (hit) pend = k;
-            } else { TR_COUNT_NODE(); }
-            idx = next_node<!SMEM>(idx, link, hit, esc, r.oct);
-        }
-        const unsigned parked = __ballot_sync(0xffffffffu, pend >= 0);
-        const unsigned walking = __ballot_sync(0xffffffffu, pend < 0 && idx < nnodes);
-        if (parked == 0u && walking == 0u) break;
-        if (__popc(parked) >= TR_LEAF_BATCH || walking == 0u) {
-            if (pend >= 0) {
-                TR_COUNT_LEAF();
-                const TrLeaf* l2 = leaves + pend;
-                float u, v, t = intersect_leaf(r, l2->a, l2->b, l2->c, u, v);
-                if (t > 0.0f && t < TR_INF && (t < tt || (t == tt && pend > target_leaf))) { visible = false; idx = nnodes; }
-                pend = -1;
-            }
+    bool visible = false, found = false; float tt = TR_INF;
+    LaneStack st; st.init(nullptr, 0, 0);
+    int cur = TR_DONE;
+    const int tlink = -target_leaf - 1;
+    if (active) {
+        float4 la, lb, lc; leaf_fetch<TM_GLOBAL>(tv, target_leaf, 0, la, lb, lc);
+        TR_COUNT(cnt_leaves);
+        cur = shadow_enter(tv, rt, r, anypar, target_leaf, la, lb, lc, tt, visible, found);
+    }
+    while (cur != TR_DONE) {
+        if (cur >= 0) { TR_COUNT(cnt_nodes); cur = node_step<TM_GLOBAL, true>(tv, r, anypar, tt, tlink, found, st, cur, 0); }
+        else {
+            TR_COUNT(cnt_leaves);
+            const int k = -cur - 1;
+            float4 la, lb, lc; leaf_fetch<TM_GLOBAL>(tv, k, 0, la, lb, lc);
+            float u, v, t = intersect_leaf(r, la, lb, lc, u, v);
+            if (blocks_target(t, k, tt, target_leaf)) { visible = false; cur = TR_DONE; } else cur = st.pop();
         }
     }
 #ifdef TR_COUNTERS
-    if (cnt && active) { atomicAdd(cnt, (unsigned long long)cnt_nodes); atomicAdd(cnt + 1, (unsigned long long)cnt_leaves); }
+    if (cnt && active) { atomicAdd(cnt, 2ull * cnt_nodes); atomicAdd(cnt + 1, (unsigned long long)cnt_leaves); }
 #endif
     if (tt_out) *tt_out = tt;          // distance to the target primitive = the reference's hit_t when the target is the nearest hit
     return visible && found;
 }
 
-// ---- TMA bulk staging of the whole BVH into shared memory (small scenes, e.g. the Cornell box)
+// ---- TMA bulk staging into shared memory --------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-// One thread issues cp.async.bulk (global -> shared, mbarrier completion); everybody waits.
-// bytes must be a multiple of 16 and both pointers 16-byte aligned.
-__device__ __forceinline__ void tma_stage_to_smem(void* smem_dst, const void* gsrc, unsigned bytes, void* smem_dst2,
-                                                  const void* gsrc2, unsigned bytes2, unsigned long long* bar) {
+// One thread issues up to two cp.async.bulk (global -> shared, mbarrier completion); tma_stage_wait() makes everybody wait.
+// bytes must be multiples of 16 and all pointers 16-byte aligned.
+__device__ __forceinline__ void tma_stage_issue(void* smem_dst, const void* gsrc, unsigned bytes, void* smem_dst2,
+                                                const void* gsrc2, unsigned bytes2, unsigned long long* bar) {
     const unsigned bar_a = smem_u32(bar);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes + bytes2) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(bar_a) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(smem_dst2)), "l"(gsrc2), "r"(bytes2), "r"(bar_a) : "memory");
+        if (bytes2)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(smem_dst2)), "l"(gsrc2), "r"(bytes2), "r"(bar_a) : "memory");
     }
-    // wait for phase 0
+}
+__device__ __forceinline__ void tma_stage_wait(unsigned long long* bar) {
+    __syncthreads();                    // the barrier was initialised by thread 0
+    const unsigned bar_a = smem_u32(bar);
     asm volatile(
         "{\n"
         ".reg .pred p;\n"

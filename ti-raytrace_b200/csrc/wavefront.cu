@@ -24,7 +24,10 @@ struct BatchParams { int frame_begin; int n_frames; unsigned long long seed; int
 
 struct WfArgs {
     // scene
-    const TrNode* nodes; const TrLeaf* leaves; const TrNodeX* nodesx; int nnodes; int nleaves;
+    const float4* nodes2; const float4* leaves4; const float4* small_img;   // TrNode2 array, TrLeaf array, replicated image of a small tree
+    int nint, nleaves, top, stack_cap;             // internal nodes, leaves, staged top nodes (TM_GTOP), stack entries kept in shared memory
+    TreeRoot root;                                 // root box + link (0: internal root, -1: the tree is a single leaf)
+    unsigned stage_bytes;                          // bytes of shared memory in front of the stack (tree image / top nodes), multiple of 128
     const TrShade* shade; const float* material; const float4* matlin; const int* light; int nl; const int* leaf_of_prim;
     const int* env; int env_w, env_h; float env_power;
     TrCamera cam;
@@ -43,7 +46,7 @@ struct WfArgs {
     int tail_max;                                  // hand the chain to k_tail once its live paths drop to this (0 = never)
     int tail_chunk;                                // k_tail: at least this many paths per warp
     int frame_off, sub_frames;                     // this chain renders local frames [frame_off, frame_off + sub_frames) of the batch
-    unsigned smem_nodes_bytes, smem_leaves_bytes, smem_next_bytes;
+    int probe;                                     // test hooks: k_tail records the hit of each path's first walk in hit[] and stops there
     SpecDev spec;                                  // tables of the spectral integrator (PT_Spec), zero for PT_RGB
 };
 
@@ -165,17 +168,31 @@ __global__ void __launch_bounds__(WF_THREADS) k_generate(WfArgs a) {
 }
 
 // ------------------------------------------------------------------ BVH staging
+// Dynamic shared memory of the traversal kernels: [tree image (stage_bytes)] [stack: stack_cap x WF_THREADS ints].
 extern __shared__ __align__(128) unsigned char wf_smem[];
 
-template <bool SMEM>
-__device__ __forceinline__ void bvh_view(const WfArgs& a, const TrNode*& nodes, const TrLeaf*& leaves, const TrNodeX*& nodesx) {
-    if (SMEM) {
-        __shared__ unsigned long long bar;
-        TrNode* sn = (TrNode*)wf_smem; TrLeaf* sl = (TrLeaf*)(wf_smem + a.smem_nodes_bytes);
-        tma_stage_to_smem(sn, a.nodes, a.smem_nodes_bytes, sl, a.leaves, a.smem_leaves_bytes, &bar);
-        nodes = sn; leaves = sl; nodesx = nullptr;      // small trees: single-link (left-first) threading, see next_node
-    } else { nodes = a.nodes; leaves = a.leaves; nodesx = a.nodesx; }
+// Thread 0 issues the TMA bulk copies of the part of the tree this MODE keeps in shared memory (nothing for TM_GLOBAL).
+// The tree is static for the whole batch, so this may run before griddepcontrol.wait (programmatic dependent launch).
+template <int MODE>
+__device__ __forceinline__ void tree_stage_issue(const WfArgs& a, unsigned long long* bar) {
+    if (MODE == TM_REP) tma_stage_issue(wf_smem, a.small_img, a.stage_bytes, nullptr, nullptr, 0u, bar);
+    else if (MODE == TM_SMEM) {
+        const unsigned nb = (unsigned)a.nint * 64u;
+        tma_stage_issue(wf_smem, a.nodes2, nb, wf_smem + nb, a.leaves4, (unsigned)a.nleaves * 48u, bar);
+    } else if (MODE == TM_GTOP) tma_stage_issue(wf_smem, a.nodes2, (unsigned)a.top * 64u, nullptr, nullptr, 0u, bar);
 }
+template <int MODE>
+__device__ __forceinline__ void tree_stage_wait(const WfArgs& a, unsigned long long* bar, TreeView& tv, int*& stack_base) {
+    if (MODE != TM_GLOBAL) tma_stage_wait(bar);
+    const float4* sm = (const float4*)wf_smem;
+    tv.gnodes = a.nodes2; tv.gleaves = a.leaves4; tv.top = a.top; tv.snodes = sm;
+    tv.sleaves = (MODE == TM_REP) ? sm + (size_t)a.nint * 32 : sm + (size_t)a.nint * 4;
+    stack_base = (int*)(wf_smem + a.stage_bytes) + threadIdx.x;
+}
+// programmatic dependent launch: everything above this call overlaps the previous kernel of the stream; nothing the previous
+// kernel wrote (queues, counters) may be read before it.  A no-op for kernels launched without the attribute.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ------------------------------------------------------------------ trace (closest hit)
 // Persistent warps with per-lane ray replacement: a warp takes WF_CHUNK consecutive rays of the queue with
@@ -195,7 +212,8 @@ struct WarpFeed { int cb, ce, chunk; bool more; };
 // warp gets work when the queue is short (deep bounces) and that the end-of-kernel tail stays short
 __device__ __forceinline__ WarpFeed make_feed(int n) {
     WarpFeed f; f.cb = f.ce = 0; f.more = true;
-    int warps = gridDim.x * (blockDim.x >> 5);
+    int blocks = min((int)gridDim.x, (n + WF_THREADS - 1) / WF_THREADS);       // surplus CTAs have left (see k_trace)
+    int warps = max(1, blocks) * (blockDim.x >> 5);
     int c = n / (warps * 8);
     f.chunk = min(256, max(32, (c + 31) & ~31));
     return f;
@@ -243,24 +261,30 @@ __device__ __forceinline__ void flush_retired(const WfArgs& a, int depth, const 
     __syncwarp();
 }
 
-template <bool SMEM>
+template <int MODE>
 __global__ void __launch_bounds__(WF_THREADS) k_trace(WfArgs a, int depth) {
+    grid_dep_wait();
     if (tail_took_over(a, depth)) return;
-    const TrNode* nodes; const TrLeaf* leaves; const TrNodeX* nodesx;
-    bvh_view<SMEM>(a, nodes, leaves, nodesx);
+    // surplus CTAs of a short queue leave BEFORE staging the tree (deep bounces, small shards: the per-stage floor)
+    const int n = a.ctr->nq[depth];
+    if ((long long)blockIdx.x * WF_THREADS >= (long long)n) return;
+    __shared__ unsigned long long bar;
+    TreeView tv; int* stack_base;
+    tree_stage_issue<MODE>(a, &bar);
+    tree_stage_wait<MODE>(a, &bar, tv, stack_base);
     __shared__ int retire_buf[WF_THREADS / 32][64];      // finished (queue index | class << 30), flushed 32 at a time
-    const int n = a.ctr->nq[depth], nnodes = a.nnodes;
     const int pp = depth & 1;
     const float4* __restrict__ pa = a.pa[pp]; const float4* __restrict__ pb = a.pb[pp];
     int* cursor = &a.ctr->wf_trace[depth];
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, lane8 = lane & 7;
     int* rbuf = retire_buf[threadIdx.x >> 5];
     int rcount = 0;
     WarpFeed feed = make_feed(n);
     unsigned idle = 0xffffffffu;                        // warp-uniform: lanes without a ray
-    bool anypar = false; int q = 0, idx = nnodes, pend = -1;
+    bool anypar = false, found = false; int q = 0, cur = TR_DONE;
+    LaneStack st; st.init(stack_base, WF_THREADS, a.stack_cap);
     RayPre r = make_ray(mk3(0.f, 0.f, 0.f), mk3(1.f, 1.f, 1.f));
-    HitRec h; h.t = TR_INF; h.u = h.v = 0.0f; h.prim = -1; h.mat = 0; h.leaf = -1;
+    HitRec h; hit_reset(h);
 #ifdef TR_COUNTERS
     unsigned long long cnt_nodes = 0, cnt_leaves = 0;
 #endif
@@ -272,50 +296,31 @@ __global__ void __launch_bounds__(WF_THREADS) k_trace(WfArgs a, int depth) {
                 float4 A = pa[nq], B = pb[nq];
                 r = make_ray(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y));
                 anypar = r.px || r.py || r.pz;
-                h.t = TR_INF; h.u = h.v = 0.0f; h.prim = -1; h.mat = 0; h.leaf = -1;
-                q = nq; idx = 0; pend = -1;
+                hit_reset(h);
+                q = nq; st.sp = 0; cur = root_enter(a.root, r, anypar);
             }
         }
         if (idle == 0xffffffffu) { if (!feed.more && feed.cb >= feed.ce) break; else continue; }
         const bool has = !((idle >> lane) & 1u);
-        // ---- WF_NODE_STEPS node steps per round (same code for internal nodes and leaves); the warp-level
-        //      bookkeeping below is paid once per round
+        // ---- WF_NODE_STEPS node steps per round; the warp-level bookkeeping below is paid once per round
 #pragma unroll
         for (int step = 0; step < WF_NODE_STEPS; ++step) {
-            if (has && pend < 0 && idx < nnodes) {
-                float4 lo, hi; int esc;
-                if (SMEM) { lo = nodes[idx].lo; hi = nodes[idx].hi; esc = __float_as_int(lo.w); }
-                else { const TrNodeX* nd = nodesx + idx; lo = nd->lo; hi = nd->hi; esc = nd->next[r.oct]; }
-                int link = __float_as_int(hi.w);
-#ifdef WF_PREFETCH
-                if (!SMEM && link >= 0) prefetch_l1(nodesx + (link & 0x1fffffff));      // right child (the left one shares this line or the next)
-#endif
-                float tmin;
-                bool hit = (anypar ? slabs(r, lo, hi, tmin) : slabs_fast(r, lo, hi, tmin)) && !(tmin > h.t * TR_PRUNE_GUARD);
-                if (link < 0) { if (hit) pend = -link - 1; }
-#ifdef TR_COUNTERS
-                else ++cnt_nodes;
-#endif
-                idx = next_node<!SMEM>(idx, link, hit, esc, r.oct);
+            if (has && (unsigned)cur < (unsigned)TR_DONE) {
+                TR_COUNT(cnt_nodes);
+                cur = node_step<MODE, false>(tv, r, anypar, h.t, 0, found, st, cur, lane8);
             }
         }
-        // ---- batched leaf step
-        const unsigned parked = __ballot_sync(0xffffffffu, has && pend >= 0);
-        const unsigned finm = __ballot_sync(0xffffffffu, has && pend < 0 && idx >= nnodes);
-        const unsigned walking = ~idle & ~parked & ~finm;
-        if (__popc(parked) >= TR_LEAF_BATCH || (walking == 0u && parked != 0u)) {
-            if (has && pend >= 0) {
-#ifdef TR_COUNTERS
-                ++cnt_leaves;
-#endif
-                const TrLeaf* lf = leaves + pend;
-                float4 la = lf->a, lb = lf->b, lc = lf->c;
-                float u, v, t = intersect_leaf(r, la, lb, lc, u, v);
-                if (closer(t, pend, h.t, h.leaf)) { h.t = t; h.u = u; h.v = v; h.prim = __float_as_int(la.w); h.mat = __float_as_int(lc.w); h.leaf = pend; }
-                pend = -1;
-            }
+        // ---- leaf step of the lanes parked at a leaf
+        if (has && cur < 0) {
+            TR_COUNT(cnt_leaves);
+            const int k = -cur - 1;
+            float4 la, lb, lc; leaf_fetch<MODE>(tv, k, lane8, la, lb, lc);
+            float u, v, t = intersect_leaf(r, la, lb, lc, u, v);
+            if (closer(t, k, h.t, h.leaf)) { h.t = t; h.u = u; h.v = v; h.prim = __float_as_int(la.w); h.mat = __float_as_int(lc.w); h.leaf = k; }
+            cur = st.pop();
         }
         // ---- retire finished rays: hit record now, material-sorted queue entries through the warp's buffer
+        const unsigned finm = __ballot_sync(0xffffffffu, has && cur == TR_DONE);
         if (finm != 0u) {
             if ((finm >> lane) & 1u) {
                 a.hit[q] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
@@ -334,7 +339,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_trace(WfArgs a, int depth) {
     }
     if (rcount > 0) flush_retired(a, depth, rbuf, rcount, rcount, lane);
 #ifdef TR_COUNTERS
-    atomicAdd(a.ctr->visits, cnt_nodes); atomicAdd(a.ctr->visits + 1, cnt_leaves);
+    atomicAdd(a.ctr->visits, 2ull * cnt_nodes); atomicAdd(a.ctr->visits + 1, cnt_leaves);      // 2 child boxes (2 x 32 B) per node visit
 #endif
 }
 
@@ -636,14 +641,17 @@ __global__ void __launch_bounds__(WF_THREADS, SPEC ? 3 : WF_SHADE_MIN_BLOCKS) k_
 // (n / #warps) so that all resident warps work.  Same device functions and the same per-path operation order as the
 // wavefront stages (NEE terms are added to Lnee in depth order, after shadow(depth-1): the kernel is enqueued behind it),
 // so the film is bit-identical with or without the hand-over.
-template <bool SMEM, bool SPEC>
+template <int MODE, bool SPEC>
 __global__ void __launch_bounds__(WF_THREADS) k_tail(WfArgs a, int depth) {
+    grid_dep_wait();
     if (a.ctr->tail_from != depth) return;
-    const TrNode* nodes; const TrLeaf* leaves; const TrNodeX* nodesx;
-    bvh_view<SMEM>(a, nodes, leaves, nodesx);
+    __shared__ unsigned long long bar;
+    TreeView tv; int* stack_base;
+    tree_stage_issue<MODE>(a, &bar);
+    tree_stage_wait<MODE>(a, &bar, tv, stack_base);
     const BatchParams bp = *a.bp;
-    const int n = a.ctr->nq[depth], pp = depth & 1, nnodes = a.nnodes;
-    const int lane = threadIdx.x & 31;
+    const int n = a.ctr->nq[depth], pp = depth & 1;
+    const int lane = threadIdx.x & 31, lane8 = lane & 7;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int chunk = min(32, max(a.tail_chunk, (n + nwarps - 1) / nwarps));
     int* cursor = &a.ctr->wf_trace[TR_MAX_DEPTH_CAP];                  // free slot: stage cursors use [0, max_depth)
@@ -651,12 +659,13 @@ __global__ void __launch_bounds__(WF_THREADS) k_tail(WfArgs a, int depth) {
 #ifdef TR_COUNTERS
     unsigned long long cnt[4] = {0, 0, 0, 0};
 #endif
-    int mode = 0, d = depth;                                           // 0 idle, 1 closest-hit walk, 2 shadow walk
+    int mode = 0, d = depth, q = 0;                                    // 0 idle, 1 closest-hit walk, 2 shadow walk
     float4 A = make_float4(0.f, 0.f, 0.f, 1.f), B = make_float4(1.f, 1.f, 1.f, 0.f), C = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 nA = A, nB = B, nC = C, sC = C; bool st_cont = false; unsigned sslot = 0;
     RayPre r = make_ray(mk3(0.f, 0.f, 0.f), mk3(1.f, 1.f, 1.f)); bool anypar = false;
-    int idx = nnodes, pend = -1, tleaf = 0; bool visible = false, found = false; float tt = TR_INF;
-    HitRec h; h.t = TR_INF; h.u = h.v = 0.0f; h.prim = -1; h.mat = 0; h.leaf = -1;
+    int cur = TR_DONE, tleaf = 0; bool visible = false, found = false; float tt = TR_INF;
+    LaneStack st; st.init(stack_base, WF_THREADS, a.stack_cap);
+    HitRec h; hit_reset(h);
     bool more = true;
     while (true) {
         if (__ballot_sync(0xffffffffu, mode != 0) == 0u) {
@@ -666,51 +675,42 @@ __global__ void __launch_bounds__(WF_THREADS) k_tail(WfArgs a, int depth) {
             base = __shfl_sync(0xffffffffu, base, 0);
             if (base >= n) break;
             if (base + chunk >= n) more = false;
-            const int q = base + lane;
+            q = base + lane;
             if (lane < chunk && q < n) {
                 A = a.pa[pp][q]; B = a.pb[pp][q]; C = a.pc[pp][q]; d = depth; mode = 1;
                 r = make_ray(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y)); anypar = r.px || r.py || r.pz;
-                h.t = TR_INF; h.u = h.v = 0.0f; h.prim = -1; h.mat = 0; h.leaf = -1; idx = 0; pend = -1;
+                hit_reset(h); st.sp = 0; cur = root_enter(a.root, r, anypar);
             }
         }
-        // ---- node steps (same code for internal nodes and leaves, as in k_trace / k_shadow)
+        // ---- node steps (same code as in k_trace / k_shadow; the mode only selects the pruning bound and the target)
 #pragma unroll
         for (int step = 0; step < WF_NODE_STEPS; ++step) {
-            if (mode != 0 && pend < 0 && idx < nnodes) {
-                float4 lo, hi; int esc;
-                if (SMEM) { lo = nodes[idx].lo; hi = nodes[idx].hi; esc = __float_as_int(lo.w); }
-                else { const TrNodeX* nd = nodesx + idx; lo = nd->lo; hi = nd->hi; esc = nd->next[r.oct]; }
-                const int link = __float_as_int(hi.w);
-                const float bound = (mode == 1) ? h.t : tt;
-                float tmin;
-                const bool hit = (anypar ? slabs(r, lo, hi, tmin) : slabs_fast(r, lo, hi, tmin)) && !(tmin > bound * TR_PRUNE_GUARD);
-                if (link < 0) {
-                    const int k = -link - 1;
-                    if (mode == 2 && k == tleaf) found = true; else if (hit) pend = k;
-                }
+            if (mode != 0 && (unsigned)cur < (unsigned)TR_DONE) {
 #ifdef TR_COUNTERS
-                else ++cnt[mode == 1 ? 0 : 2];
+                ++cnt[mode == 1 ? 0 : 2];
 #endif
-                idx = next_node<!SMEM>(idx, link, hit, esc, r.oct);
+                if (mode == 1) cur = node_step<MODE, false>(tv, r, anypar, h.t, 0, found, st, cur, lane8);
+                else cur = node_step<MODE, true>(tv, r, anypar, tt, -tleaf - 1, found, st, cur, lane8);
             }
         }
         // ---- leaf step
-        if (mode != 0 && pend >= 0) {
-            const TrLeaf* lf = leaves + pend;
-            float4 la = lf->a, lb = lf->b, lc = lf->c;
+        if (mode != 0 && cur < 0) {
+            const int k = -cur - 1;
+            float4 la, lb, lc; leaf_fetch<MODE>(tv, k, lane8, la, lb, lc);
             float u, v, t = intersect_leaf(r, la, lb, lc, u, v);
 #ifdef TR_COUNTERS
             ++cnt[mode == 1 ? 1 : 3];
 #endif
-            if (mode == 1) { if (closer(t, pend, h.t, h.leaf)) { h.t = t; h.u = u; h.v = v; h.prim = __float_as_int(la.w); h.mat = __float_as_int(lc.w); h.leaf = pend; } }
-            else if (t > 0.0f && t < TR_INF && (t < tt || (t == tt && pend > tleaf))) { visible = false; idx = nnodes; }
-            pend = -1;
+            cur = st.pop();
+            if (mode == 1) { if (closer(t, k, h.t, h.leaf)) { h.t = t; h.u = u; h.v = v; h.prim = __float_as_int(la.w); h.mat = __float_as_int(lc.w); h.leaf = k; } }
+            else if (blocks_target(t, k, tt, tleaf)) { visible = false; cur = TR_DONE; }
         }
         // ---- a finished walk: shade / add the NEE term, then start the lane's next walk
-        if (mode != 0 && pend < 0 && idx >= nnodes) {
+        if (mode != 0 && cur == TR_DONE) {
             bool advance = true;
             if (mode == 1) {
                 ++n_closest;
+                if (a.probe) { a.hit[q] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v); mode = 0; continue; }      // test hook: the first walk only
                 int cl = 0;
                 if (h.prim >= 0) {
                     int mt = (int)__ldg(a.material + (size_t)h.mat * 10);
@@ -723,13 +723,12 @@ __global__ void __launch_bounds__(WF_THREADS) k_tail(WfArgs a, int depth) {
                     ++n_shadow;
                     r = make_ray(mk3(o.sA.x, o.sA.y, o.sA.z), mk3(o.sA.w, o.sB.x, o.sB.y)); anypar = r.px || r.py || r.pz;
                     tleaf = __ldg(a.leaf_of_prim + __float_as_int(o.sB.z)); sslot = __float_as_uint(o.sB.w); sC = o.sC;
-                    const TrLeaf* lf = leaves + tleaf;
-                    float u, v; tt = intersect_leaf(r, lf->a, lf->b, lf->c, u, v);
+                    float4 la, lb, lc; leaf_fetch<MODE>(tv, tleaf, lane8, la, lb, lc);
 #ifdef TR_COUNTERS
                     ++cnt[3];
 #endif
-                    visible = (tt > 0.0f && tt < TR_INF); found = false;
-                    idx = visible ? 0 : nnodes; pend = -1; mode = 2; advance = false;
+                    st.sp = 0; cur = shadow_enter(tv, a.root, r, anypar, tleaf, la, lb, lc, tt, visible, found);
+                    mode = 2; advance = false;
                 }
             } else if (visible && found) {
                 float4 Lv = a.Lnee[sslot]; Lv.x += sC.x; Lv.y += sC.y; Lv.z += sC.z; Lv.w += sC.w; a.Lnee[sslot] = Lv;
@@ -738,7 +737,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_tail(WfArgs a, int depth) {
                 if (st_cont) {
                     A = nA; B = nB; C = nC; ++d; mode = 1; st_cont = false;
                     r = make_ray(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y)); anypar = r.px || r.py || r.pz;
-                    h.t = TR_INF; h.u = h.v = 0.0f; h.prim = -1; h.mat = 0; h.leaf = -1; idx = 0; pend = -1;
+                    hit_reset(h); st.sp = 0; cur = root_enter(a.root, r, anypar);
                 } else mode = 0;
             }
         }
@@ -746,7 +745,8 @@ __global__ void __launch_bounds__(WF_THREADS) k_tail(WfArgs a, int depth) {
     if (n_closest) atomicAdd(&a.ctr->tail_rays[0], n_closest);
     if (n_shadow) atomicAdd(&a.ctr->tail_rays[1], n_shadow);
 #ifdef TR_COUNTERS
-    for (int k = 0; k < 4; ++k) if (cnt[k]) atomicAdd(a.ctr->visits + k, cnt[k]);
+    atomicAdd(a.ctr->visits + 0, 2ull * cnt[0]); atomicAdd(a.ctr->visits + 1, cnt[1]);
+    atomicAdd(a.ctr->visits + 2, 2ull * cnt[2]); atomicAdd(a.ctr->visits + 3, cnt[3]);
 #endif
 }
 
@@ -755,18 +755,23 @@ __global__ void __launch_bounds__(WF_THREADS) k_tail(WfArgs a, int depth) {
 // primitive that would have won the reference's nearest-hit comparison (see trace_shadow_visible).
 // QUERY (BDPT connections): instead of adding a contribution, report per queue item (sb.w) the distance to the target when it is
 // the nearest hit, -1 otherwise.
-template <bool SMEM, bool QUERY = false>
+template <int MODE, bool QUERY = false>
 __global__ void __launch_bounds__(WF_THREADS) k_shadow(WfArgs a, int depth) {
+    grid_dep_wait();
     if (tail_took_over(a, depth)) return;
-    const TrNode* nodes; const TrLeaf* leaves; const TrNodeX* nodesx;
-    bvh_view<SMEM>(a, nodes, leaves, nodesx);
-    const int n = a.ctr->nshadow[depth], nnodes = a.nnodes;
+    const int n = a.ctr->nshadow[depth];
+    if ((long long)blockIdx.x * WF_THREADS >= (long long)n) return;          // surplus CTAs leave before staging the tree
+    __shared__ unsigned long long bar;
+    TreeView tv; int* stack_base;
+    tree_stage_issue<MODE>(a, &bar);
+    tree_stage_wait<MODE>(a, &bar, tv, stack_base);
     int* cursor = &a.ctr->wf_shadow[depth];
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, lane8 = lane & 7;
     WarpFeed feed = make_feed(n);
     unsigned idle = 0xffffffffu;
-    bool anypar = false, visible = false, found = false; int q = 0, idx = nnodes, pend = -1, tleaf = 0;
+    bool anypar = false, visible = false, found = false; int q = 0, cur = TR_DONE, tleaf = 0;
     float tt = TR_INF; unsigned slot = 0;
+    LaneStack st; st.init(stack_base, WF_THREADS, a.stack_cap);
     RayPre r = make_ray(mk3(0.f, 0.f, 0.f), mk3(1.f, 1.f, 1.f));
 #ifdef TR_COUNTERS
     unsigned long long cnt_nodes = 0, cnt_leaves = 0;
@@ -779,50 +784,29 @@ __global__ void __launch_bounds__(WF_THREADS) k_shadow(WfArgs a, int depth) {
                 r = make_ray(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y));
                 anypar = r.px || r.py || r.pz;
                 tleaf = __ldg(a.leaf_of_prim + __float_as_int(B.z)); slot = __float_as_uint(B.w);
-                const TrLeaf* lf = leaves + tleaf;
-                float u, v; tt = intersect_leaf(r, lf->a, lf->b, lf->c, u, v);
-#ifdef TR_COUNTERS
-                ++cnt_leaves;
-#endif
-                visible = (tt > 0.0f && tt < TR_INF); found = false;
-                q = nq; idx = visible ? 0 : nnodes; pend = -1;
+                float4 la, lb, lc; leaf_fetch<MODE>(tv, tleaf, lane8, la, lb, lc);
+                TR_COUNT(cnt_leaves);
+                q = nq; st.sp = 0; cur = shadow_enter(tv, a.root, r, anypar, tleaf, la, lb, lc, tt, visible, found);
             }
         }
         if (idle == 0xffffffffu) { if (!feed.more && feed.cb >= feed.ce) break; else continue; }
         const bool has = !((idle >> lane) & 1u);
+        const int tlink = -tleaf - 1;
 #pragma unroll
         for (int step = 0; step < WF_NODE_STEPS; ++step) {
-            if (has && pend < 0 && idx < nnodes) {
-                float4 lo, hi; int esc;
-                if (SMEM) { lo = nodes[idx].lo; hi = nodes[idx].hi; esc = __float_as_int(lo.w); }
-                else { const TrNodeX* nd = nodesx + idx; lo = nd->lo; hi = nd->hi; esc = nd->next[r.oct]; }
-                int link = __float_as_int(hi.w);
-#ifdef WF_PREFETCH
-                if (!SMEM && link >= 0) prefetch_l1(nodesx + (link & 0x1fffffff));      // right child (the left one shares this line or the next)
-#endif
-                float tmin;
-                bool hit = (anypar ? slabs(r, lo, hi, tmin) : slabs_fast(r, lo, hi, tmin)) && !(tmin > tt * TR_PRUNE_GUARD);
-                if (link < 0) { int k = -link - 1; if (k == tleaf) found = true; else if (hit) pend = k; }
-#ifdef TR_COUNTERS
-                else ++cnt_nodes;
-#endif
-                idx = next_node<!SMEM>(idx, link, hit, esc, r.oct);
+            if (has && (unsigned)cur < (unsigned)TR_DONE) {
+                TR_COUNT(cnt_nodes);
+                cur = node_step<MODE, true>(tv, r, anypar, tt, tlink, found, st, cur, lane8);
             }
         }
-        const unsigned parked = __ballot_sync(0xffffffffu, has && pend >= 0);
-        unsigned finm = __ballot_sync(0xffffffffu, has && pend < 0 && idx >= nnodes);
-        const unsigned walking = ~idle & ~parked & ~finm;
-        if (__popc(parked) >= TR_LEAF_BATCH || (walking == 0u && parked != 0u)) {
-            if (has && pend >= 0) {
-#ifdef TR_COUNTERS
-                ++cnt_leaves;
-#endif
-                const TrLeaf* l2 = leaves + pend;
-                float u, v, t = intersect_leaf(r, l2->a, l2->b, l2->c, u, v);
-                if (t > 0.0f && t < TR_INF && (t < tt || (t == tt && pend > tleaf))) { visible = false; idx = nnodes; }
-                pend = -1;
-            }
+        if (has && cur < 0) {
+            TR_COUNT(cnt_leaves);
+            const int k = -cur - 1;
+            float4 la, lb, lc; leaf_fetch<MODE>(tv, k, lane8, la, lb, lc);
+            float u, v, t = intersect_leaf(r, la, lb, lc, u, v);
+            if (blocks_target(t, k, tt, tleaf)) { visible = false; cur = TR_DONE; } else cur = st.pop();
         }
+        const unsigned finm = __ballot_sync(0xffffffffu, has && cur == TR_DONE);
         if (QUERY) { if ((finm >> lane) & 1u) a.vis[slot] = (visible && found) ? tt : -1.0f; }
         else if ((finm >> lane) & 1u) {
             if (visible && found) {
@@ -833,7 +817,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_shadow(WfArgs a, int depth) {
         idle |= finm;
     }
 #ifdef TR_COUNTERS
-    atomicAdd(a.ctr->visits + 2, cnt_nodes); atomicAdd(a.ctr->visits + 3, cnt_leaves);
+    atomicAdd(a.ctr->visits + 2, 2ull * cnt_nodes); atomicAdd(a.ctr->visits + 3, cnt_leaves);
 #endif
 }
 
@@ -883,7 +867,8 @@ __global__ void k_debug(WfArgs a, float* __restrict__ fh) {
     int i = p / a.H, j = p - i * a.H;
     V3 o = mk3(a.cam.eye[0], a.cam.eye[1], a.cam.eye[2]), d = camera_dir(a.cam, i, j, 0.0f, 0.0f);
     RayPre r = make_ray(o, d);
-    HitRec h = trace_closest<false>(a.nodes, a.leaves, a.nodesx, a.nnodes, r, active, a.ctr->visits);
+    TreeView tv; tv.snodes = tv.sleaves = nullptr; tv.gnodes = a.nodes2; tv.gleaves = a.leaves4; tv.top = 0;
+    HitRec h = trace_closest(tv, a.root, r, active, a.ctr->visits);
     if (!active) return;
     float* f = fh + (size_t)p * 16;
     V3 col = mk3(0, 0, 0), pos = mk3(0, 0, 0), gn = mk3(0, 0, 0), nn = mk3(0, 0, 0);
@@ -951,6 +936,15 @@ __global__ void k_matlin(const float* __restrict__ material, int nm, float4* __r
     out[i] = make_float4(c.x, c.y, c.z, 0.0f);
 }
 
+// the tree as the traversal kernels see it (mode-independent part; launch_cfg picks the mode and the staging sizes)
+static void tr_tree_args(tr_ctx* ctx, WfArgs& a) {
+    a.nodes2 = (const float4*)ctx->d_nodes2; a.leaves4 = (const float4*)ctx->d_leaves; a.small_img = ctx->d_small_img;
+    a.nint = ctx->np - 1; a.nleaves = ctx->np; a.top = 0; a.stack_cap = 0; a.stage_bytes = 0;
+    a.root.lo = make_float4(ctx->root_box[0], ctx->root_box[1], ctx->root_box[2], 0.0f);
+    a.root.hi = make_float4(ctx->root_box[3], ctx->root_box[4], ctx->root_box[5], 0.0f);
+    a.root.link = ctx->np > 1 ? 0 : -1;
+}
+
 static int fill_args(tr_ctx* ctx, WfArgs& a, bool spec = false) {
     if (!ctx->bvh_ready) return tr_fail(ctx, TR_ERR_INVALID, "render: BVH not built (call tr_bvh_build)");
     if (!ctx->cam_set) return tr_fail(ctx, TR_ERR_INVALID, "render: camera not set");
@@ -965,7 +959,7 @@ static int fill_args(tr_ctx* ctx, WfArgs& a, bool spec = false) {
         ctx->matlin_ready = true; ctx->gen++;
     }
     memset(&a, 0, sizeof(a));
-    a.nodes = ctx->d_nodes; a.leaves = ctx->d_leaves; a.nodesx = ctx->d_nodesx; a.nnodes = 2 * ctx->np - 1; a.nleaves = ctx->np;
+    tr_tree_args(ctx, a);
     a.shade = ctx->d_shade; a.material = ctx->d_material; a.matlin = ctx->d_matlin; a.light = ctx->d_light; a.nl = ctx->nl; a.leaf_of_prim = ctx->d_leaf_of_prim;
     a.env = ctx->d_env; a.env_w = ctx->d_env ? ctx->env_w : 0; a.env_h = ctx->env_h; a.env_power = ctx->env_power;
     a.cam = ctx->cam; a.W = ctx->W; a.H = ctx->H; a.tiles = ctx->d_tiles; a.npix = ctx->n_local_tiles * TR_TILE * TR_TILE;
@@ -975,10 +969,7 @@ static int fill_args(tr_ctx* ctx, WfArgs& a, bool spec = false) {
     for (int k = 0; k < 2; ++k) { a.sa[k] = ctx->d_shq[k][0]; a.sb[k] = ctx->d_shq[k][1]; a.sc[k] = ctx->d_shq[k][2]; }
     a.L = ctx->d_L; a.Lnee = ctx->d_Lnee;
     a.ctr = ctx->d_ctr; a.bp = (const BatchParams*)ctx->d_batch_params;
-    a.frame_off = 0; a.sub_frames = 1 << 20; a.tail_max = ctx->opt_tail_max; a.tail_chunk = ctx->opt_tail_chunk < 1 ? 1 : ctx->opt_tail_chunk;
-    a.smem_nodes_bytes = (unsigned)((size_t)a.nnodes * sizeof(TrNode));
-    a.smem_leaves_bytes = (unsigned)((size_t)a.nleaves * sizeof(TrLeaf));
-    a.smem_next_bytes = (unsigned)((size_t)a.nnodes * 8 * sizeof(int));
+    a.frame_off = 0; a.sub_frames = 1 << 20; a.tail_max = ctx->opt_tail_max < 0 ? 16384 : ctx->opt_tail_max; a.tail_chunk = ctx->opt_tail_chunk < 1 ? 1 : ctx->opt_tail_chunk;
     if (spec) { if ((rc = tr_spec_prepare(ctx))) return rc; a.spec = ctx->spec; }
     return TR_OK;
 }
@@ -996,34 +987,46 @@ static int ensure_wavefront(tr_ctx* ctx, size_t slots) {
     return TR_OK;
 }
 
-struct LaunchCfg { int grid_trace, grid_shadow, grid_simple, grid_tail[2]; size_t smem; bool use_smem; };   // grid_tail[SPEC]   // memset before use (compared bytewise)
+struct LaunchCfg { int mode, grid_trace, grid_shadow, grid_simple, grid_tail[2]; size_t smem; };   // grid_tail[SPEC]   // memset before use (compared bytewise)
 
-static int launch_cfg(tr_ctx* ctx, const WfArgs& a, LaunchCfg& c) {
-    size_t bytes = (size_t)a.smem_nodes_bytes + a.smem_leaves_bytes;
-    c.use_smem = ctx->opt_smem_bvh && bytes <= 96 * 1024;
-    c.smem = c.use_smem ? bytes : 0;
-    int bt = 0, bs = 0;
-    if (c.use_smem) {
-        TR_CUDA(ctx, cudaFuncSetAttribute(k_trace<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-        TR_CUDA(ctx, cudaFuncSetAttribute(k_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-        TR_CUDA(ctx, cudaFuncSetAttribute(k_tail<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-        TR_CUDA(ctx, cudaFuncSetAttribute(k_tail<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-        TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, k_trace<true>, WF_THREADS, c.smem));
-        TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_shadow<true>, WF_THREADS, c.smem));
-    } else {
-        TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, k_trace<false>, WF_THREADS, 0));
-        TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_shadow<false>, WF_THREADS, 0));
-    }
-    if (bt < 1) bt = 1; if (bs < 1) bs = 1;
-    int t0 = 0, t1 = 0;        // the tail kernel deals its paths over the warps that are resident at once
-    if (c.use_smem) {
-        TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t0, k_tail<true, false>, WF_THREADS, c.smem));
-        TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t1, k_tail<true, true>, WF_THREADS, c.smem));
-    } else {
-        TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t0, k_tail<false, false>, WF_THREADS, 0));
-        TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t1, k_tail<false, true>, WF_THREADS, 0));
-    }
-    c.grid_tail[0] = ctx->num_sms * (t0 < 1 ? 1 : t0); c.grid_tail[1] = ctx->num_sms * (t1 < 1 ? 1 : t1);
+// instantiate-and-dispatch on the tree mode
+#define TR_MODE_SWITCH(mode, CALL) do { switch (mode) { \
+    case TM_REP: { constexpr int M = TM_REP; CALL; } break; case TM_SMEM: { constexpr int M = TM_SMEM; CALL; } break; \
+    case TM_GTOP: { constexpr int M = TM_GTOP; CALL; } break; default: { constexpr int M = TM_GLOBAL; CALL; } break; } } while (0)
+
+template <typename K> static int kernel_blocks(tr_ctx* ctx, K kern, size_t smem, int& blocks) {
+    TR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, WF_THREADS, smem));
+    if (blocks < 1) blocks = 1;
+    return TR_OK;
+}
+
+// Picks how the traversal kernels read the tree and sizes their dynamic shared memory:
+//   TM_REP    whole tree, 8-way replicated conflict-free image      (image <= 40 KB: Cornell box 31 KB)
+//   TM_SMEM   whole tree, plain                                     (nodes + leaves <= 64 KB)
+//   TM_GTOP   global memory + the breadth-first top `top_nodes` nodes staged (option "top_nodes" > 0)
+//   TM_GLOBAL global memory
+// plus stack_cap x 1 KB for the traversal stacks (stack_cap = min(entries the tree needs, TR_STACK_SMEM)).
+static int launch_cfg(tr_ctx* ctx, WfArgs& a, LaunchCfg& c) {
+    const size_t rep_bytes = ((size_t)a.nint * 4 + (size_t)a.nleaves * 3) * 128, plain_bytes = (size_t)a.nint * 64 + (size_t)a.nleaves * 48;
+    a.top = 0;
+    if (ctx->opt_smem_bvh && ctx->opt_replicas && ctx->d_small_img && rep_bytes <= TR_SMALL_IMG_MAX) { c.mode = TM_REP; a.stage_bytes = (unsigned)rep_bytes; }
+    else if (ctx->opt_smem_bvh && plain_bytes <= 64 * 1024) { c.mode = TM_SMEM; a.stage_bytes = (unsigned)((plain_bytes + 127) & ~(size_t)127); }
+    else if (ctx->opt_top_nodes > 0 && ctx->top_count > 0) {
+        c.mode = TM_GTOP; a.top = ctx->opt_top_nodes < ctx->top_count ? ctx->opt_top_nodes : ctx->top_count; a.stage_bytes = (unsigned)a.top * 64u;
+    } else { c.mode = TM_GLOBAL; a.stage_bytes = 0; }
+    a.stack_cap = ctx->stack_need < ctx->opt_stack_smem ? ctx->stack_need : ctx->opt_stack_smem;
+    if (a.stack_cap < 1) a.stack_cap = 1;
+    c.smem = (size_t)a.stage_bytes + (size_t)a.stack_cap * WF_THREADS * sizeof(int);
+    int bt = 0, bs = 0, t0 = 0, t1 = 0, rc = TR_OK;
+    TR_MODE_SWITCH(c.mode, {
+        if (!rc) rc = kernel_blocks(ctx, k_trace<M>, c.smem, bt);
+        if (!rc) rc = kernel_blocks(ctx, k_shadow<M, false>, c.smem, bs);
+        if (!rc) rc = kernel_blocks(ctx, k_tail<M, false>, c.smem, t0);
+        if (!rc) rc = kernel_blocks(ctx, k_tail<M, true>, c.smem, t1);
+    });
+    if (rc) return rc;
+    c.grid_tail[0] = ctx->num_sms * t0; c.grid_tail[1] = ctx->num_sms * t1;        // the tail kernel deals its paths over the warps that are resident at once
     c.grid_trace = ctx->num_sms * bt; c.grid_shadow = ctx->num_sms * bs;
     c.grid_simple = ctx->num_sms * 8;
     return TR_OK;
@@ -1053,24 +1056,21 @@ static int enqueue_chain(tr_ctx* ctx, const WfArgs& a, const LaunchCfg& c, int m
     k_generate<SPEC><<<c.grid_simple, WF_THREADS, 0, s>>>(a); ++*launches;
     for (int d = 0; d < max_depth; ++d) {
         if (ev) cudaEventRecord(ev[4 * d + 0], s);
-        if (c.use_smem) k_trace<true><<<c.grid_trace, WF_THREADS, c.smem, s>>>(a, d);
-        else k_trace<false><<<c.grid_trace, WF_THREADS, 0, s>>>(a, d);
+        TR_MODE_SWITCH(c.mode, (k_trace<M><<<c.grid_trace, WF_THREADS, c.smem, s>>>(a, d)));
         if (ev) cudaEventRecord(ev[4 * d + 1], s);
         if (split && d >= 2) TR_CUDA(ctx, cudaStreamWaitEvent(s, dep[2 * (d - 2) + 1], 0));
         k_shade<SPEC><<<c.grid_simple, WF_THREADS, 0, s>>>(a, d);
         if (ev) cudaEventRecord(ev[4 * d + 2], s);
         if (a.nl > 0) {
             if (split) { TR_CUDA(ctx, cudaEventRecord(dep[2 * d], s)); TR_CUDA(ctx, cudaStreamWaitEvent(ss, dep[2 * d], 0)); }
-            if (c.use_smem) k_shadow<true><<<c.grid_shadow, WF_THREADS, c.smem, ss>>>(a, d);
-            else k_shadow<false><<<c.grid_shadow, WF_THREADS, 0, ss>>>(a, d);
+            TR_MODE_SWITCH(c.mode, (k_shadow<M, false><<<c.grid_shadow, WF_THREADS, c.smem, ss>>>(a, d)));
             if (split) TR_CUDA(ctx, cudaEventRecord(dep[2 * d + 1], ss));
             ++*launches;
         }
         if (a.tail_max > 0 && d + 1 < max_depth) {
             // behind shadow(d) on the same stream: NEE terms stay in depth order; shade(d) (the hand-over decision) is done
             if (split && a.nl == 0) { TR_CUDA(ctx, cudaEventRecord(dep[2 * d], s)); TR_CUDA(ctx, cudaStreamWaitEvent(ss, dep[2 * d], 0)); }
-            if (c.use_smem) k_tail<true, SPEC><<<c.grid_tail[SPEC], WF_THREADS, c.smem, ss>>>(a, d + 1);
-            else k_tail<false, SPEC><<<c.grid_tail[SPEC], WF_THREADS, 0, ss>>>(a, d + 1);
+            TR_MODE_SWITCH(c.mode, (k_tail<M, SPEC><<<c.grid_tail[SPEC], WF_THREADS, c.smem, ss>>>(a, d + 1)));
             ++*launches;
         }
         if (ev) cudaEventRecord(ev[4 * d + 3], s);
@@ -1292,18 +1292,20 @@ extern "C" int tr_tonemap(tr_ctx* ctx, float exposure) {
     return TR_OK;
 }
 
-// ------------------------------------------------------------------ arbitrary-ray test hook
+// ------------------------------------------------------------------ arbitrary-ray test hooks
+// kernel 0: the simple one-lane-per-ray walk (trace_closest / trace_shadow_visible, also used by the Debug integrator)
 __global__ void k_test_trace(WfArgs a, int n, const float* __restrict__ o, const float* __restrict__ d, int shadow,
                              float* __restrict__ t, int* __restrict__ prim, float* __restrict__ uv) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = k < n;
     if (!active) k = 0;
     RayPre r = make_ray(mk3(o[k * 3], o[k * 3 + 1], o[k * 3 + 2]), mk3(d[k * 3], d[k * 3 + 1], d[k * 3 + 2]));
-    HitRec h = trace_closest<false>(a.nodes, a.leaves, a.nodesx, a.nnodes, r, active, nullptr);
+    TreeView tv; tv.snodes = tv.sleaves = nullptr; tv.gnodes = a.nodes2; tv.gleaves = a.leaves4; tv.top = 0;
+    HitRec h = trace_closest(tv, a.root, r, active, nullptr);
     if (shadow) {
         // cross-check the early-exit shadow query against the closest-hit answer it must reproduce
         bool has = active && h.prim >= 0;
-        bool vis = trace_shadow_visible<false>(a.nodes, a.leaves, a.nodesx, a.nnodes, r, has, has ? a.leaf_of_prim[h.prim] : 0, nullptr);
+        bool vis = trace_shadow_visible(tv, a.root, r, has, has ? a.leaf_of_prim[h.prim] : 0, nullptr);
         if (has && !vis) h.prim = -2;
     }
     if (!active) return;
@@ -1311,27 +1313,86 @@ __global__ void k_test_trace(WfArgs a, int n, const float* __restrict__ o, const
     if (uv) { uv[k * 2] = h.u; uv[k * 2 + 1] = h.v; }
 }
 
-extern "C" int tr_test_trace(tr_ctx* ctx, int n, const float* o, const float* d, int shadow, float* t, int32_t* prim, float* uv) {
-    if (!ctx || n <= 0 || !o || !d || !t || !prim) return tr_fail(ctx, TR_ERR_INVALID, "tr_test_trace: bad arguments");
+// the rays as queue records of the PRODUCTION kernels: path queue (k_trace, k_tail) or shadow queue with a per-ray target
+// primitive and unit contribution (k_shadow)
+__global__ void k_test_fill(WfArgs a, int n, const float* __restrict__ o, const float* __restrict__ d, const int* __restrict__ target, int pp) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    float4 A = make_float4(o[k * 3], o[k * 3 + 1], o[k * 3 + 2], d[k * 3]);
+    if (target) {
+        a.sa[0][k] = A; a.sb[0][k] = make_float4(d[k * 3 + 1], d[k * 3 + 2], __int_as_float(target[k]), __uint_as_float((unsigned)k));
+        a.sc[0][k] = make_float4(1.0f, 0.0f, 0.0f, 0.0f); a.Lnee[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    } else {
+        a.pa[pp][k] = A; a.pb[pp][k] = make_float4(d[k * 3 + 1], d[k * 3 + 2], 1.0f, __uint_as_float((unsigned)k | SPEC_BIT));
+        a.pc[pp][k] = make_float4(1.0f, 1.0f, 1.0f, 0.0f); a.hit[k] = make_float4(-1.0f, __int_as_float(-7), 0.0f, 0.0f);
+    }
+}
+__global__ void k_test_ctr(TrCounters* c, int n, int which) {
+    if (which == 2) c->nshadow[0] = n; else if (which == 3) { c->nq[1] = n; c->tail_from = 1; } else c->nq[0] = n;
+}
+
+// kernel: 0 simple walk (shadow != 0: plus the shadow-query cross-check); 1 production k_trace; 2 production k_shadow (target[] =
+// primitive each ray must see: prim out = target if visible else -2, t = 1 / 0); 3 production k_tail (first walk of each path).
+// Kernels 1..3 run in the tree mode the renderer would use (options smem_bvh / replicas / top_nodes apply).
+extern "C" int tr_test_trace_kernel(tr_ctx* ctx, int kernel, int n, const float* o, const float* d, const int32_t* target, int shadow,
+                                    float* t, int32_t* prim, float* uv) {
+    if (!ctx || n <= 0 || !o || !d || !t || !prim || kernel < 0 || kernel > 3 || (kernel == 2 && !target))
+        return tr_fail(ctx, TR_ERR_INVALID, "tr_test_trace_kernel: bad arguments");
     TR_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (!ctx->bvh_ready) return tr_fail(ctx, TR_ERR_INVALID, "tr_test_trace: BVH not built");
-    int rc; if ((rc = tr_build_shade_table(ctx))) return rc;
+    if (!ctx->bvh_ready) return tr_fail(ctx, TR_ERR_INVALID, "tr_test_trace_kernel: BVH not built");
+    int rc; if ((rc = tr_stats_resolve(ctx))) return rc;
+    if ((rc = tr_build_shade_table(ctx))) return rc;
     WfArgs a; memset(&a, 0, sizeof(a));
-    a.nodes = ctx->d_nodes; a.leaves = ctx->d_leaves; a.nodesx = ctx->d_nodesx; a.nnodes = 2 * ctx->np - 1; a.leaf_of_prim = ctx->d_leaf_of_prim;
-    float *d_o, *d_d, *d_t, *d_uv; int* d_p;
+    tr_tree_args(ctx, a);
+    a.leaf_of_prim = ctx->d_leaf_of_prim; a.material = ctx->d_material; a.ctr = ctx->d_ctr; a.bp = (const BatchParams*)ctx->d_batch_params;
+    a.tail_chunk = 8; a.probe = 1;
+    cudaStream_t s = ctx->stream;
+    if (kernel > 0) {
+        if ((rc = ensure_wavefront(ctx, (size_t)n))) return rc;
+        for (int k = 0; k < 2; ++k) { a.pa[k] = ctx->d_path[k][0]; a.pb[k] = ctx->d_path[k][1]; a.pc[k] = ctx->d_path[k][2]; }
+        a.hit = ctx->d_hit; a.cls = ctx->d_cls; a.cap = ctx->wf_cap; a.Lnee = ctx->d_Lnee; a.L = ctx->d_L;
+        for (int k = 0; k < 2; ++k) { a.sa[k] = ctx->d_shq[k][0]; a.sb[k] = ctx->d_shq[k][1]; a.sc[k] = ctx->d_shq[k][2]; }
+    }
+    float *d_o, *d_d, *d_t, *d_uv; int *d_p, *d_tg = nullptr;
     TR_CUDA(ctx, cudaMalloc((void**)&d_o, (size_t)n * 12)); TR_CUDA(ctx, cudaMalloc((void**)&d_d, (size_t)n * 12));
     TR_CUDA(ctx, cudaMalloc((void**)&d_t, (size_t)n * 4)); TR_CUDA(ctx, cudaMalloc((void**)&d_p, (size_t)n * 4));
     TR_CUDA(ctx, cudaMalloc((void**)&d_uv, (size_t)n * 8));
-    cudaStream_t s = ctx->stream;
     cudaMemcpyAsync(d_o, o, (size_t)n * 12, cudaMemcpyHostToDevice, s); cudaMemcpyAsync(d_d, d, (size_t)n * 12, cudaMemcpyHostToDevice, s);
-    k_test_trace<<<cdiv(n, 128), 128, 0, s>>>(a, n, d_o, d_d, shadow, d_t, d_p, d_uv);
-    cudaMemcpyAsync(t, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, s); cudaMemcpyAsync(prim, d_p, (size_t)n * 4, cudaMemcpyDeviceToHost, s);
-    if (uv) cudaMemcpyAsync(uv, d_uv, (size_t)n * 8, cudaMemcpyDeviceToHost, s);
+    if (kernel == 2) { TR_CUDA(ctx, cudaMalloc((void**)&d_tg, (size_t)n * 4)); cudaMemcpyAsync(d_tg, target, (size_t)n * 4, cudaMemcpyHostToDevice, s); }
+    std::vector<float4> hbuf;
+    if (kernel == 0) {
+        k_test_trace<<<cdiv(n, 128), 128, 0, s>>>(a, n, d_o, d_d, shadow, d_t, d_p, d_uv);
+        cudaMemcpyAsync(t, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, s); cudaMemcpyAsync(prim, d_p, (size_t)n * 4, cudaMemcpyDeviceToHost, s);
+        if (uv) cudaMemcpyAsync(uv, d_uv, (size_t)n * 8, cudaMemcpyDeviceToHost, s);
+    } else {
+        LaunchCfg c; memset(&c, 0, sizeof(c));
+        if ((rc = launch_cfg(ctx, a, c))) return rc;
+        BatchParams bp; bp.frame_begin = 0; bp.n_frames = 1; bp.seed = 0; bp.max_depth = 4; bp.pad = 0;
+        cudaMemcpyAsync(ctx->d_batch_params, &bp, sizeof(bp), cudaMemcpyHostToDevice, s);
+        cudaMemsetAsync(ctx->d_ctr, 0, sizeof(TrCounters), s);
+        k_test_fill<<<cdiv(n, 256), 256, 0, s>>>(a, n, d_o, d_d, d_tg, kernel == 3 ? 1 : 0);
+        k_test_ctr<<<1, 1, 0, s>>>(ctx->d_ctr, n, kernel);
+        if (kernel == 1) TR_MODE_SWITCH(c.mode, (k_trace<M><<<c.grid_trace, WF_THREADS, c.smem, s>>>(a, 0)));
+        else if (kernel == 2) TR_MODE_SWITCH(c.mode, (k_shadow<M, false><<<c.grid_shadow, WF_THREADS, c.smem, s>>>(a, 0)));
+        else TR_MODE_SWITCH(c.mode, (k_tail<M, false><<<c.grid_tail[0], WF_THREADS, c.smem, s>>>(a, 1)));
+        hbuf.resize((size_t)n);
+        cudaMemcpyAsync(hbuf.data(), kernel == 2 ? a.Lnee : a.hit, (size_t)n * 16, cudaMemcpyDeviceToHost, s);
+    }
     cudaError_t e = cudaStreamSynchronize(s);
-    cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_p); cudaFree(d_uv);
-    if (e != cudaSuccess) return tr_fail(ctx, TR_ERR_CUDA, "tr_test_trace: %s", cudaGetErrorString(e));
-    TR_CHECK_LAUNCH(ctx);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_p); cudaFree(d_uv); if (d_tg) cudaFree(d_tg);
+    if (e != cudaSuccess) return tr_fail(ctx, TR_ERR_CUDA, "tr_test_trace_kernel: %s", cudaGetErrorString(e));
+    if (kernel == 2) for (int k = 0; k < n; ++k) { const bool vis = hbuf[k].x == 1.0f; t[k] = vis ? 1.0f : 0.0f; prim[k] = vis ? target[k] : -2; }
+    else if (kernel > 0) for (int k = 0; k < n; ++k) {
+        t[k] = hbuf[k].x; memcpy(&prim[k], &hbuf[k].y, 4);
+        if (uv) { uv[k * 2] = hbuf[k].z; uv[k * 2 + 1] = hbuf[k].w; }
+    }
+    ctx->gen++;                                 // the queues were overwritten
     return TR_OK;
+}
+
+extern "C" int tr_test_trace(tr_ctx* ctx, int n, const float* o, const float* d, int shadow, float* t, int32_t* prim, float* uv) {
+    return tr_test_trace_kernel(ctx, 0, n, o, d, nullptr, shadow, t, prim, uv);
 }
 
 #include "bdpt.cuh"
