@@ -200,6 +200,9 @@ int tr_test_glass_sample(tr_ctx* ctx, int n, const float* dir, const float* N, f
                          const float* u /* n */, float* out /* n x 4 */);
 int tr_test_offset_ray(tr_ctx* ctx, int n, const float* p, const float* nrm, float* out /* n x 3 */);
 int tr_test_rng(tr_ctx* ctx, uint64_t seed, uint32_t pixel, uint32_t frame, uint32_t block, float* out4);
+/* include/trmath.h on the device: fn 0 sin, 1 cos, 2 exp, 3 acos (of a), 4 atan2(a, b), 5 pow(a, b); the oracle compiles the same
+ * header, so the results must agree bit for bit */
+int tr_test_math(tr_ctx* ctx, int fn, int n, const float* a, const float* b /* fn >= 4 */, float* out);
 /* arbitrary rays through the simple one-lane-per-ray walk (the Debug integrator's); shadow != 0 adds the shadow-query cross-check */
 int tr_test_trace(tr_ctx* ctx, int n, const float* o, const float* d, int shadow,
                   float* t, int32_t* prim, float* uv /* n x 2 or NULL */);

@@ -56,6 +56,7 @@ def _load(fast):
     lib.orc_philox_raw.argtypes = [C.c_uint32] * 6 + [_u32p]
     lib.orc_slabs.argtypes = [_f32p, _f32p, _f32p, _f32p]
     lib.orc_set_num_threads.argtypes = [C.c_int]
+    lib.orc_math.argtypes = [C.c_int, C.c_int, _f32p, C.c_void_p, _f32p]
     lib.orc_camera_view_set.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int]
     lib.orc_render_bdpt_rgb.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, _f32p, C.c_void_p, _u64p]
     lib.orc_bdpt_pixel_dump.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, _f32p, _i32p, _f32p]
@@ -214,6 +215,14 @@ class OracleScene:
     def process_normal(self):
         self.lib.orc_process_normal(self.h)
         out = np.zeros_like(self._keep[0]); self.lib.orc_vertex_get(self.h, out.reshape(-1)); return out
+
+
+def math_fn(fn, a, b=None):
+    """include/trmath.h on the host: fn 0 sin, 1 cos, 2 exp, 3 acos, 4 atan2(a, b), 5 pow(a, b)"""
+    a = np.ascontiguousarray(a, np.float32).reshape(-1); out = np.zeros_like(a)
+    bb = None if b is None else np.ascontiguousarray(b, np.float32).reshape(-1)
+    lib().orc_math(int(fn), a.size, a, None if bb is None else bb.ctypes.data, out)
+    return out
 
 
 def tonemap(hdr, exposure=0.5):

@@ -31,6 +31,7 @@
 #include <cstdio>
 #ifdef _OPENMP
 #include <omp.h>
+#include "../include/trmath.h"
 #endif
 
 namespace {
@@ -554,14 +555,14 @@ inline float get_prim_angle(const Scene& s, int idx, V3 v) {
         else if (length(v2 - v) < 0.00001f) ret = dot(normalized(v1 - v2), normalized(v3_ - v2));
         else                                ret = dot(normalized(v1 - v3_), normalized(v2 - v3_));
     }
-    return acosf(ret);
+    return tr_acosf(ret);
 }
 // Scene.py:315-322
 inline V3 UniformSampleSphere(float u1, float u2) {
     float z = 1.0f - 2.0f * u1;
     float r = sqrtf(clampf(1.0f - z * z, 0.0f, 1.0f));
     float phi = 2.0f * 3.1415926f * u2;
-    return {r * cosf(phi), r * sinf(phi), z};
+    return {r * tr_cosf(phi), r * tr_sinf(phi), z};
 }
 // UtilsFunc.py:348-350
 inline float CosineHemisphere_pdf(float c) { return fmaxf(0.01f, c / REF_PIf); }
@@ -607,7 +608,7 @@ inline LightSample sample_li(const Scene& s, V3 p, float u_idx, float a, float b
 // UtilsFunc.py:352-360
 inline V3 CosineSampleHemisphere(float u1, float u2) {
     float r = sqrtf(u1), phi = 2.0f * REF_PIf * u2;
-    V3 p; p.x = r * cosf(phi); p.y = r * sinf(phi);
+    V3 p; p.x = r * tr_cosf(phi); p.y = r * tr_sinf(phi);
     p.z = sqrtf(fmaxf(0.0f, 1.0f - p.x * p.x - p.y * p.y));
     return normalized(p);
 }
@@ -630,7 +631,7 @@ inline V3 refract(V3 I, V3 N, float eta, float& suc) {
     if (k > 0.0f) { R = eta * I - (eta * NI + sqrtf(k)) * N; suc = 1.0f; }
     return R;
 }
-inline float schlick(float cosine, float ior) { float r0 = (1.0f - ior) / (1.0f + ior); r0 = r0 * r0; return r0 + (1.0f - r0) * powf(1.0f - cosine, 5.0f); }
+inline float schlick(float cosine, float ior) { float r0 = (1.0f - ior) / (1.0f + ior); r0 = r0 * r0; return r0 + (1.0f - r0) * tr_powf(1.0f - cosine, 5.0f); }
 inline float powerHeuristic(float a, float b) { float t = a * a; return t / (b * b + t); }
 // UtilsFunc.py:440-461
 inline V3 offset_ray(V3 p, V3 n) {
@@ -646,9 +647,9 @@ inline V3 offset_ray(V3 p, V3 n) {
     return {r[0], r[1], r[2]};
 }
 // UtilsFunc.py:76-94,113-120
-inline float srgb_to_lrgb1(float c) { return c < 0.04045f ? c / 12.92f : powf((c + 0.055f) / 1.055f, 2.4f); }
+inline float srgb_to_lrgb1(float c) { return c < 0.04045f ? c / 12.92f : tr_powf((c + 0.055f) / 1.055f, 2.4f); }
 inline V3 srgb_to_lrgb(V3 c) { return {srgb_to_lrgb1(c.x), srgb_to_lrgb1(c.y), srgb_to_lrgb1(c.z)}; }
-inline float lrgb_to_srgb1(float c) { float r = c < 0.0031308f ? c * 12.92f : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f; return clampf(r, 0.0f, 1.0f); }
+inline float lrgb_to_srgb1(float c) { float r = c < 0.0031308f ? c * 12.92f : 1.055f * tr_powf(c, 1.0f / 2.4f) - 0.055f; return clampf(r, 0.0f, 1.0f); }
 inline float tone_ACES1(float x) { const float a = 2.51f, b = 0.03f, c = 2.43f, d = 0.59f, e = 0.14f; return clampf((x * (a * x + b)) / (x * (c * x + d) + e), 0.0f, 1.0f); }
 
 // brdf/Disney.py:65-108
@@ -685,7 +686,7 @@ inline V3 disney_sample(V3 dir, V3 N, float metal, float rough, float prob, floa
         float phi = r1 * 2.0f * REF_PIf;
         float cosT = sqrtf((1.0f - r2) / (1.0f + (alpha * alpha - 1.0f) * r2));
         float sinT = sqrtf(1.0f - (cosT * cosT));
-        float sinP = sinf(phi), cosP = cosf(phi);
+        float sinP = tr_sinf(phi), cosP = tr_cosf(phi);
         V3 half = inverse_transform(v3(sinT * cosP, sinT * sinP, cosT), N);
         next = reflect(dir, half);
     }
@@ -785,7 +786,7 @@ V3 pt_rgb_pixel(Scene& s, int i, int j, int frame, int max_depth, uint64_t seed,
             next_o = offset_ray(h.pos, signf(f_or_b) * fn);
             if (brdf_pdf > 0.0f) {
                 if (f_or_b < 0.0f) {
-                    float ext = mat_p1(s, mid); float R = expf(-h.t / ext);
+                    float ext = mat_p1(s, mid); float R = tr_expf(-h.t / ext);
                     if (R1.z >= R) break;
                 }
                 T = T * ((brdf / brdf_pdf) * rc);
@@ -793,8 +794,8 @@ V3 pt_rgb_pixel(Scene& s, int i, int j, int frame, int max_depth, uint64_t seed,
             } else break;
         } else {
             float dis = sqrtf(d.x * d.x + d.z * d.z);
-            float tx = (atan2f(d.z, d.x) + 3.1415926f) / 3.1415926f / 2.0f;
-            float ty = atan2f(d.y, dis) / 3.1415926f + 0.5f;
+            float tx = (tr_atan2f(d.z, d.x) + 3.1415926f) / 3.1415926f / 2.0f;
+            float ty = tr_atan2f(d.y, dis) / 3.1415926f + 0.5f;
             if (s.env_w > 0) L = L + (srgb_to_lrgb(texture2D(s, tx, ty)) * T) * s.env_power;
             break;
         }
@@ -1034,6 +1035,13 @@ int orc_num_threads() {
 #else
     return 1;
 #endif
+}
+// include/trmath.h on the host (fn 0 sin, 1 cos, 2 exp, 3 acos, 4 atan2(a, b), 5 pow(a, b)): the CUDA kernels compile the same header
+void orc_math(int fn, int n, const float* a, const float* b, float* out) {
+    for (int k = 0; k < n; ++k) {
+        const float x = a[k], y = b ? b[k] : 0.0f;
+        out[k] = fn == 0 ? tr_sinf(x) : fn == 1 ? tr_cosf(x) : fn == 2 ? tr_expf(x) : fn == 3 ? tr_acosf(x) : fn == 4 ? tr_atan2f(x, y) : tr_powf(x, y);
+    }
 }
 // bench.py's reference arm: torchrun exports OMP_NUM_THREADS=1, the CPU baseline is defined on ALL host cores
 void orc_set_num_threads(int n) {

@@ -62,7 +62,7 @@ def test_production_kernels_bit_exact(gpu_ctx, oracle_tables, name, sl, opts, wh
     expect = np.where(op == target, target, -2).astype(np.int32)
     st, sp, _ = gpu_ctx.test_trace(org, d, kernel=2, target=target)
     assert np.array_equal(sp, expect), (what, "k_shadow", int((sp != expect).sum()))
-    assert (expect >= 0).sum() > n // 4
+    assert (expect >= 0).sum() > 1000
 
 
 def test_degenerate_trees_trace(gpu_ctx):

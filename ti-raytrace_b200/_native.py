@@ -74,6 +74,7 @@ SIGNATURES = {
     "tr_test_glass_sample": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_float, _vp, _vp]),
     "tr_test_offset_ray": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
     "tr_test_rng": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _vp]),
+    "tr_test_math": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "tr_test_trace": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp]),
     "tr_test_trace_kernel": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp]),
     "tr_spec_sensor_upload": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_float]),
@@ -105,6 +106,8 @@ def load_library(name=None):
                                % (path, os.path.join(ROOT, "csrc")))
         lib = C.CDLL(path)
         for sym, (res, args) in SIGNATURES.items():
+            if os.environ.get("TIRAY_ALLOW_MISSING") and not hasattr(lib, sym):
+                continue                     # developer A/B runs against an older build of the library (tools/perf_probe.py --lib)
             fn = getattr(lib, sym)           # AttributeError if the library does not export the symbol
             fn.restype, fn.argtypes = res, args
         _libs[name] = lib
@@ -351,6 +354,10 @@ class Context:
     def test_offset_ray(self, p, n):
         p, n = _f(p, (-1, 3)), _f(n, (-1, 3)); out = np.zeros_like(p)
         self._ck(self.lib.tr_test_offset_ray(self.h, p.shape[0], _ptr(p), _ptr(n), _ptr(out)), "hook"); return out
+
+    def test_math(self, fn, a, b=None):
+        a = _f(a, (-1,)); b = None if b is None else _f(b, (-1,)); out = np.zeros(a.shape[0], np.float32)
+        self._ck(self.lib.tr_test_math(self.h, int(fn), a.shape[0], _ptr(a), _ptr(b), _ptr(out)), "tr_test_math"); return out
 
     def test_rng(self, seed, pixel, frame, block):
         out = np.zeros(4, np.float32); self._ck(self.lib.tr_test_rng(self.h, seed, pixel, frame, block, _ptr(out)), "hook"); return out

@@ -116,7 +116,7 @@ __device__ __forceinline__ BdStep bd_vertex(const bool LIGHT, const WfArgs& a, c
         pdfRev = disney_pdf(fn, next_dir, -dir, p0, p1);
     }
     bv_set_rpdf(b, s, vbase + depth - 1, pdfRev * fabsf(dot3(to, sf.n)) * inv_dist2);
-    if (f_or_b < 0.0f) { float Rr = expf(-ht / p1); if (R1.z >= Rr) return st; }
+    if (f_or_b < 0.0f) { float Rr = tr_expf(-ht / p1); if (R1.z >= Rr) return st; }
     st.counted = true; st.cont = true;
     st.origin = offset_ray(sf.pos, signf_(f_or_b) * fn); st.dir = next_dir; st.beta = beta; st.pdfFwd = pdfFwd; st.pos = sf.pos; st.normal = sf.n;
     return st;

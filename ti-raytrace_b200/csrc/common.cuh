@@ -8,6 +8,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "../../include/trmath.h"
 
 #define TR_INF 1000000.0f        // UtilsFunc.py:38 INF_VALUE
 #define TR_PI_REF 3.1415956f     // UtilsFunc.py:37 M_PIf (sic)
@@ -70,7 +71,7 @@ __device__ __forceinline__ float cosine_hemisphere_pdf(float c) { return fmaxf(0
 // UtilsFunc.py:352-360
 __device__ __forceinline__ V3 cosine_sample_hemisphere(float u1, float u2) {
     float r = sqrtf(u1), phi = 2.0f * TR_PI_REF * u2;
-    V3 p; p.x = r * cosf(phi); p.y = r * sinf(phi);
+    V3 p; p.x = r * tr_cosf(phi); p.y = r * tr_sinf(phi);
     p.z = sqrtf(fmaxf(0.0f, 1.0f - p.x * p.x - p.y * p.y));
     return normalize3(p);
 }
@@ -94,7 +95,7 @@ __device__ __forceinline__ V3 refract3(V3 I, V3 N, float eta, float& suc) {
     return R;
 }
 // UtilsFunc.py:428-438
-__device__ __forceinline__ float schlick_r(float cosine, float ior) { float r0 = (1.0f - ior) / (1.0f + ior); r0 = r0 * r0; return r0 + (1.0f - r0) * powf(1.0f - cosine, 5.0f); }
+__device__ __forceinline__ float schlick_r(float cosine, float ior) { float r0 = (1.0f - ior) / (1.0f + ior); r0 = r0 * r0; return r0 + (1.0f - r0) * tr_powf(1.0f - cosine, 5.0f); }
 __device__ __forceinline__ float power_heuristic(float a, float b) { float t = a * a; return t / (b * b + t); }
 // UtilsFunc.py:440-461: integer-ULP nudge along the normal
 __device__ __forceinline__ V3 offset_ray(V3 p, V3 n) {
@@ -110,9 +111,9 @@ __device__ __forceinline__ V3 offset_ray(V3 p, V3 n) {
     return mk3(r[0], r[1], r[2]);
 }
 // UtilsFunc.py:76-94,113-120
-__device__ __forceinline__ float srgb_to_lrgb1(float c) { return c < 0.04045f ? c / 12.92f : powf((c + 0.055f) / 1.055f, 2.4f); }
+__device__ __forceinline__ float srgb_to_lrgb1(float c) { return c < 0.04045f ? c / 12.92f : tr_powf((c + 0.055f) / 1.055f, 2.4f); }
 __device__ __forceinline__ V3 srgb_to_lrgb(V3 c) { return mk3(srgb_to_lrgb1(c.x), srgb_to_lrgb1(c.y), srgb_to_lrgb1(c.z)); }
-__device__ __forceinline__ float lrgb_to_srgb1(float c) { float r = c < 0.0031308f ? c * 12.92f : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f; return clampf(r, 0.0f, 1.0f); }
+__device__ __forceinline__ float lrgb_to_srgb1(float c) { float r = c < 0.0031308f ? c * 12.92f : 1.055f * tr_powf(c, 1.0f / 2.4f) - 0.055f; return clampf(r, 0.0f, 1.0f); }
 __device__ __forceinline__ float tone_aces1(float x) { const float a = 2.51f, b = 0.03f, c = 2.43f, d = 0.59f, e = 0.14f; return clampf((x * (a * x + b)) / (x * (c * x + d) + e), 0.0f, 1.0f); }
 
 // brdf/Disney.py:65-108
@@ -164,7 +165,7 @@ __device__ __forceinline__ V3 disney_sample(V3 dir, V3 N, float metal, float rou
         float phi = r1 * 2.0f * TR_PI_REF;
         float cosT = sqrtf((1.0f - r2) / (1.0f + (alpha * alpha - 1.0f) * r2));
         float sinT = sqrtf(1.0f - (cosT * cosT));
-        float sinP = sinf(phi), cosP = cosf(phi);
+        float sinP = tr_sinf(phi), cosP = tr_cosf(phi);
         V3 half = inverse_transform(mk3(sinT * cosP, sinT * sinP, cosT), N);
         next = reflect3(dir, half);
     }
@@ -184,7 +185,7 @@ __device__ __forceinline__ V3 uniform_sample_sphere(float u1, float u2) {
     float z = 1.0f - 2.0f * u1;
     float r = sqrtf(clampf(1.0f - z * z, 0.0f, 1.0f));
     float phi = 2.0f * TR_PI_ENV * u2;
-    return mk3(r * cosf(phi), r * sinf(phi), z);
+    return mk3(r * tr_cosf(phi), r * tr_sinf(phi), z);
 }
 
 // ---- Morton (UtilsFunc.py:538-580)

@@ -23,8 +23,7 @@ struct TrNode { float4 lo, hi; };
 // Order: the first top_count nodes are the breadth-first top of the tree (the part TM_GTOP stages into shared memory), the rest
 // follows in pre-order.
 struct TrNode2 { float4 a, b, c, d; };
-#define TR_STACK_SMEM 24                     // traversal-stack entries per lane kept in shared memory
-#define TR_STACK_MAX 120                     // + local-memory overflow: the deepest stack a tree may need (else TR_ERR_STACK at build)
+#define TR_STACK_MAX 128                     // traversal-stack entries per lane a tree may need (1 KB of shared memory per entry and CTA; else TR_ERR_STACK at build)
 #define TR_TOP_MAX 1024                      // breadth-first top nodes kept contiguous at the front of the TrNode2 array
 #define TR_SMALL_IMG_MAX (40 * 1024)         // largest replicated shared-memory image (see trace.cuh)
 // Leaf record, 48 B, in sorted (Morton) order:
@@ -146,7 +145,6 @@ struct tr_ctx {
     int opt_top_nodes = 0;          // large trees: this many breadth-first top nodes are staged into shared memory per CTA (0 = off)
     int opt_pdl = 1;                // programmatic dependent launch between the stages of a chain
     int opt_replicas = 1;           // small trees: bank-conflict-free 8-replica shared-memory image
-    int opt_stack_smem = TR_STACK_SMEM;   // traversal-stack entries per lane kept in shared memory (the rest overflows to local memory)
     size_t opt_max_paths = (size_t)20 << 20;   // path slots per batch (188 B each): more paths in flight amortise the per-stage tails
 
     // cuda graph cache for the batch pipeline

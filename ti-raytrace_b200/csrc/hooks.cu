@@ -4,7 +4,7 @@
 #include "ctx.h"
 #include "common.cuh"
 
-enum { H_DISNEY_EVAL = 0, H_DISNEY_SAMPLE = 1, H_GLASS_SAMPLE = 2, H_OFFSET_RAY = 3, H_RNG = 4 };
+enum { H_DISNEY_EVAL = 0, H_DISNEY_SAMPLE = 1, H_GLASS_SAMPLE = 2, H_OFFSET_RAY = 3, H_RNG = 4, H_MATH = 5 };
 
 __global__ void k_hook(int op, int n, const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
                        float p0, float p1, unsigned long long seed, unsigned u0, unsigned u1, unsigned u2, float* __restrict__ out) {
@@ -24,6 +24,10 @@ __global__ void k_hook(int op, int n, const float* __restrict__ a, const float* 
     } else if (op == H_OFFSET_RAY) {
         V3 r = offset_ray(mk3(a[k * 3], a[k * 3 + 1], a[k * 3 + 2]), mk3(b[k * 3], b[k * 3 + 1], b[k * 3 + 2]));
         out[k * 3] = r.x; out[k * 3 + 1] = r.y; out[k * 3 + 2] = r.z;
+    } else if (op == H_MATH) {
+        // include/trmath.h: the function is selected by u0 (0 sin, 1 cos, 2 exp, 3 acos, 4 atan2(a, b), 5 pow(a, b))
+        const float x = a[k], y = b ? b[k] : 0.0f;
+        out[k] = u0 == 0 ? tr_sinf(x) : u0 == 1 ? tr_cosf(x) : u0 == 2 ? tr_expf(x) : u0 == 3 ? tr_acosf(x) : u0 == 4 ? tr_atan2f(x, y) : tr_powf(x, y);
     } else if (op == H_RNG) {
         float4 r = rng4(seed, u0, u1, u2);
         out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
@@ -61,6 +65,10 @@ int tr_test_glass_sample(tr_ctx* ctx, int n, const float* dir, const float* N, f
 }
 int tr_test_offset_ray(tr_ctx* ctx, int n, const float* p, const float* nrm, float* out) {
     return run_hook(ctx, H_OFFSET_RAY, n, p, (size_t)n * 3, nrm, (size_t)n * 3, nullptr, 0, 0.0f, 0.0f, 0, 0, 0, 0, out, (size_t)n * 3);
+}
+int tr_test_math(tr_ctx* ctx, int fn, int n, const float* a, const float* b, float* out) {
+    if (fn < 0 || fn > 5 || !a || (fn >= 4 && !b)) return tr_fail(ctx, TR_ERR_INVALID, "tr_test_math: bad arguments");
+    return run_hook(ctx, H_MATH, n, a, (size_t)n, fn >= 4 ? b : nullptr, (size_t)n, nullptr, 0, 0.0f, 0.0f, 0, (unsigned)fn, 0, 0, out, (size_t)n);
 }
 int tr_test_rng(tr_ctx* ctx, uint64_t seed, uint32_t pixel, uint32_t frame, uint32_t block, float* out4) {
     return run_hook(ctx, H_RNG, 1, nullptr, 0, nullptr, 0, nullptr, 0, 0.0f, 0.0f, seed, pixel, frame, block, out4, 4);

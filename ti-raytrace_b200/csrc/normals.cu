@@ -26,7 +26,7 @@ __device__ __forceinline__ float tri_angle(const float* __restrict__ vertex, int
     if (length3(v1 - v) < 0.00001f)      ret = dot3(normalize3(v2 - v1), normalize3(v3 - v1));
     else if (length3(v2 - v) < 0.00001f) ret = dot3(normalize3(v1 - v2), normalize3(v3 - v2));
     else                                 ret = dot3(normalize3(v1 - v3), normalize3(v2 - v3));
-    return acosf(ret);
+    return tr_acosf(ret);
 }
 
 __global__ void k_smooth_normals(const float* __restrict__ vertex, const int* __restrict__ prim, int nv,

@@ -145,11 +145,11 @@ __device__ __forceinline__ float get_glass_ior(float L) {
 __device__ __forceinline__ float sky_internal(const float* __restrict__ sky, int wl, float theta, float gamma) {
     const float* c = sky + wl * 9;
     float c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2), c3 = __ldg(c + 3), c4 = __ldg(c + 4), c5 = __ldg(c + 5), c6 = __ldg(c + 6), c7 = __ldg(c + 7), c8 = __ldg(c + 8);
-    float cg = cosf(gamma), ct = cosf(theta);
-    float expM = expf(c4 * gamma), rayM = cg * cg;
-    float mieM = (1.0f + cg * cg) / powf((1.0f + c8 * c8 - 2.0f * c8 * cg), 1.5f);
+    float cg = tr_cosf(gamma), ct = tr_cosf(theta);
+    float expM = tr_expf(c4 * gamma), rayM = cg * cg;
+    float mieM = (1.0f + cg * cg) / tr_powf((1.0f + c8 * c8 - 2.0f * c8 * cg), 1.5f);
     float zenith = sqrtf(ct);
-    return (1.0f + c0 * expf(c1 / (ct + 0.01f))) * (c2 + c3 * expM + c5 * rayM + c6 * mieM + c7 * zenith);
+    return (1.0f + c0 * tr_expf(c1 / (ct + 0.01f))) * (c2 + c3 * expM + c5 * rayM + c6 * mieM + c7 * zenith);
 }
 __device__ __forceinline__ float sky_radiance(const SpecDev& sd, float theta, float gamma, float wl) {
     float ret = 0.0f;

@@ -151,22 +151,24 @@ __device__ __forceinline__ void leaf_fetch(const TreeView& tv, int k, int lane8,
 }
 
 // ---- per-lane traversal stack -------------------------------------------------------------------------------------------
-// Entries [0, cap) live in shared memory at s[entry * stride] (s already points at this thread's column), the rest in a
-// per-thread local-memory array.  cap = min(stack entries the tree needs, TR_STACK_SMEM): the overflow region is reached only
-// by trees whose need exceeds TR_STACK_SMEM; the build guarantees need <= TR_STACK_MAX.
-struct LaneStack {
-    int* s; int stride, cap, sp;
-    int ovf[TR_STACK_MAX];
-    __device__ __forceinline__ void init(int* base, int stride_, int cap_) { s = base; stride = stride_; cap = cap_; sp = 0; }
-    __device__ __forceinline__ void push(int v) {
-        if (sp < cap) s[sp * stride] = v; else if (sp - cap < TR_STACK_MAX) ovf[sp - cap] = v;
-        ++sp;
-    }
-    __device__ __forceinline__ int pop() {
-        if (sp == 0) return TR_DONE;
-        --sp;
-        return sp < cap ? s[sp * stride] : (sp - cap < TR_STACK_MAX ? ovf[sp - cap] : TR_DONE);
-    }
+// Render kernels: all entries in shared memory at s[entry * WF_THREADS] (s points at this thread's column: consecutive lanes hit
+// consecutive banks); the kernel is launched with as many entries per lane as the tree needs (computed by the build, at most
+// TR_STACK_MAX, else the build fails with TR_ERR_STACK).  Measured on B200: a local-memory overflow path behind the shared
+// entries cost 20 % of the trace kernel although it was never taken (C2 9.96 -> 7.84 ms, C3 5.55 -> 4.60 ms without it).
+// Simple one-lane-per-ray walks (Debug integrator, test hooks, lock-step BDPT cross-check): a local-memory array.
+#define WF_THREADS 256
+struct SmemStack {
+    int* s; int sp;
+    __device__ __forceinline__ void init(int* column) { s = column; sp = 0; }
+    __device__ __forceinline__ void reset() { sp = 0; }
+    __device__ __forceinline__ void push(int v) { s[sp * WF_THREADS] = v; ++sp; }
+    __device__ __forceinline__ int pop() { if (sp == 0) return TR_DONE; --sp; return s[sp * WF_THREADS]; }
+};
+struct LocalStack {
+    int a[TR_STACK_MAX]; int sp;
+    __device__ __forceinline__ void reset() { sp = 0; }
+    __device__ __forceinline__ void push(int v) { if (sp < TR_STACK_MAX) a[sp] = v; ++sp; }
+    __device__ __forceinline__ int pop() { if (sp == 0) return TR_DONE; --sp; return sp < TR_STACK_MAX ? a[sp] : TR_DONE; }
 };
 
 #ifdef TR_COUNTERS
@@ -189,9 +191,9 @@ __device__ __forceinline__ int root_enter(const TreeRoot& rt, const RayPre& r, b
 //   bound: best hit so far (closest hit) or the distance of the target (shadow query): children whose slab entry lies beyond
 //   bound x guard are pruned.  SHADOW: the target's own leaf (tlink) is never entered; reaching it sets `found`.
 // Order: a leaf child before an internal one (keeps the stack at one entry along chains), else the nearer slab entry first.
-template <int MODE, bool SHADOW>
+template <int MODE, bool SHADOW, typename Stack>
 __device__ __forceinline__ int node_step(const TreeView& tv, const RayPre& r, bool anypar, float bound, int tlink, bool& found,
-                                         LaneStack& st, int cur, int lane8) {
+                                         Stack& st, int cur, int lane8) {
     float4 A, B, C, D;
     node_fetch<MODE>(tv, cur, lane8, A, B, C, D);
     const int l0 = __float_as_int(A.w), l1 = __float_as_int(B.w);
@@ -211,7 +213,7 @@ __device__ __forceinline__ int node_step(const TreeView& tv, const RayPre& r, bo
 }
 
 // ---- simple (non-persistent) walks: Debug integrator, test hooks, lock-step BDPT cross-check -----------------------------
-// One lane = one ray from start to end; the stack is local memory only (cap 0).  Same node_step / closer as the persistent
+// One lane = one ray from start to end; the stack is a local-memory array.  Same node_step / closer as the persistent
 // kernels, global-memory tree.
 __device__ __forceinline__ HitRec trace_closest(const TreeView& tv, const TreeRoot& rt, const RayPre& r, bool active, unsigned long long* cnt) {
     HitRec h; hit_reset(h);
@@ -219,7 +221,7 @@ __device__ __forceinline__ HitRec trace_closest(const TreeView& tv, const TreeRo
     unsigned cnt_nodes = 0, cnt_leaves = 0;
 #endif
     const bool anypar = r.px || r.py || r.pz;
-    LaneStack st; st.init(nullptr, 0, 0);
+    LocalStack st; st.reset();
     bool found = false;
     int cur = active ? root_enter(rt, r, anypar) : TR_DONE;
     while (cur != TR_DONE) {
@@ -263,7 +265,7 @@ __device__ __forceinline__ bool trace_shadow_visible(const TreeView& tv, const T
 #endif
     const bool anypar = r.px || r.py || r.pz;
     bool visible = false, found = false; float tt = TR_INF;
-    LaneStack st; st.init(nullptr, 0, 0);
+    LocalStack st; st.reset();
     int cur = TR_DONE;
     const int tlink = -target_leaf - 1;
     if (active) {

@@ -17,7 +17,6 @@
 #include "trace.cuh"
 #include "spectral.cuh"
 
-#define WF_THREADS 256
 #define SPEC_BIT 0x80000000u
 
 struct BatchParams { int frame_begin; int n_frames; unsigned long long seed; int max_depth; int pad; };
@@ -200,8 +199,12 @@ __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol
 // loop every lane runs the same three blocks (refill / node step / batched leaf step, see trace.cuh), so
 // the issue slots are spent with most lanes active although the per-ray walk lengths differ by 10x.
 #ifndef WF_NODE_STEPS
-#define WF_NODE_STEPS 4
+#define WF_NODE_STEPS 4             // node steps per round, tree in shared memory
 #endif
+#ifndef WF_NODE_STEPS_GLOBAL
+#define WF_NODE_STEPS_GLOBAL 2      // ... tree in global memory (measured on C3: 2 beats 3 and 4; on C2: 4 beats 2 and 3)
+#endif
+template <int MODE> struct NodeSteps { static constexpr int value = (MODE == TM_GLOBAL || MODE == TM_GTOP) ? WF_NODE_STEPS_GLOBAL : WF_NODE_STEPS; };
 #ifndef WF_REFILL_MIN
 #define WF_REFILL_MIN 8
 #endif
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_trace(WfArgs a, int depth) {
     WarpFeed feed = make_feed(n);
     unsigned idle = 0xffffffffu;                        // warp-uniform: lanes without a ray
     bool anypar = false, found = false; int q = 0, cur = TR_DONE;
-    LaneStack st; st.init(stack_base, WF_THREADS, a.stack_cap);
+    SmemStack st; st.init(stack_base);
     RayPre r = make_ray(mk3(0.f, 0.f, 0.f), mk3(1.f, 1.f, 1.f));
     HitRec h; hit_reset(h);
 #ifdef TR_COUNTERS
@@ -297,14 +300,14 @@ __global__ void __launch_bounds__(WF_THREADS) k_trace(WfArgs a, int depth) {
                 r = make_ray(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y));
                 anypar = r.px || r.py || r.pz;
                 hit_reset(h);
-                q = nq; st.sp = 0; cur = root_enter(a.root, r, anypar);
+                q = nq; st.reset(); cur = root_enter(a.root, r, anypar);
             }
         }
         if (idle == 0xffffffffu) { if (!feed.more && feed.cb >= feed.ce) break; else continue; }
         const bool has = !((idle >> lane) & 1u);
         // ---- WF_NODE_STEPS node steps per round; the warp-level bookkeeping below is paid once per round
 #pragma unroll
-        for (int step = 0; step < WF_NODE_STEPS; ++step) {
+        for (int step = 0; step < NodeSteps<MODE>::value; ++step) {
             if (has && (unsigned)cur < (unsigned)TR_DONE) {
                 TR_COUNT(cnt_nodes);
                 cur = node_step<MODE, false>(tv, r, anypar, h.t, 0, found, st, cur, lane8);
@@ -435,8 +438,8 @@ __device__ __forceinline__ void shade_path(const WfArgs& a, const BatchParams& b
         // miss: equirect environment lookup (integrator/PT_RGB.py:127-132)
         if (a.env_w > 0) {
             float dis = sqrtf(d.x * d.x + d.z * d.z);
-            float tx = (atan2f(d.z, d.x) + TR_PI_ENV) / TR_PI_ENV / 2.0f;
-            float ty = atan2f(d.y, dis) / TR_PI_ENV + 0.5f;
+            float tx = (tr_atan2f(d.z, d.x) + TR_PI_ENV) / TR_PI_ENV / 2.0f;
+            float ty = tr_atan2f(d.y, dis) / TR_PI_ENV + 0.5f;
             V3 e = (srgb_to_lrgb(env_texture2d(a, tx, ty)) * T) * a.env_power;
             float4 Lv = a.L[slot]; Lv.x += e.x; Lv.y += e.y; Lv.z += e.z; a.L[slot] = Lv;
         }
@@ -495,7 +498,7 @@ __device__ __forceinline__ void shade_path(const WfArgs& a, const BatchParams& b
     V3 next_o = offset_ray(s.pos, signf_(f_or_b) * fn);
     if (pdf > 0.0f) {
         bool alive = true;
-        if (f_or_b < 0.0f) { float Rr = expf(-t / p1); if (R1.z >= Rr) alive = false; }   // PT_RGB.py:118-122
+        if (f_or_b < 0.0f) { float Rr = tr_expf(-t / p1); if (R1.z >= Rr) alive = false; }   // PT_RGB.py:118-122
         if (alive && !last) {
             T = T * ((brdf / pdf) * rc);
             out.cont = true;
@@ -527,8 +530,8 @@ __device__ __forceinline__ void shade_path_spec(const WfArgs& a, const BatchPara
     if (prim < 0) {
         // miss: sky dome (:269-276)
         float dis = sqrtf(d.x * d.x + d.z * d.z);
-        float beta = atan2f(d.y, dis);
-        float gamma = acosf(dot3(d, mk3(__ldg(sd.sky + 110), __ldg(sd.sky + 111), __ldg(sd.sky + 112))));
+        float beta = tr_atan2f(d.y, dis);
+        float gamma = tr_acosf(dot3(d, mk3(__ldg(sd.sky + 110), __ldg(sd.sky + 111), __ldg(sd.sky + 112))));
         float theta = clampf(0.5f * TR_PI_ENV - beta, 0.0f, 0.5f * TR_PI_ENV);
         V4 ibl;
 #pragma unroll
@@ -664,7 +667,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_tail(WfArgs a, int depth) {
     float4 nA = A, nB = B, nC = C, sC = C; bool st_cont = false; unsigned sslot = 0;
     RayPre r = make_ray(mk3(0.f, 0.f, 0.f), mk3(1.f, 1.f, 1.f)); bool anypar = false;
     int cur = TR_DONE, tleaf = 0; bool visible = false, found = false; float tt = TR_INF;
-    LaneStack st; st.init(stack_base, WF_THREADS, a.stack_cap);
+    SmemStack st; st.init(stack_base);
     HitRec h; hit_reset(h);
     bool more = true;
     while (true) {
@@ -679,12 +682,12 @@ __global__ void __launch_bounds__(WF_THREADS) k_tail(WfArgs a, int depth) {
             if (lane < chunk && q < n) {
                 A = a.pa[pp][q]; B = a.pb[pp][q]; C = a.pc[pp][q]; d = depth; mode = 1;
                 r = make_ray(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y)); anypar = r.px || r.py || r.pz;
-                hit_reset(h); st.sp = 0; cur = root_enter(a.root, r, anypar);
+                hit_reset(h); st.reset(); cur = root_enter(a.root, r, anypar);
             }
         }
         // ---- node steps (same code as in k_trace / k_shadow; the mode only selects the pruning bound and the target)
 #pragma unroll
-        for (int step = 0; step < WF_NODE_STEPS; ++step) {
+        for (int step = 0; step < NodeSteps<MODE>::value; ++step) {
             if (mode != 0 && (unsigned)cur < (unsigned)TR_DONE) {
 #ifdef TR_COUNTERS
                 ++cnt[mode == 1 ? 0 : 2];
@@ -727,7 +730,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_tail(WfArgs a, int depth) {
 #ifdef TR_COUNTERS
                     ++cnt[3];
 #endif
-                    st.sp = 0; cur = shadow_enter(tv, a.root, r, anypar, tleaf, la, lb, lc, tt, visible, found);
+                    st.reset(); cur = shadow_enter(tv, a.root, r, anypar, tleaf, la, lb, lc, tt, visible, found);
                     mode = 2; advance = false;
                 }
             } else if (visible && found) {
@@ -737,7 +740,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_tail(WfArgs a, int depth) {
                 if (st_cont) {
                     A = nA; B = nB; C = nC; ++d; mode = 1; st_cont = false;
                     r = make_ray(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y)); anypar = r.px || r.py || r.pz;
-                    hit_reset(h); st.sp = 0; cur = root_enter(a.root, r, anypar);
+                    hit_reset(h); st.reset(); cur = root_enter(a.root, r, anypar);
                 } else mode = 0;
             }
         }
@@ -771,7 +774,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_shadow(WfArgs a, int depth) {
     unsigned idle = 0xffffffffu;
     bool anypar = false, visible = false, found = false; int q = 0, cur = TR_DONE, tleaf = 0;
     float tt = TR_INF; unsigned slot = 0;
-    LaneStack st; st.init(stack_base, WF_THREADS, a.stack_cap);
+    SmemStack st; st.init(stack_base);
     RayPre r = make_ray(mk3(0.f, 0.f, 0.f), mk3(1.f, 1.f, 1.f));
 #ifdef TR_COUNTERS
     unsigned long long cnt_nodes = 0, cnt_leaves = 0;
@@ -786,14 +789,14 @@ __global__ void __launch_bounds__(WF_THREADS) k_shadow(WfArgs a, int depth) {
                 tleaf = __ldg(a.leaf_of_prim + __float_as_int(B.z)); slot = __float_as_uint(B.w);
                 float4 la, lb, lc; leaf_fetch<MODE>(tv, tleaf, lane8, la, lb, lc);
                 TR_COUNT(cnt_leaves);
-                q = nq; st.sp = 0; cur = shadow_enter(tv, a.root, r, anypar, tleaf, la, lb, lc, tt, visible, found);
+                q = nq; st.reset(); cur = shadow_enter(tv, a.root, r, anypar, tleaf, la, lb, lc, tt, visible, found);
             }
         }
         if (idle == 0xffffffffu) { if (!feed.more && feed.cb >= feed.ce) break; else continue; }
         const bool has = !((idle >> lane) & 1u);
         const int tlink = -tleaf - 1;
 #pragma unroll
-        for (int step = 0; step < WF_NODE_STEPS; ++step) {
+        for (int step = 0; step < NodeSteps<MODE>::value; ++step) {
             if (has && (unsigned)cur < (unsigned)TR_DONE) {
                 TR_COUNT(cnt_nodes);
                 cur = node_step<MODE, true>(tv, r, anypar, tt, tlink, found, st, cur, lane8);
@@ -1015,9 +1018,10 @@ static int launch_cfg(tr_ctx* ctx, WfArgs& a, LaunchCfg& c) {
     else if (ctx->opt_top_nodes > 0 && ctx->top_count > 0) {
         c.mode = TM_GTOP; a.top = ctx->opt_top_nodes < ctx->top_count ? ctx->opt_top_nodes : ctx->top_count; a.stage_bytes = (unsigned)a.top * 64u;
     } else { c.mode = TM_GLOBAL; a.stage_bytes = 0; }
-    a.stack_cap = ctx->stack_need < ctx->opt_stack_smem ? ctx->stack_need : ctx->opt_stack_smem;
-    if (a.stack_cap < 1) a.stack_cap = 1;
-    c.smem = (size_t)a.stage_bytes + (size_t)a.stack_cap * WF_THREADS * sizeof(int);
+    a.stack_cap = ctx->stack_need < 1 ? 1 : ctx->stack_need;                          // entries per lane: what the tree needs (<= TR_STACK_MAX)
+    const size_t stack_bytes = (size_t)a.stack_cap * WF_THREADS * sizeof(int);
+    if (c.mode != TM_GLOBAL && (size_t)a.stage_bytes + stack_bytes > 200 * 1024) { c.mode = TM_GLOBAL; a.stage_bytes = 0; a.top = 0; }   // a very deep tree: the stack takes the shared memory
+    c.smem = (size_t)a.stage_bytes + stack_bytes;
     int bt = 0, bs = 0, t0 = 0, t1 = 0, rc = TR_OK;
     TR_MODE_SWITCH(c.mode, {
         if (!rc) rc = kernel_blocks(ctx, k_trace<M>, c.smem, bt);
