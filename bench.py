@@ -317,6 +317,18 @@ def measure_native(args, name, steps, warmup, rank, world, local, D, detail=True
         rays += int(st["rays_closest"]) + int(st["rays_shadow"]); launches += int(st["kernel_launches"])
     wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
+    # the film reduce on its own (N > 1): all ranks enter together, CUDA events around 5 back-to-back ncclReduce calls
+    reduce_ms = 0.0
+    if world > 1:
+        ctx.film_reduce(); torch.cuda.synchronize(local); D.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(5):
+                ctx.film_reduce()
+            e1.record(stream)
+        torch.cuda.synchronize(local)
+        reduce_ms = D.reduce([e0.elapsed_time(e1) / 5.0], "max")[0]
     per_rank = D.gather([ms / steps, rays / steps])
     ms_max = D.reduce([ms], "max")[0]
     rays_all, launches_all = D.reduce([rays, launches], "sum")
@@ -374,7 +386,7 @@ def measure_native(args, name, steps, warmup, rank, world, local, D, detail=True
            "vs_baseline": None, "dtype": "f32", "data": "reference assets (model/*.obj), counter-based RNG seed 0",
            "config": cfg, "rays_per_step": rays_all // steps,
            "per_rank": [{"rank": r, "ms_per_step": v[0], "rays_per_step": int(v[1])} for r, v in enumerate(per_rank)],
-           "wall_ms_per_step": wall / steps * 1e3, "clocks": clocks, "gpu_launches": launches_all,
+           "wall_ms_per_step": wall / steps * 1e3, "clocks": clocks, "gpu_launches": launches_all, "nccl_reduce_ms": reduce_ms,
            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
                    "ms_per_step": e2e_t / n_e2e * 1e3, "film_checksum": checksum},
            "bvh_build": {"primitives": int(scene.primitive_count), "device_ms": build_ms,

@@ -100,20 +100,15 @@ def test_degenerate_trees_trace(gpu_ctx):
 
 def test_full_size_cornell_per_pixel_vs_oracle(gpu_ctx, oracle_tables):
     """C2 at full size (512^2 x 64 spp, BASELINE configs[1]) per pixel against the oracle with the shared counter-based RNG
-    (the CPU port renders it in a few seconds): rel 1e-3 per pixel, <= 0.1 % outliers, ray counts within 1e-4"""
+    (the CPU port renders it in a few seconds): the 786 432 film words and both ray counts are identical"""
     W = H = 512
     scene, cam, integ = build_gpu_scene("cornell", W, H)
     st = integ.render_frames(64)
     g = integ.hdr.to_numpy()
     o = build_oracle_scene(oracle_tables("cornell"), W, H, fast=False)
     ref, cnt = o.render_pt_rgb(W, H, 0, 64)
-    err = np.abs(g - ref).max(axis=2)
-    tol = 1e-3 * np.maximum(1.0, ref.max(axis=2))
-    frac_bad = float((err > tol).mean())
-    assert frac_bad < 1e-3, frac_bad
-    assert abs(g.mean() - ref.mean()) < 1e-4 * ref.mean()
-    assert abs(int(st["rays_closest"]) - cnt["closest"]) <= 1e-4 * cnt["closest"]
-    assert abs(int(st["rays_shadow"]) - cnt["shadow"]) <= 1e-4 * cnt["shadow"]
+    assert np.array_equal(g, ref)
+    assert int(st["rays_closest"]) == cnt["closest"] and int(st["rays_shadow"]) == cnt["shadow"]
 
 
 def test_tree_modes_render_the_same_film(gpu_ctx):
@@ -229,3 +224,22 @@ def test_two_gpu_library_reduce(tmp_path):
     assert np.array_equal(r0["sum2"], full2) and np.array_equal(r0["sum4"], full4)
     assert np.array_equal(r0["all4"], full4) and np.array_equal(r1["all4"], full4)
     assert not np.array_equal(r1["sum4"], full4)         # a non-root rank keeps presenting its partial film after a rooted reduce
+
+
+def test_small_render_stress(gpu_ctx):
+    """regression guard for a flaky failure seen on B200: 150 small renders each of PT_RGB and PT_Spec (128^2, every path handed
+    to the tail kernel at depth 1) must give the same film every time (see the comment at k_tail in csrc/wavefront.cu)"""
+    import _native
+    from test_gpu_spectral import build_gpu_spectral
+    for build in (lambda: build_gpu_scene("cornell", 128, 128), lambda: build_gpu_spectral(128, 128)):
+        scene, cam, integ = build()
+        ctx = _native.context()
+        ref = None
+        for i in range(150):
+            ctx.film_clear(); cam.frame = 0; cam.frame_cpu[0] = 0
+            for _ in range(2):
+                integ.render(); cam.update_frame()
+            img = integ.hdr.to_numpy()
+            if ref is None:
+                ref = img
+            assert np.array_equal(img, ref, equal_nan=True), i

@@ -199,10 +199,10 @@ __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol
 // loop every lane runs the same three blocks (refill / node step / batched leaf step, see trace.cuh), so
 // the issue slots are spent with most lanes active although the per-ray walk lengths differ by 10x.
 #ifndef WF_NODE_STEPS
-#define WF_NODE_STEPS 4             // node steps per round, tree in shared memory
+#define WF_NODE_STEPS 3             // node steps per round, tree in shared memory (measured on C2: 3 beats 2, 4 and 6)
 #endif
 #ifndef WF_NODE_STEPS_GLOBAL
-#define WF_NODE_STEPS_GLOBAL 2      // ... tree in global memory (measured on C3: 2 beats 3 and 4; on C2: 4 beats 2 and 3)
+#define WF_NODE_STEPS_GLOBAL 2      // ... tree in global memory (measured on C3: 2 and 3 beat 1 and 4)
 #endif
 template <int MODE> struct NodeSteps { static constexpr int value = (MODE == TM_GLOBAL || MODE == TM_GTOP) ? WF_NODE_STEPS_GLOBAL : WF_NODE_STEPS; };
 #ifndef WF_REFILL_MIN
@@ -305,7 +305,10 @@ __global__ void __launch_bounds__(WF_THREADS) k_trace(WfArgs a, int depth) {
         }
         if (idle == 0xffffffffu) { if (!feed.more && feed.cb >= feed.ce) break; else continue; }
         const bool has = !((idle >> lane) & 1u);
-        // ---- WF_NODE_STEPS node steps per round; the warp-level bookkeeping below is paid once per round
+        // ---- node steps of a round; the warp-level bookkeeping below is paid once per round.  A lane that reaches a leaf waits
+        //      (parked, cur < 0) for the leaf step of the round.  (Measured and rejected: putting the leaf aside and walking on
+        //      from the stack within the round -- fewer idle slots, but the extra instructions per step cost more: C2 trace
+        //      7.48 -> 7.57 ms, C3 4.76 -> 4.97 ms.)
 #pragma unroll
         for (int step = 0; step < NodeSteps<MODE>::value; ++step) {
             if (has && (unsigned)cur < (unsigned)TR_DONE) {
@@ -644,8 +647,13 @@ __global__ void __launch_bounds__(WF_THREADS, SPEC ? 3 : WF_SHADE_MIN_BLOCKS) k_
 // (n / #warps) so that all resident warps work.  Same device functions and the same per-path operation order as the
 // wavefront stages (NEE terms are added to Lnee in depth order, after shadow(depth-1): the kernel is enqueued behind it),
 // so the film is bit-identical with or without the hand-over.
+// Register budget: the RGB instantiation fits 128 registers (2 CTAs per SM).  The spectral one needs ~200; capped at 128 it
+// spills, and that spilling build produced garbage tree links once in ~10 small renders on B200 (tools/stress_spec.py: film
+// words differ / illegal shared-memory address in leaf_fetch, while the same source built without the cap, or with an extra
+// printf, ran 600 renders clean; compute-sanitizer initcheck / racecheck found nothing in the source).  Cause not found
+// (ptxas 12.9 spill code is the suspect), so the spectral tail is built without spills: 1 CTA per SM.
 template <int MODE, bool SPEC>
-__global__ void __launch_bounds__(WF_THREADS) k_tail(WfArgs a, int depth) {
+__global__ void __launch_bounds__(WF_THREADS, SPEC ? 1 : 2) k_tail(WfArgs a, int depth) {
     grid_dep_wait();
     if (a.ctr->tail_from != depth) return;
     __shared__ unsigned long long bar;
@@ -696,6 +704,12 @@ __global__ void __launch_bounds__(WF_THREADS) k_tail(WfArgs a, int depth) {
                 else cur = node_step<MODE, true>(tv, r, anypar, tt, -tleaf - 1, found, st, cur, lane8);
             }
         }
+#ifdef TR_DEBUG_WALK
+        if (mode != 0 && cur != TR_DONE && (cur >= a.nint || cur < -a.nleaves || st.sp < 0 || st.sp > a.stack_cap)) {
+            printf("k_tail bad link %d (nint %d nleaves %d) sp %d cap %d mode %d d %d q %d n %d tid %d blk %d tleaf %d\n", cur, a.nint, a.nleaves, st.sp, a.stack_cap, mode, d, q, n, threadIdx.x, blockIdx.x, tleaf);
+            cur = TR_DONE; mode = 0;
+        }
+#endif
         // ---- leaf step
         if (mode != 0 && cur < 0) {
             const int k = -cur - 1;
