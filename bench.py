@@ -470,6 +470,11 @@ def pt_roofline(out, args, name, wl, ex, ctx, local, spp, paths_in_flight):
 
 
 def run_native(args):
+    # stdout carries exactly ONE JSON line: everything else this process (or a library it loads: NCCL prints its version banner
+    # at communicator creation) writes to file descriptor 1 goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import parallel
     rank, world, local = parallel.init_process_group("nccl" if args.gpus > 1 else None)
@@ -484,7 +489,8 @@ def run_native(args):
         out["workloads"] = {"teapot_mc": sub}
         out["gpu_launches_all_workloads"] = out["gpu_launches"] + sub["gpu_launches"]
     if rank == 0:
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         import torch.distributed as dist
         dist.barrier(); dist.destroy_process_group()
