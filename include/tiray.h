@@ -155,7 +155,9 @@ int tr_render_pt_spec(tr_ctx* ctx, int frame_begin, int n_frames, int max_depth,
  * 0 <= e+l-2 <= MAX_DEPTH = 5 (connect_path :436-580, Camera.get_image_point Camera.py:144-158) weighted by mis_weight
  * (:258-434), light-tracing (e == 1) contributions splatted across pixels, running mean into hdr.  Needs the view matrix of
  * tr_camera_set and at least one emitter.  With tile sharding every rank's hdr also receives that rank's splats on foreign
- * pixels, so the film reduce must be a SUM.  Synchronous per batch. */
+ * pixels, so the film reduce must be a SUM.  Asynchronous like tr_render_pt_rgb (tr_stats_get waits).  The e == 1 splats
+ * are accumulated with float atomics (as the reference does): their summation order, hence the last bits of the film, may differ
+ * from run to run; the e >= 2 strategies are summed in a fixed order. */
 int tr_render_bdpt_rgb(tr_ctx* ctx, int frame_begin, int n_frames, uint64_t seed);
 /* with "stage_timing" on: device time of the last tr_render_bdpt_rgb spent in the closest-hit kernels of the sub-path stages and
  * in the connection shadow-query kernel (CUDA events around every launch) */

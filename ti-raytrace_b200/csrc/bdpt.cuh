@@ -631,6 +631,8 @@ static int render_bdpt(tr_ctx* ctx, int frame_begin, int n_frames, uint64_t seed
     TR_CUDA(ctx, cudaSetDevice(ctx->device));
     WfArgs a; int rc;
     if ((rc = tr_stats_resolve(ctx))) return rc;
+    ctx->present_sum = false;
+    if (!ctx->h_ring) TR_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_ring, sizeof(TrCounters) * TR_MAX_CHAINS * TR_RING_BATCHES, cudaHostAllocDefault));
     if ((rc = fill_args(ctx, a, false))) return rc;
     if (ctx->nl <= 0) return tr_fail(ctx, TR_ERR_INVALID, "tr_render_bdpt_rgb: the scene has no emitter (Scene.sample_light needs one)");
     if (!ctx->view_set) return tr_fail(ctx, TR_ERR_INVALID, "tr_render_bdpt_rgb: tr_camera_set was called without the view matrix (Camera.get_image_point needs it)");
@@ -721,6 +723,16 @@ static int render_bdpt(tr_ctx* ctx, int frame_begin, int n_frames, uint64_t seed
         k_bdpt_film<<<cfg.grid_simple, WF_THREADS, 0, s>>>(a, b); ++launches;
         if (ev) cudaEventRecord(ev[4], s);
         TR_CHECK_LAUNCH(ctx);
+        // ray counters of this batch.  Asynchronous like PT_RGB: snapshot into the pinned ring (slot 0: the wavefront counters,
+        // slot 1: the four BDPT counters) and go on; tr_stats_get folds the snapshots.  Stage timing stays synchronous.
+        const int bi = f0 / F;
+        if (!timing && bi < TR_RING_BATCHES) {
+            TR_CUDA(ctx, cudaMemcpyAsync(ctx->h_ring + (size_t)bi * TR_MAX_CHAINS, ctx->d_ctr, sizeof(TrCounters), cudaMemcpyDeviceToHost, s));
+            TR_CUDA(ctx, cudaMemcpyAsync(ctx->h_ring + (size_t)bi * TR_MAX_CHAINS + 1, ctx->d_bd_ctr, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+            ctx->ring_batches = bi + 1;
+            if (bi + 1 == TR_RING_BATCHES && f0 + F < n_frames) TR_CUDA(ctx, cudaStreamSynchronize(s));     // ring full: later batches take the synchronous path
+            continue;
+        }
         unsigned long long hc[4];
         TR_CUDA(ctx, cudaMemcpyAsync(hc, ctx->d_bd_ctr, sizeof(hc), cudaMemcpyDeviceToHost, s));
         TR_CUDA(ctx, cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(TrCounters), cudaMemcpyDeviceToHost, s));
@@ -739,11 +751,11 @@ static int render_bdpt(tr_ctx* ctx, int frame_begin, int n_frames, uint64_t seed
         }
     }
     TR_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
-    TR_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
-    float ms = 0.0f; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-    ctx->stats.rays_closest = rays_c; ctx->stats.rays_shadow = rays_s;
+    ctx->stats.rays_closest = rays_c; ctx->stats.rays_shadow = rays_s; ctx->stats.shade_terminal = 0;
     ctx->stats.node_visits = vis[0]; ctx->stats.leaf_tests = vis[1]; ctx->stats.node_visits_shadow = vis[2]; ctx->stats.leaf_tests_shadow = vis[3];
-    ctx->stats.kernel_launches = launches; ctx->stats.ms_total = ms; ctx->stats.frames = n_frames; ctx->stats.paths_in_flight = (int)cap; ctx->stats.chains = 1;
+    ctx->stats.kernel_launches = launches; ctx->stats.ms_total = 0.0f; ctx->stats.frames = n_frames; ctx->stats.paths_in_flight = (int)cap; ctx->stats.chains = 1;
+    ctx->ring_mode = wave ? 1 : 2; ctx->ring_depth = BD_EYE_MAX - 1; ctx->stats_pending = true;            // tr_stats_resolve waits for ev1 and folds the ring
+    if (timing && (rc = tr_stats_resolve(ctx))) return rc;
     // stage timing: ms_trace = the sub-path stage, ms_shadow = the connection stage, ms_shade = items + film; the traversal
     // kernels alone (wavefront pipeline) are reported through tr_bdpt_kernel_ms
     ctx->stats.ms_trace = ms_paths; ctx->stats.ms_shade = ms_other; ctx->stats.ms_shadow = ms_connect;

@@ -114,7 +114,7 @@ struct tr_ctx {
     TrCounters* d_ctr = nullptr;          // TR_MAX_CHAINS entries
     TrCounters h_ctr[TR_MAX_CHAINS];
     // deferred statistics of an asynchronous render: per-batch counter snapshots land in a pinned ring, tr_stats_get folds them
-    TrCounters* h_ring = nullptr; int ring_batches = 0, ring_K = 0, ring_depth = 0; bool stats_pending = false;
+    TrCounters* h_ring = nullptr; int ring_batches = 0, ring_K = 0, ring_depth = 0, ring_mode = 0; bool stats_pending = false;   // ring_mode 0 PT, 1 BDPT wavefront, 2 BDPT lock-step
     float4* d_matlin = nullptr; bool matlin_ready = false;
     cudaStream_t sub_stream[TR_MAX_CHAINS] = {}; cudaEvent_t ev_join[TR_MAX_CHAINS] = {}; cudaEvent_t ev_fork = nullptr;
 
@@ -139,7 +139,7 @@ struct tr_ctx {
     int opt_smem_bvh = 1;
     int opt_chains = 2;
     int opt_shadow_overlap = 1;
-    int opt_tail_max = -1;          // hand-over threshold of k_tail: -1 = auto (a fraction of the chain's paths), 0 = never
+    int opt_tail_max = -1;          // hand-over threshold of k_tail (live paths of a chain): -1 = default (4096, measured on 8-way shards of C2 / C3), 0 = never
     int opt_tail_chunk = 8;
     int opt_bdpt_wavefront = 1;     // 0: lock-step BDPT pipeline (cross-check)
     int opt_top_nodes = 0;          // large trees: this many breadth-first top nodes are staged into shared memory per CTA (0 = off)

@@ -986,7 +986,7 @@ static int fill_args(tr_ctx* ctx, WfArgs& a, bool spec = false) {
     for (int k = 0; k < 2; ++k) { a.sa[k] = ctx->d_shq[k][0]; a.sb[k] = ctx->d_shq[k][1]; a.sc[k] = ctx->d_shq[k][2]; }
     a.L = ctx->d_L; a.Lnee = ctx->d_Lnee;
     a.ctr = ctx->d_ctr; a.bp = (const BatchParams*)ctx->d_batch_params;
-    a.frame_off = 0; a.sub_frames = 1 << 20; a.tail_max = ctx->opt_tail_max < 0 ? 16384 : ctx->opt_tail_max; a.tail_chunk = ctx->opt_tail_chunk < 1 ? 1 : ctx->opt_tail_chunk;
+    a.frame_off = 0; a.sub_frames = 1 << 20; a.tail_max = ctx->opt_tail_max < 0 ? 4096 : ctx->opt_tail_max; a.tail_chunk = ctx->opt_tail_chunk < 1 ? 1 : ctx->opt_tail_chunk;
     if (spec) { if ((rc = tr_spec_prepare(ctx))) return rc; a.spec = ctx->spec; }
     return TR_OK;
 }
@@ -1228,7 +1228,7 @@ static int render_wavefront(tr_ctx* ctx, int frame_begin, int n_frames, int max_
     ctx->stats.node_visits = vis[0]; ctx->stats.leaf_tests = vis[1]; ctx->stats.node_visits_shadow = vis[2]; ctx->stats.leaf_tests_shadow = vis[3];
     ctx->stats.kernel_launches = launches; ctx->stats.ms_total = 0.0f; ctx->stats.frames = n_frames; ctx->stats.paths_in_flight = (int)((size_t)F * a.npix); ctx->stats.chains = K;
     ctx->stats.ms_trace = ms_trace; ctx->stats.ms_shade = ms_shade; ctx->stats.ms_shadow = ms_shadow;
-    ctx->ring_K = K; ctx->ring_depth = max_depth; ctx->stats_pending = true;
+    ctx->ring_K = K; ctx->ring_depth = max_depth; ctx->ring_mode = 0; ctx->stats_pending = true;
     if (timing) return tr_stats_resolve(ctx);
     return TR_OK;
 }
@@ -1239,6 +1239,18 @@ int tr_stats_resolve(tr_ctx* ctx) {
     TR_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
     ctx->stats_pending = false;
     uint64_t rays_c = 0, rays_s = 0, vis[4] = {0, 0, 0, 0}, n_term = 0;
+    if (ctx->ring_mode != 0) {
+        // BDPT_RGB batches: slot 0 = wavefront counters (ring_depth sub-path stages, one connection-query stage), slot 1 = the
+        // BDPT counters (lock-step pipeline: closest / shadow traversals)
+        for (int b = 0; b < ctx->ring_batches; ++b) {
+            const TrCounters& c = ctx->h_ring[(size_t)b * TR_MAX_CHAINS];
+            const unsigned long long* hc = (const unsigned long long*)(ctx->h_ring + (size_t)b * TR_MAX_CHAINS + 1);
+            if (ctx->ring_mode == 1) { for (int d = 0; d < ctx->ring_depth; ++d) rays_c += (uint64_t)c.nq[d]; rays_s += (uint64_t)c.nshadow[0]; }
+            else { rays_c += hc[0]; rays_s += hc[1]; }
+            for (int k = 0; k < 4; ++k) vis[k] += c.visits[k];
+        }
+        ctx->ring_batches = 0; ctx->ring_K = 0;
+    }
     for (int b = 0; b < ctx->ring_batches; ++b) for (int j = 0; j < ctx->ring_K; ++j) {
         const TrCounters& c = ctx->h_ring[(size_t)b * TR_MAX_CHAINS + j];
         const int tf = c.tail_from;
