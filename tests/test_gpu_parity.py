@@ -377,7 +377,8 @@ def test_options_do_not_change_the_film(gpu_ctx):
     scene, cam, integ = build_gpu_scene("sphere", W, H, sphere_light=True, glass0=True, env_power=5.0)
     ref = None
     for opts in [dict(chains=1, shadow_overlap=0, tail_max=0, graph=0), dict(chains=4, shadow_overlap=1, tail_max=16384, graph=1),
-                 dict(chains=8, shadow_overlap=1, tail_max=100000000, graph=1, batch_frames=3), dict(chains=2, tail_max=64, batch_frames=1)]:
+                 dict(chains=8, shadow_overlap=1, tail_max=100000000, graph=1, batch_frames=3), dict(chains=2, tail_max=64, batch_frames=1),
+                 dict(chains=2, tail_max=4096, batch_frames=0, pdl=1, graph=1), dict(pdl=1, graph=0, shadow_overlap=0), dict(pdl=0)]:
         for k, v in opts.items():
             gpu_ctx.set_option(k, v)
         gpu_ctx.film_clear(); cam.frame = 0; cam.frame_cpu[0] = 0

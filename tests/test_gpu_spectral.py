@@ -78,15 +78,13 @@ def test_rgb2spec_and_sky_hooks_match_oracle(gpu_ctx, oracle_tables):
     ref = np.zeros((n, 4), np.float32)
     o.lib.orc_spec_srgb_to_spec(o.h, n, rgb.reshape(-1), lam0, ref.reshape(-1))
     g = gpu_ctx.test_srgb_to_spec(rgb, lam0)
-    # powf in srgb_to_lrgb may differ by an ulp, which moves the trilinear weights slightly
-    assert np.abs(g - ref).max() < 1e-4 and (g == ref).mean() > 0.8, (np.abs(g - ref).max(), (g == ref).mean())
+    assert np.array_equal(g, ref)                              # pow in srgb_to_lrgb comes from the shared header
     theta = rng.uniform(0.0, 1.5707963, n).astype(np.float32)
     gamma = rng.uniform(0.0, 3.14, n).astype(np.float32)
     wl = rng.uniform(300.0, 760.0, n).astype(np.float32)
     sref = np.zeros(n, np.float32); o.lib.orc_spec_sky_radiance(o.h, n, theta, gamma, wl, sref)
     sg = gpu_ctx.test_sky_radiance(theta, gamma, wl)
-    assert np.array_equal(sg == 0, sref == 0)
-    assert np.allclose(sg, sref, rtol=2e-5, atol=1e-7), np.abs(sg - sref).max()
+    assert np.array_equal(sg, sref)
 
 
 def test_pt_spec_cornell_matches_oracle(gpu_ctx, oracle_tables):
@@ -100,11 +98,9 @@ def test_pt_spec_cornell_matches_oracle(gpu_ctx, oracle_tables):
     st = gpu_ctx.stats()
     o = spectral_oracle(oracle_tables, W, H)
     ref, cnt = spectral.render_pt_spec(o, W, H, 0, 4)
-    frac_bad, mean_err = _compare_radiance(g, ref, rel=2e-3, outlier_budget=5e-3, floor=0.05)
-    assert frac_bad < 5e-3 and mean_err < 5e-3, (frac_bad, mean_err)
+    assert np.array_equal(g, ref, equal_nan=True)              # shared RNG + shared include/trmath.h: every bit of the film
     _, c3 = spectral.render_pt_spec(o, W, H, 3, 1)
-    assert abs(st["rays_closest"] - c3["closest"]) <= 1e-3 * c3["closest"]
-    assert abs(st["rays_shadow"] - c3["shadow"]) <= 1e-3 * c3["shadow"]
+    assert st["rays_closest"] == c3["closest"] and st["rays_shadow"] == c3["shadow"]
 
 
 def test_pt_spec_glass_and_rgb_materials_match_oracle(gpu_ctx, oracle_tables):
@@ -131,8 +127,7 @@ def test_pt_spec_glass_and_rgb_materials_match_oracle(gpu_ctx, oracle_tables):
     o.set_camera(cam.view_inv_np[0], cam.eye_np[0], cam.fx, cam.fy, cam.cx, cam.cy); o.process_normal(); spectral.attach(o, PKG)
     ref, cnt = spectral.render_pt_spec(o, W, H, 0, 4)
     assert cnt["closest"] > 4 * W * H and ref[..., 2].mean() > 0
-    frac_bad, mean_err = _compare_radiance(g, ref, rel=2e-3, outlier_budget=1e-2, floor=0.05)
-    assert frac_bad < 1e-2 and mean_err < 1e-2, (frac_bad, mean_err)
+    assert np.array_equal(g, ref, equal_nan=True)
 
 
 def test_pt_spec_batched_sharded_and_options(gpu_ctx):
@@ -199,13 +194,9 @@ def test_pt_spec_full_size_vs_oracle(gpu_ctx, oracle_tables):
     ref, cnt = spectral.render_pt_spec(o, W, H, 0, 64)
     ok = np.isfinite(hdr).all(axis=2) & np.isfinite(ref).all(axis=2)
     assert (~np.isfinite(hdr).all(axis=2)).sum() <= 16 and (~np.isfinite(ref).all(axis=2)).sum() <= 16
-    assert abs(st["rays_closest"] - cnt["closest"]) <= 1e-4 * cnt["closest"]
-    assert abs(st["rays_shadow"] - cnt["shadow"]) <= 1e-4 * cnt["shadow"]
-    g2, r2 = np.where(ok[..., None], hdr, 0.0), np.where(ok[..., None], ref, 0.0)
-    frac_bad, mean_err = _compare_radiance(g2, r2, rel=2e-3, outlier_budget=2e-2, floor=0.05)
-    # 64 frames of running mean: a path that flips a branch anywhere in the 64 samples marks its pixel
-    assert frac_bad < 2e-2 and mean_err < 2e-3, (frac_bad, mean_err)
-    hdr = g2
+    assert st["rays_closest"] == cnt["closest"] and st["rays_shadow"] == cnt["shadow"]
+    assert np.array_equal(hdr, ref, equal_nan=True)            # 786 432 film words, NaN pixels included
+    hdr = np.where(ok[..., None], hdr, 0.0)
     img = cv2.imread(os.path.join(GOLDEN, "spectral-cornellbox.png"))[:, :, ::-1].astype(np.float64) / 255.0
     y = np.clip(np.where(img < 0.04045, img / 12.92, ((img + 0.055) / 1.055) ** 2.4), 0.0, 0.999)
     a, b, c, d, e = 2.51, 0.03, 2.43, 0.59, 0.14
@@ -227,8 +218,7 @@ def test_sky_dome_example_matches_oracle_and_reference_image(gpu_ctx, oracle_tab
     g = ex.integrator.hdr.to_numpy()
     o = sky_dome_oracle(oracle_tables, 128, 128)
     ref, cnt = spectral.render_pt_spec(o, 128, 128, 0, 8)
-    frac_bad, mean_err = _compare_radiance(g, ref, rel=2e-3, outlier_budget=5e-3, floor=0.05)
-    assert frac_bad < 5e-3 and mean_err < 2e-3, (frac_bad, mean_err)
+    assert np.array_equal(g, ref, equal_nan=True)
     ex = sky_dome.example(512, 512, 64); ex.build_scene()
     ex.integrator.render_frames(256)
     UF.tone_map(0.5, ex.integrator.hdr, ex.integrator.rgb_film)

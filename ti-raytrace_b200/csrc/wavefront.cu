@@ -266,7 +266,7 @@ __device__ __forceinline__ void flush_retired(const WfArgs& a, int depth, const 
 
 template <int MODE>
 __global__ void __launch_bounds__(WF_THREADS) k_trace(WfArgs a, int depth) {
-    grid_dep_wait();
+    grid_dep_wait(); grid_dep_launch();
     if (tail_took_over(a, depth)) return;
     // surplus CTAs of a short queue leave BEFORE staging the tree (deep bounces, small shards: the per-stage floor)
     const int n = a.ctr->nq[depth];
@@ -606,6 +606,7 @@ __device__ __forceinline__ void shade_any(const WfArgs& a, const BatchParams& bp
 #endif
 template <bool SPEC>
 __global__ void __launch_bounds__(WF_THREADS, SPEC ? 3 : WF_SHADE_MIN_BLOCKS) k_shade(WfArgs a, int depth) {
+    grid_dep_wait(); grid_dep_launch();
     if (tail_took_over(a, depth)) return;
     const BatchParams bp = *a.bp;
     const int n0 = a.ctr->ncls[depth][0], n1 = a.ctr->ncls[depth][1], n2 = a.ctr->ncls[depth][2];
@@ -654,7 +655,7 @@ __global__ void __launch_bounds__(WF_THREADS, SPEC ? 3 : WF_SHADE_MIN_BLOCKS) k_
 // (ptxas 12.9 spill code is the suspect), so the spectral tail is built without spills: 1 CTA per SM.
 template <int MODE, bool SPEC>
 __global__ void __launch_bounds__(WF_THREADS, SPEC ? 1 : 2) k_tail(WfArgs a, int depth) {
-    grid_dep_wait();
+    grid_dep_wait(); grid_dep_launch();
     if (a.ctr->tail_from != depth) return;
     __shared__ unsigned long long bar;
     TreeView tv; int* stack_base;
@@ -774,7 +775,7 @@ __global__ void __launch_bounds__(WF_THREADS, SPEC ? 1 : 2) k_tail(WfArgs a, int
 // the nearest hit, -1 otherwise.
 template <int MODE, bool QUERY = false>
 __global__ void __launch_bounds__(WF_THREADS) k_shadow(WfArgs a, int depth) {
-    grid_dep_wait();
+    grid_dep_wait(); grid_dep_launch();
     if (tail_took_over(a, depth)) return;
     const int n = a.ctr->nshadow[depth];
     if ((long long)blockIdx.x * WF_THREADS >= (long long)n) return;          // surplus CTAs leave before staging the tree
@@ -1061,6 +1062,20 @@ static WfArgs chain_args(const WfArgs& a, int j, int fs) {
     return c;
 }
 
+// Launch of a wavefront stage.  pdl: programmatic dependent launch (cudaLaunchAttributeProgrammaticStreamSerialization): the
+// CTAs of this kernel may be scheduled while the previous kernel of the stream drains (every stage kernel triggers its dependents
+// at its very start and waits for its predecessor with griddepcontrol.wait before it reads anything), which hides the launch
+// latency between the ~45 dependent stages of a chain.
+template <typename... KArgs, typename... Args>
+static inline void wf_launch(bool pdl, void (*kern)(KArgs...), int grid, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(WF_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at; memset(&at, 0, sizeof(at));
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization; at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at; cfg.numAttrs = pdl ? 1u : 0u;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // one chain: generate, then max_depth x (trace, shade) on stream s, with shadow(d) on stream ss:
 //   shadow(d) needs shade(d) (its queue) and shadow(d-1) (it sums the NEE terms in depth order);
 //   shade(d+2) needs shadow(d) (the shadow queue is a ping-pong pair).
@@ -1074,21 +1089,22 @@ static int enqueue_chain(tr_ctx* ctx, const WfArgs& a, const LaunchCfg& c, int m
     k_generate<SPEC><<<c.grid_simple, WF_THREADS, 0, s>>>(a); ++*launches;
     for (int d = 0; d < max_depth; ++d) {
         if (ev) cudaEventRecord(ev[4 * d + 0], s);
-        TR_MODE_SWITCH(c.mode, (k_trace<M><<<c.grid_trace, WF_THREADS, c.smem, s>>>(a, d)));
+        const bool pdl = ctx->opt_pdl != 0 && !ev;
+        TR_MODE_SWITCH(c.mode, wf_launch(pdl && d > 0, k_trace<M>, c.grid_trace, c.smem, s, a, d));      // depth 0 follows k_generate (no trigger there)
         if (ev) cudaEventRecord(ev[4 * d + 1], s);
         if (split && d >= 2) TR_CUDA(ctx, cudaStreamWaitEvent(s, dep[2 * (d - 2) + 1], 0));
-        k_shade<SPEC><<<c.grid_simple, WF_THREADS, 0, s>>>(a, d);
+        wf_launch(pdl, k_shade<SPEC>, c.grid_simple, 0, s, a, d);
         if (ev) cudaEventRecord(ev[4 * d + 2], s);
         if (a.nl > 0) {
             if (split) { TR_CUDA(ctx, cudaEventRecord(dep[2 * d], s)); TR_CUDA(ctx, cudaStreamWaitEvent(ss, dep[2 * d], 0)); }
-            TR_MODE_SWITCH(c.mode, (k_shadow<M, false><<<c.grid_shadow, WF_THREADS, c.smem, ss>>>(a, d)));
+            TR_MODE_SWITCH(c.mode, wf_launch(pdl && !split, k_shadow<M, false>, c.grid_shadow, c.smem, ss, a, d));   // on its own stream it follows an event wait
             if (split) TR_CUDA(ctx, cudaEventRecord(dep[2 * d + 1], ss));
             ++*launches;
         }
         if (a.tail_max > 0 && d + 1 < max_depth) {
             // behind shadow(d) on the same stream: NEE terms stay in depth order; shade(d) (the hand-over decision) is done
             if (split && a.nl == 0) { TR_CUDA(ctx, cudaEventRecord(dep[2 * d], s)); TR_CUDA(ctx, cudaStreamWaitEvent(ss, dep[2 * d], 0)); }
-            TR_MODE_SWITCH(c.mode, (k_tail<M, SPEC><<<c.grid_tail[SPEC], WF_THREADS, c.smem, ss>>>(a, d + 1)));
+            TR_MODE_SWITCH(c.mode, wf_launch(pdl && a.nl > 0, k_tail<M, SPEC>, c.grid_tail[SPEC], c.smem, ss, a, d + 1));   // follows k_shadow(d) on ss
             ++*launches;
         }
         if (ev) cudaEventRecord(ev[4 * d + 3], s);

@@ -3,6 +3,11 @@
 mkdir -p gpurun_out
 timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/k_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/k_pytest.log
 tail -6 gpurun_out/k_pytest.log
+for o in "pdl=0" "pdl=1"; do for wl in cornell teapot_mc; do
+  timeout 200 python tools/perf_probe.py --reps 4 --workload $wl --opts $o 2>&1 | grep -v "libpng\|total light" | sed "s/^/[$o] /" >> gpurun_out/k_pdl.log
+  timeout 200 python tools/perf_probe.py --reps 4 --workload $wl --shard 0,8 --opts $o 2>&1 | grep -v "libpng\|total light" | sed "s/^/[$o shard 0,8] /" >> gpurun_out/k_pdl.log
+done; done
+cat gpurun_out/k_pdl.log
 timeout 900 python tools/parity_report.py 2>&1 | grep -v libpng > gpurun_out/k_parity.log; tail -14 gpurun_out/k_parity.log
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/k_launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/k_launches_bench.json 2> gpurun_out/k_launches_bench.err
 for wl in cornell teapot_mc16 spectral_box veach_bdpt; do
