@@ -66,6 +66,13 @@ int  tr_synchronize(tr_ctx* ctx);
  * context's own stream. */
 int  tr_stream_set(tr_ctx* ctx, void* cuda_stream);
 
+/* Page-lock a host array the caller keeps handing to the upload functions (e.g. the packed vertex table of a scene that is
+ * re-uploaded every frame): uploads of page-locked arrays are DMA'd straight from the caller's memory instead of being copied
+ * into the library's staging buffer first.  Purely an optimisation; the arrays are still only borrowed for the call.  No context
+ * needed; unregister before freeing the memory. */
+int tr_host_register(void* p, size_t bytes);
+int tr_host_unregister(void* p);
+
 /* ---- scene upload: replaces the from_numpy calls of Scene.setup_data_gpu (Scene.py:299-309) ---
  * vertex nv x 9 f32, prim np x 3 i32, material nm x 10 f32, shape ns x 10 f32 (may be NULL, ns=0),
  * light nl i32 (may be NULL, nl=0): exactly the tables packed at Scene.py:225-273. */

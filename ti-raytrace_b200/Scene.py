@@ -108,6 +108,8 @@ class Scene:
                 s.fillStruct(self.shape_np, i)
         else:
             self.shape_np = np.zeros((1, SCD.SHA_VEC_SIZE), np.float32)
+        # the big tables are re-uploaded by every setup_data_gpu(): page-lock them once so the upload is a direct DMA
+        self._pins = [_native.pin_array(self.vertex_np), _native.pin_array(self.primitive_np)]
         self.bvh = LBvh.Bvh(self.primitive_count, self.minboundarynp, self.maxboundarynp)
         self.bvh.setup_data_cpu()
         if self.env_power == 0.0:

@@ -31,6 +31,8 @@ SIGNATURES = {
     "tr_last_error": (C.c_char_p, [_vp]),
     "tr_device_count": (C.c_int, []),
     "tr_synchronize": (C.c_int, [_vp]),
+    "tr_host_register": (C.c_int, [_vp, C.c_size_t]),
+    "tr_host_unregister": (C.c_int, [_vp]),
     "tr_stream_set": (C.c_int, [_vp, _vp]),
     "tr_scene_upload": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp]),
     "tr_material_upload": (C.c_int, [_vp, _vp, C.c_int]),
@@ -123,6 +125,28 @@ def _ptr(a):
 def _f(a, shape=None):
     a = np.ascontiguousarray(a, np.float32)
     return a if shape is None else a.reshape(shape)
+
+
+def pin_array(a):
+    """Best effort: page-lock the memory of a numpy array that will be uploaded repeatedly (Scene's packed tables), so that
+    tr_scene_upload DMAs from it directly.  Returns a finalizer-carrying token to keep next to the array (unregisters when
+    dropped), or None when there is no device / library (CPU-only use of the host classes) or the array is small."""
+    import weakref
+    if a is None or a.nbytes < (1 << 20) or not a.flags["C_CONTIGUOUS"]:
+        return None
+    try:
+        lib = load_library()
+        if lib.tr_device_count() <= 0 or lib.tr_host_register(a.ctypes.data, a.nbytes) != 0:
+            return None
+    except Exception:
+        return None
+
+    class _Pin:
+        pass
+    tok = _Pin(); addr = a.ctypes.data
+    weakref.finalize(tok, lambda: lib.tr_host_unregister(addr))
+    tok.array = a                           # the registration lives exactly as long as the array is reachable through the token
+    return tok
 
 
 class Context:

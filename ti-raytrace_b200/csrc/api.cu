@@ -19,6 +19,20 @@ extern "C" {
 
 const char* tr_last_error(tr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
 
+int tr_host_register(void* p, size_t bytes) {
+    if (!p || bytes == 0) return tr_fail(nullptr, TR_ERR_INVALID, "tr_host_register: NULL or empty range");
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return TR_OK; }
+    if (e != cudaSuccess) { cudaGetLastError(); return tr_fail(nullptr, TR_ERR_CUDA, "cudaHostRegister: %s", cudaGetErrorString(e)); }
+    return TR_OK;
+}
+int tr_host_unregister(void* p) {
+    if (!p) return TR_ERR_INVALID;
+    cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) { cudaGetLastError(); return tr_fail(nullptr, TR_ERR_CUDA, "cudaHostUnregister: %s", cudaGetErrorString(e)); }
+    return TR_OK;
+}
+
 int tr_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -132,9 +146,22 @@ static int stage_reserve(tr_ctx* ctx, size_t bytes) {
     }
     return TR_OK;
 }
-// copy `bytes` from the caller's array into the staging buffer and enqueue the DMA to dst (reserve the total first)
+// true when the caller's array already is page-locked (tr_host_register, or any cudaHostAlloc / cudaHostRegister memory)
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+// copy `bytes` from the caller's array into the staging buffer and enqueue the DMA to dst (reserve the total first).
+// Page-locked source arrays (>= 64 KB) skip the staging copy: the DMA reads them directly and stage_commit waits for it, so the
+// arrays are still only borrowed for the duration of the call.
 static int stage_upload(tr_ctx* ctx, void* dst, const void* src, size_t bytes) {
     if (bytes == 0) return TR_OK;
+    if (bytes >= (64u << 10) && is_pinned(src)) {
+        TR_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->stage_direct = true;
+        return TR_OK;
+    }
     char* h = ctx->h_stage + ctx->stage_used;
     memcpy(h, src, bytes);
     ctx->stage_used += (bytes + 255) & ~(size_t)255;
@@ -144,6 +171,11 @@ static int stage_upload(tr_ctx* ctx, void* dst, const void* src, size_t bytes) {
 static int stage_commit(tr_ctx* ctx) {
     TR_CUDA(ctx, cudaEventRecord(ctx->ev_stage, ctx->stream));
     ctx->stage_busy = true;
+    if (ctx->stage_direct) {                      // a DMA is reading the caller's own (page-locked) array: wait until it has
+        ctx->stage_direct = false;
+        TR_CUDA(ctx, cudaEventSynchronize(ctx->ev_stage));
+        ctx->stage_busy = false;
+    }
     return TR_OK;
 }
 }  // extern "C"

@@ -93,7 +93,7 @@ struct tr_ctx {
     float* d_hdr_sum = nullptr; bool present_sum = false;
     void* nccl_comm = nullptr; int comm_rank = 0, comm_nranks = 1;
     // pinned host memory: upload staging (bump allocator), film download target, LBVH build status
-    char* h_stage = nullptr; size_t stage_cap = 0, stage_used = 0; bool stage_busy = false; cudaEvent_t ev_stage = nullptr;
+    char* h_stage = nullptr; size_t stage_cap = 0, stage_used = 0; bool stage_busy = false, stage_direct = false; cudaEvent_t ev_stage = nullptr;
     float* h_film = nullptr; size_t film_host_cap = 0;
     int* h_build_status = nullptr;
     // first-hit buffers (Debug integrator)

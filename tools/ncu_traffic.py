@@ -48,6 +48,8 @@ def main():
                                    "dram_throughput_pct_of_peak": g("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
                                    "warps_active_pct": g("sm__warps_active.avg.pct_of_peak_sustained_active"),
                                    "shared_bank_conflicts": g("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum")}
+                # the bound that matters for these kernels: fraction of the lane-issue peak (issue slots busy x lanes active per instruction)
+                out["ncu_full"]["lane_issue_frac"] = out["ncu_full"]["issue_active_pct"] / 100.0 * out["ncu_full"]["threads_per_instruction"] / 32.0
                 break
     print(json.dumps(out, indent=1))
 
