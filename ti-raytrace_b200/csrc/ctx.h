@@ -32,7 +32,7 @@ struct TrNode2 { float4 a, b, c, d; };
 //   kind 2: shape that never intersects (Scene.py:597-598)
 struct TrLeaf { float4 a, b, c; };
 // Shading record per primitive, 96 B (built lazily: process_normal may rewrite normals)
-//   q0 = (v1, as_float(mat)), q1 = (v2, as_float(kind)), q2 = (v3, area), q3..q5 = (n1), (n2), (n3)
+//   q0 = (v1, as_float(mat)), q1 = (v2, as_float(kind)), q2 = (v3, area), q3..q5 = (n1, gn.x), (n2, gn.y), (n3, gn.z); gn = geometric normal
 //   sphere: q0 = (centre, mat), q1 = (radius,0,0,kind=1), q2 = (0,0,0,area)
 struct TrShade { float4 q[6]; };
 
@@ -143,6 +143,7 @@ struct tr_ctx {
     int opt_tail_chunk = 8;
     int opt_bdpt_wavefront = 1;     // 0: lock-step BDPT pipeline (cross-check)
     int opt_top_nodes = 0;          // large trees: this many breadth-first top nodes are staged into shared memory per CTA (0 = off)
+    int opt_chain_skew = 0;         // two chains: percent of a batch's frames given to chain 0 (0 = even split)
     int opt_pdl = 0;                // programmatic dependent launch between the stages of a chain
     int opt_replicas = 1;           // small trees: bank-conflict-free 8-replica shared-memory image
     size_t opt_max_paths = (size_t)20 << 20;   // path slots per batch (188 B each): more paths in flight amortise the per-stage tails

@@ -362,8 +362,7 @@ __device__ __forceinline__ Surf surface_at(const WfArgs& a, int prim, float u, f
         float4 q3 = __ldg(q + 3), q4 = __ldg(q + 4), q5 = __ldg(q + 5);
         V3 v1 = f4xyz(q0), v2 = f4xyz(q1), v3 = f4xyz(q2);
         float aa = 1.0f - u - v, bb = u, cc = v;
-        V3 v13 = v3 - v1, v12 = v2 - v1;
-        s.gn = normalize3(cross3(v12, v13));
+        s.gn = mk3(q3.w, q4.w, q5.w);                      // normalize((v2 - v1) x (v3 - v1)), precomputed per primitive by k_shade_table
         s.pos = (aa * v1 + bb * v2) + cc * v3;
         s.n = normalize3((aa * f4xyz(q3) + bb * f4xyz(q4)) + cc * f4xyz(q5));
     } else {
@@ -918,9 +917,12 @@ __global__ void k_shade_table(const float* __restrict__ vertex, const int* __res
         s.q[0] = make_float4(v1.x, v1.y, v1.z, __int_as_float(mat));
         s.q[1] = make_float4(v2.x, v2.y, v2.z, __int_as_float(0));
         s.q[2] = make_float4(v3.x, v3.y, v3.z, area);
-        s.q[3] = make_float4(p[3], p[4], p[5], 0.0f);
-        s.q[4] = make_float4(p[12], p[13], p[14], 0.0f);
-        s.q[5] = make_float4(p[21], p[22], p[23], 0.0f);
+        // geometric normal of Scene.intersect_prim (Scene.py:547-549), same expression as the per-hit evaluation it replaces
+        V3 v13 = v3 - v1, v12 = v2 - v1;
+        V3 gn = normalize3(cross3(v12, v13));
+        s.q[3] = make_float4(p[3], p[4], p[5], gn.x);
+        s.q[4] = make_float4(p[12], p[13], p[14], gn.y);
+        s.q[5] = make_float4(p[21], p[22], p[23], gn.z);
     } else {
         const float* sp = shape + (size_t)vi * 10;
         int st = (int)sp[0];
@@ -1051,14 +1053,14 @@ static int launch_cfg(tr_ctx* ctx, WfArgs& a, LaunchCfg& c) {
     return TR_OK;
 }
 
-// per-chain view of the queues: chain j of K renders local frames [j*fs, (j+1)*fs) with its own queue region + counters
-static WfArgs chain_args(const WfArgs& a, int j, int fs) {
+// per-chain view of the queues: chain j renders local frames [f0, f0 + nfr) of the batch with its own queue region + counters
+static WfArgs chain_args(const WfArgs& a, int j, int f0, int nfr) {
     WfArgs c = a;
-    size_t off = (size_t)j * fs * a.npix;
+    size_t off = (size_t)f0 * a.npix;
     for (int k = 0; k < 2; ++k) { c.pa[k] = a.pa[k] + off; c.pb[k] = a.pb[k] + off; c.pc[k] = a.pc[k] + off; }
-    c.hit = a.hit + off; c.cls = a.cls + 3 * off; c.cap = (size_t)fs * a.npix;
+    c.hit = a.hit + off; c.cls = a.cls + 3 * off; c.cap = (size_t)nfr * a.npix;
     for (int k = 0; k < 2; ++k) { c.sa[k] = a.sa[k] + off; c.sb[k] = a.sb[k] + off; c.sc[k] = a.sc[k] + off; }
-    c.ctr = a.ctr + j; c.frame_off = j * fs; c.sub_frames = fs;
+    c.ctr = a.ctr + j; c.frame_off = f0; c.sub_frames = nfr;
     return c;
 }
 
@@ -1129,8 +1131,14 @@ static int enqueue_batch(tr_ctx* ctx, const WfArgs& a, const LaunchCfg& c, int m
         TR_CUDA(ctx, cudaEventRecord(ctx->ev_fork, s));
         for (int j = 1; j < K; ++j) TR_CUDA(ctx, cudaStreamWaitEvent(ctx->sub_stream[j], ctx->ev_fork, 0));
     }
+    // frames per chain: even split, or (two chains, option "chain_skew" = percent of the frames for chain 0) an uneven one, so that
+    // the chains do not reach their thin, latency-bound deep stages at the same time
+    int f0 = 0;
     for (int j = 0; j < K; ++j) {
-        WfArgs cj = chain_args(a, j, fs);
+        int nfr = fs;
+        if (K == 2 && ctx->opt_chain_skew > 0) { const int n0 = max(1, min(2 * fs - 1, (2 * fs * ctx->opt_chain_skew + 50) / 100)); nfr = j == 0 ? n0 : 2 * fs - n0; }
+        WfArgs cj = chain_args(a, j, f0, nfr);
+        f0 += nfr;
         cudaStream_t sj = (j == 0) ? s : ctx->sub_stream[j];
         cudaStream_t ssj = (ev || !ctx->opt_shadow_overlap) ? sj : ctx->shadow_stream[j];
         if ((rc = enqueue_chain<SPEC>(ctx, cj, c, max_depth, sj, ssj, ctx->dep_ev.data() + (size_t)j * 2 * (TR_MAX_DEPTH_CAP + 1), launches, K == 1 ? ev : nullptr))) return rc;
