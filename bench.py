@@ -378,13 +378,13 @@ def measure_native(args, name, steps, warmup, rank, world, local, D, detail=True
     h2d_all, d2h_all = (int(v) for v in D.reduce([h2d, d2h], "sum"))
     e2e_value = e2e_rays / e2e_t / 1e6
 
-    cfg = workload_config(wl)
-    cfg.update({"paths_in_flight": paths_in_flight,
-                "tile_shard": "32x32 tiles, rank=(tx+3ty)%N, 1 ncclReduce per step (tr_film_reduce)" if world > 1 else "none"})
+    cfg = workload_config(wl)                # identical to the reference arm's `config`: same workload, same samples per step
     out = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
            "ms_per_step": ms_max / steps, "ms_per_spp": ms_max / steps / spp, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f32", "data": "reference assets (model/*.obj), counter-based RNG seed 0",
            "config": cfg, "rays_per_step": rays_all // steps,
+           "run": {"paths_in_flight": paths_in_flight,
+                   "tile_shard": "32x32 tiles, rank=(tx+3ty)%N, 1 ncclReduce per step (tr_film_reduce)" if world > 1 else "none"},
            "per_rank": [{"rank": r, "ms_per_step": v[0], "rays_per_step": int(v[1])} for r, v in enumerate(per_rank)],
            "wall_ms_per_step": wall / steps * 1e3, "clocks": clocks, "gpu_launches": launches_all, "nccl_reduce_ms": reduce_ms,
            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,

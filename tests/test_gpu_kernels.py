@@ -243,3 +243,34 @@ def test_small_render_stress(gpu_ctx):
             if ref is None:
                 ref = img
             assert np.array_equal(img, ref, equal_nan=True), i
+
+
+def test_full_size_teapot_mc_per_pixel_vs_oracle(gpu_ctx, oracle_tables):
+    """C3 at full size (1024^2, the 130 720-triangle scene with the environment map, the sphere light and smoothed normals,
+    BASELINE configs[2]) per pixel against the oracle: 2 spp, every film word and both ray counts identical"""
+    W = H = 1024
+    scene, cam, integ = build_gpu_scene("teapot_mc", W, H, sphere_light=True, env_power=5.0)
+    scene.process_normal()
+    st = integ.render_frames(2)
+    g = integ.hdr.to_numpy()
+    o = build_oracle_scene(oracle_tables("teapot_mc", sphere_light=True), W, H, env_power=5.0, fast=False)
+    o.process_normal()
+    ref, cnt = o.render_pt_rgb(W, H, 0, 2)
+    assert np.array_equal(g, ref, equal_nan=True)
+    assert int(st["rays_closest"]) == cnt["closest"] and int(st["rays_shadow"]) == cnt["shadow"]
+
+
+def test_registered_host_tables_upload_directly(gpu_ctx):
+    """page-locked caller arrays (tr_host_register, what Scene does with its packed tables) are uploaded by direct DMA: same tree,
+    same film as with pageable arrays"""
+    import _native
+    scene, cam, integ = build_gpu_scene("teapot", 64, 64)
+    assert any(p is not None for p in scene._pins)               # the 25 200-triangle vertex table is above the 1 MiB threshold
+    integ.render_frames(2); a = integ.hdr.to_numpy()
+    comp = scene.bvh.compact_node.to_numpy()
+    scene._pins = []                                             # drop the registrations: pageable path
+    import gc; gc.collect()
+    scene.setup_data_gpu(); cam.dirty = True
+    gpu_ctx.film_clear(); cam.frame = 0; cam.frame_cpu[0] = 0
+    integ.render_frames(2)
+    assert np.array_equal(integ.hdr.to_numpy(), a) and np.array_equal(scene.bvh.compact_node.to_numpy(), comp)

@@ -644,6 +644,7 @@ static int render_bdpt(tr_ctx* ctx, int frame_begin, int n_frames, uint64_t seed
     const size_t npix = (size_t)(a.npix > 0 ? a.npix : 1);
     int F = ctx->opt_batch_frames > 0 ? ctx->opt_batch_frames : (int)(budget / npix);
     if (F < 1) F = 1; if (F > n_frames) F = n_frames;
+    if (ctx->opt_batch_frames <= 0) { const int nb = (n_frames + F - 1) / F; F = (n_frames + nb - 1) / nb; }     // equal batches
     const size_t cap = (size_t)F * npix;
     if (cap >= ((size_t)1 << 26)) return tr_fail(ctx, TR_ERR_INVALID, "tr_render_bdpt_rgb: %zu samples per batch exceed the queue encoding (2^26)", cap);
     if (cap > ctx->bd_cap) {

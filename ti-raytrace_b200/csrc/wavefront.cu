@@ -1169,6 +1169,10 @@ static int render_wavefront(tr_ctx* ctx, int frame_begin, int n_frames, int max_
     if (F <= 0) { F = (int)(ctx->opt_max_paths / (size_t)a.npix); if (F < 1) F = 1; }     // auto: as many frames per batch as the path budget allows
     while (F > 1 && (size_t)F * a.npix > ctx->opt_max_paths) --F;
     if (F > n_frames) F = n_frames;
+    if (ctx->opt_batch_frames <= 0) {                                  // auto: equal batches instead of full ones plus a small rest (64 spp of C3: 4 x 16, not 3 x 20 + 4)
+        const int nb = (n_frames + F - 1) / F;
+        F = (n_frames + nb - 1) / nb;
+    }
     const bool timing = ctx->opt_stage_timing != 0;
     int K = timing ? 1 : ctx->opt_chains;
     if (K < 1) K = 1; if (K > TR_MAX_CHAINS) K = TR_MAX_CHAINS; if (K > F) K = F;
