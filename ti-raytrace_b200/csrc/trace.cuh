@@ -5,16 +5,17 @@
 // Here:
 //   * traversal nodes (TrNode2, 64 B) hold the boxes of BOTH children of an internal node, so one dependent load serves two
 //     slab tests and the chain of dependent loads per ray is halved;
-//   * the per-lane stack lives in SHARED memory ([entry][thread]: conflict free), with a local-memory overflow region that
-//     only degenerate trees touch; a leaf child is always taken before an internal one, so chains of duplicate Morton codes
-//     (the reference's duplicate rule builds them) need one entry, and the build rejects trees that need more than
-//     TR_STACK_MAX entries with the reference's "overflow, need larger stack" (Scene.py:741-742);
+//   * the per-lane stack lives in SHARED memory ([entry][thread]: conflict free), sized at launch to what the tree can need;
+//     a leaf child is always taken before an internal one, so chains of duplicate Morton codes (the reference's duplicate rule
+//     builds them) need one entry, and the build rejects trees that need more than TR_STACK_MAX entries with the reference's
+//     "overflow, need larger stack" (Scene.py:741-742);
 //   * of two hit children the one whose slab entry is nearer is visited first, and sub-trees whose slab entry lies beyond the
 //     best hit (relative guard band, so exact / near ties are still tested) are pruned;
 //   * small trees are staged whole into shared memory by TMA (cp.async.bulk) as a bank-conflict-free image: every 16-byte
 //     word is replicated 8 times in a 128-byte row and lane l reads column l & 7, so the 8 lanes of a quarter-warp (the unit
 //     a 128-bit shared load is served in) always touch 8 different bank quads whatever nodes they are at; medium trees are
-//     staged once (plain); of large trees the breadth-first top is staged, the rest is read from global memory.
+//     staged once (plain); large trees are read from global memory (L1 / L2), optionally with their breadth-first top staged
+//     (option "top_nodes": built and measured, slower than L1 on B200, off by default).
 // The result is the reference's: the slab arithmetic (UtilsFunc.py:494-523) and Moller-Trumbore (Scene.py:603-638) are
 // restated operation by operation, every internal node's box is tested before its children are entered, and among equal-t
 // hits the reference's winner is kept explicitly (it pops the right child first and accepts strict t < best, so the LARGEST
