@@ -353,7 +353,7 @@ int tr_set_option(tr_ctx* ctx, const char* name, int value) {
         {"batch_frames", &ctx->opt_batch_frames, 0, 1 << 20}, {"stage_timing", &ctx->opt_stage_timing, 0, 1}, {"graph", &ctx->opt_graph, 0, 1},
         {"smem_bvh", &ctx->opt_smem_bvh, 0, 1}, {"chains", &ctx->opt_chains, 1, TR_MAX_CHAINS}, {"shadow_overlap", &ctx->opt_shadow_overlap, 0, 1},
         {"tail_max", &ctx->opt_tail_max, -1, 1 << 30}, {"tail_chunk", &ctx->opt_tail_chunk, 1, 32}, {"bdpt_wavefront", &ctx->opt_bdpt_wavefront, 0, 1},
-        {"top_nodes", &ctx->opt_top_nodes, 0, 1 << 16}, {"pdl", &ctx->opt_pdl, 0, 1}, {"replicas", &ctx->opt_replicas, 0, 1}, {"chain_skew", &ctx->opt_chain_skew, 0, 95},
+        {"top_nodes", &ctx->opt_top_nodes, 0, 1 << 16}, {"pdl", &ctx->opt_pdl, 0, 1}, {"replicas", &ctx->opt_replicas, 0, 1}, {"chain_skew", &ctx->opt_chain_skew, 0, 95}, {"persist_blocks", &ctx->opt_persist_blocks, 0, 8},
     };
     bool found = false;
     for (const Opt& o : opts) if (!strcmp(name, o.name)) {

@@ -144,6 +144,7 @@ struct tr_ctx {
     int opt_bdpt_wavefront = 1;     // 0: lock-step BDPT pipeline (cross-check)
     int opt_top_nodes = 0;          // large trees: this many breadth-first top nodes are staged into shared memory per CTA (0 = off)
     int opt_chain_skew = 65;        // two chains: percent of a batch's frames given to chain 0 (0 = even split); 65: their thin deep stages do not coincide
+    int opt_persist_blocks = 0;     // cap on the resident CTAs per SM of the persistent trace / shadow kernels (0 = what fits)
     int opt_pdl = 0;                // programmatic dependent launch between the stages of a chain
     int opt_replicas = 1;           // small trees: bank-conflict-free 8-replica shared-memory image
     size_t opt_max_paths = (size_t)20 << 20;   // path slots per batch (188 B each): more paths in flight amortise the per-stage tails

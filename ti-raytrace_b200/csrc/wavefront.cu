@@ -1048,6 +1048,7 @@ static int launch_cfg(tr_ctx* ctx, WfArgs& a, LaunchCfg& c) {
     });
     if (rc) return rc;
     c.grid_tail[0] = ctx->num_sms * t0; c.grid_tail[1] = ctx->num_sms * t1;        // the tail kernel deals its paths over the warps that are resident at once
+    if (ctx->opt_persist_blocks > 0) { bt = bt < ctx->opt_persist_blocks ? bt : ctx->opt_persist_blocks; bs = bs < ctx->opt_persist_blocks ? bs : ctx->opt_persist_blocks; }   // leave SM slots to the other chain's kernels
     c.grid_trace = ctx->num_sms * bt; c.grid_shadow = ctx->num_sms * bs;
     c.grid_simple = ctx->num_sms * 8;
     return TR_OK;
