@@ -165,17 +165,6 @@ struct SmemStack {
     __device__ __forceinline__ void push(int v) { s[sp * WF_THREADS] = v; ++sp; }
     __device__ __forceinline__ int pop() { if (sp == 0) return TR_DONE; --sp; return s[sp * WF_THREADS]; }
 };
-// Stack of the closest-hit kernel: entries [sb, sp).  An idle lane of the warp may take the OLDEST entry (steal_bottom: the pending
-// sub-tree nearest to the root, i.e. the largest one) of a busy lane's ray -- see the work-stealing block of k_trace.
-struct StealStack {
-    int* s; int sp, sb;
-    __device__ __forceinline__ void init(int* column) { s = column; sp = sb = 0; }
-    __device__ __forceinline__ void reset() { sp = sb = 0; }
-    __device__ __forceinline__ void push(int v) { s[sp * WF_THREADS] = v; ++sp; }
-    __device__ __forceinline__ int pop() { if (sp == sb) return TR_DONE; --sp; return s[sp * WF_THREADS]; }
-    __device__ __forceinline__ int pending() const { return sp - sb; }
-    __device__ __forceinline__ int steal_bottom() { int v = s[sb * WF_THREADS]; ++sb; return v; }
-};
 struct LocalStack {
     int a[TR_STACK_MAX]; int sp;
     __device__ __forceinline__ void reset() { sp = 0; }

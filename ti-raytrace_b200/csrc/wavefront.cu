@@ -208,9 +208,6 @@ template <int MODE> struct NodeSteps { static constexpr int value = (MODE == TM_
 #ifndef WF_REFILL_MIN
 #define WF_REFILL_MIN 8
 #endif
-#ifndef WF_STEAL
-#define WF_STEAL 1                  // intra-warp work stealing at the end of the queue in k_trace (see there)
-#endif
 
 struct WarpFeed { int cb, ce, chunk; bool more; };
 
@@ -288,13 +285,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_trace(WfArgs a, int depth) {
     WarpFeed feed = make_feed(n);
     unsigned idle = 0xffffffffu;                        // warp-uniform: lanes without a ray
     bool anypar = false, found = false; int q = 0, cur = TR_DONE;
-#if WF_STEAL
-    StealStack st; st.init(stack_base);
-    int owner = -1, kids = 0;                           // owner >= 0: this lane helps lane `owner` with its ray; kids: helpers of my ray still at work
-    bool helping = false;                               // warp-uniform: some lane of the warp is a helper
-#else
     SmemStack st; st.init(stack_base);
-#endif
     RayPre r = make_ray(mk3(0.f, 0.f, 0.f), mk3(1.f, 1.f, 1.f));
     HitRec h; hit_reset(h);
 #ifdef TR_COUNTERS
@@ -334,62 +325,8 @@ __global__ void __launch_bounds__(WF_THREADS) k_trace(WfArgs a, int depth) {
             if (closer(t, k, h.t, h.leaf)) { h.t = t; h.u = u; h.v = v; h.prim = __float_as_int(la.w); h.mat = __float_as_int(lc.w); h.leaf = k; }
             cur = st.pop();
         }
-#if WF_STEAL
-        // ---- work stealing at the end of the queue.  Once the warp has no more rays to fetch, the kernel time is the walk of its
-        //      slowest ray (hundreds of dependent node visits on the 130 k-triangle scene, at the issue latency of a single lane).
-        //      Idle lanes therefore take the oldest pending sub-tree off a busy lane's stack and walk it for the same ray; a helper
-        //      prunes with the owner's best t at hand-over and returns its own best hit, which the owner merges with closer() -- a
-        //      total order on (t, leaf), so the result is the sequential one whatever the schedule.
-        if (helping) {                                  // helpers that finished hand their hit back and become idle again
-            unsigned back = __ballot_sync(0xffffffffu, has && owner >= 0 && cur == TR_DONE);
-            idle |= back;
-            while (back) {
-                const int b = __ffs(back) - 1; back &= back - 1;
-                const int ow = __shfl_sync(0xffffffffu, owner, b);
-                const float bt = __shfl_sync(0xffffffffu, h.t, b), bu = __shfl_sync(0xffffffffu, h.u, b), bv = __shfl_sync(0xffffffffu, h.v, b);
-                const int bp = __shfl_sync(0xffffffffu, h.prim, b), bm = __shfl_sync(0xffffffffu, h.mat, b), bl = __shfl_sync(0xffffffffu, h.leaf, b);
-                if (lane == ow) {
-                    if (bp >= 0 && closer(bt, bl, h.t, h.leaf)) { h.t = bt; h.u = bu; h.v = bv; h.prim = bp; h.mat = bm; h.leaf = bl; }
-                    --kids;
-                }
-                if (lane == b) { owner = -1; cur = TR_DONE; }
-            }
-            helping = __ballot_sync(0xffffffffu, owner >= 0) != 0u;
-        }
-        if (!feed.more && feed.cb >= feed.ce && idle != 0u) {
-            const unsigned donors = __ballot_sync(0xffffffffu, !((idle >> lane) & 1u) && st.pending() > 0);
-            if (donors != 0u) {
-                const unsigned lt = (1u << lane) - 1u;
-                const int npair = min(__popc(donors), __popc(idle));
-                const bool donor = ((donors >> lane) & 1u) && __popc(donors & lt) < npair;
-                const bool thief = ((idle >> lane) & 1u) && __popc(idle & lt) < npair;
-                const int src = thief ? __fns(donors, 0, __popc(idle & lt) + 1) : lane;
-                int link = donor ? st.steal_bottom() : 0;
-                link = __shfl_sync(0xffffffffu, link, src);
-                const float ox = __shfl_sync(0xffffffffu, r.o.x, src), oy = __shfl_sync(0xffffffffu, r.o.y, src), oz = __shfl_sync(0xffffffffu, r.o.z, src);
-                const float dx = __shfl_sync(0xffffffffu, r.d.x, src), dy = __shfl_sync(0xffffffffu, r.d.y, src), dz = __shfl_sync(0xffffffffu, r.d.z, src);
-                const float ht = __shfl_sync(0xffffffffu, h.t, src);
-                const int root_owner = __shfl_sync(0xffffffffu, owner >= 0 ? owner : lane, src);
-                if (thief) {
-                    r = make_ray(mk3(ox, oy, oz), mk3(dx, dy, dz)); anypar = r.px || r.py || r.pz;
-                    hit_reset(h); h.t = ht;                          // prune with the owner's best so far; prim stays -1 until this lane finds a hit
-                    st.reset(); cur = link; owner = root_owner;
-                }
-                unsigned tm = __ballot_sync(0xffffffffu, thief);
-                idle &= ~tm;
-                while (tm) {                                     // owners count their new helpers
-                    const int b = __ffs(tm) - 1; tm &= tm - 1;
-                    if (lane == __shfl_sync(0xffffffffu, owner, b)) ++kids;
-                }
-                helping = true;
-            }
-        }
-        // ---- retire finished rays (a ray with helpers at work waits for them; helpers never retire a ray)
-        const unsigned finm = __ballot_sync(0xffffffffu, !((idle >> lane) & 1u) && owner < 0 && kids == 0 && cur == TR_DONE);
-#else
         // ---- retire finished rays: hit record now, material-sorted queue entries through the warp's buffer
         const unsigned finm = __ballot_sync(0xffffffffu, has && cur == TR_DONE);
-#endif
         if (finm != 0u) {
             if ((finm >> lane) & 1u) {
                 a.hit[q] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
