@@ -1,6 +1,7 @@
 """include/trmath.h — the transcendental functions shared by the CUDA kernels and the CPU oracle.
 CPU: accuracy against float64 libm on the ranges the renderer uses, special values.  GPU: the device build of the same header
 returns the same bits as the host build (that is what makes radiance parity exact)."""
+import os
 import numpy as np
 import pytest
 from oracle import oracle
@@ -67,3 +68,23 @@ def test_device_build_returns_the_same_bits(gpu_ctx):
         g = gpu_ctx.test_math(fn, a, b); c = oracle.math_fn(fn, a, b)
         same = (g.view(np.uint32) == c.view(np.uint32)) | (np.isnan(g) & np.isnan(c))
         assert same.all(), (fn, a[~same][:5], None if b is None else b[~same][:5], g[~same][:5], c[~same][:5])
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/trmath.h is shared by nvcc (device), g++ (oracle) and plain C hosts: it compiles as C99 -pedantic -Werror and gives
+    the oracle's bits there too"""
+    import shutil, subprocess, struct
+    from conftest import ROOT
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include "trmath.h"\nint main(void) { float v[6]; unsigned u; int k;\n'
+                   ' v[0] = tr_sinf(1.25f); v[1] = tr_cosf(-2.5f); v[2] = tr_expf(-3.75f); v[3] = tr_acosf(0.3f); v[4] = tr_atan2f(0.7f, -0.2f); v[5] = tr_powf(0.37f, 2.4f);\n'
+                   ' for (k = 0; k < 6; ++k) { memcpy(&u, &v[k], 4); printf("%08x\\n", u); } return 0; }\n')
+    exe = str(tmp_path / "t")
+    subprocess.check_call([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-O2", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe, "-lm"])
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
+    ref = [oracle.math_fn(0, [1.25])[0], oracle.math_fn(1, [-2.5])[0], oracle.math_fn(2, [-3.75])[0], oracle.math_fn(3, [0.3])[0],
+           oracle.math_fn(4, [0.7], [-0.2])[0], oracle.math_fn(5, [0.37], [2.4])[0]]
+    assert out == ["%08x" % struct.unpack("<I", struct.pack("<f", float(r)))[0] for r in ref]
