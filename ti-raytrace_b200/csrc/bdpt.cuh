@@ -683,8 +683,10 @@ static int render_bdpt(tr_ctx* ctx, int frame_begin, int n_frames, uint64_t seed
     cudaEvent_t* ev = timing ? ctx->stage_ev.data() : nullptr;
     float ms_paths = 0.0f, ms_connect = 0.0f, ms_other = 0.0f, ms_ktrace = 0.0f, ms_kshadow = 0.0f;
     TR_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
-    for (int f0 = 0; f0 < n_frames; f0 += F) {
-        const int nf = (n_frames - f0 < F) ? n_frames - f0 : F;
+    // auto mode: the batches differ by at most one frame (32 frames at 6 per batch: 6 6 5 5 5 5 instead of 6 6 6 6 6 2)
+    const int nbatch = (n_frames + F - 1) / F, fbase = n_frames / nbatch, fextra = n_frames % nbatch;
+    for (int f0 = 0, bi = 0, nf = 0; f0 < n_frames; f0 += nf, ++bi) {
+        nf = ctx->opt_batch_frames > 0 ? ((n_frames - f0 < F) ? n_frames - f0 : F) : fbase + (bi < fextra ? 1 : 0);
         BatchParams bp; bp.frame_begin = frame_begin + f0; bp.n_frames = nf; bp.seed = seed; bp.max_depth = BD_MAX_DEPTH; bp.pad = 0;
         TR_CUDA(ctx, cudaMemcpyAsync(ctx->d_batch_params, &bp, sizeof(bp), cudaMemcpyHostToDevice, s));
         TR_CUDA(ctx, cudaMemsetAsync(ctx->d_ctr, 0, sizeof(TrCounters), s));
@@ -726,12 +728,11 @@ static int render_bdpt(tr_ctx* ctx, int frame_begin, int n_frames, uint64_t seed
         TR_CHECK_LAUNCH(ctx);
         // ray counters of this batch.  Asynchronous like PT_RGB: snapshot into the pinned ring (slot 0: the wavefront counters,
         // slot 1: the four BDPT counters) and go on; tr_stats_get folds the snapshots.  Stage timing stays synchronous.
-        const int bi = f0 / F;
         if (!timing && bi < TR_RING_BATCHES) {
             TR_CUDA(ctx, cudaMemcpyAsync(ctx->h_ring + (size_t)bi * TR_MAX_CHAINS, ctx->d_ctr, sizeof(TrCounters), cudaMemcpyDeviceToHost, s));
             TR_CUDA(ctx, cudaMemcpyAsync(ctx->h_ring + (size_t)bi * TR_MAX_CHAINS + 1, ctx->d_bd_ctr, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
             ctx->ring_batches = bi + 1;
-            if (bi + 1 == TR_RING_BATCHES && f0 + F < n_frames) TR_CUDA(ctx, cudaStreamSynchronize(s));     // ring full: later batches take the synchronous path
+            if (bi + 1 == TR_RING_BATCHES && f0 + nf < n_frames) TR_CUDA(ctx, cudaStreamSynchronize(s));     // ring full: later batches take the synchronous path
             continue;
         }
         unsigned long long hc[4];
