@@ -206,8 +206,12 @@ __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol
 #endif
 template <int MODE> struct NodeSteps { static constexpr int value = (MODE == TM_GLOBAL || MODE == TM_GTOP) ? WF_NODE_STEPS_GLOBAL : WF_NODE_STEPS; };
 #ifndef WF_REFILL_MIN
-#define WF_REFILL_MIN 8
+#define WF_REFILL_MIN 8             // idle lanes of a warp before it fetches new rays, tree in shared memory
 #endif
+#ifndef WF_REFILL_MIN_GLOBAL
+#define WF_REFILL_MIN_GLOBAL 12     // ... tree in global memory (measured on C3: 12 beats 8 by 3 %, 6 loses 3 %; on C2 8 beats 6 and 12)
+#endif
+template <int MODE> struct RefillMin { static constexpr int value = (MODE == TM_GLOBAL || MODE == TM_GTOP) ? WF_REFILL_MIN_GLOBAL : WF_REFILL_MIN; };
 
 struct WarpFeed { int cb, ce, chunk; bool more; };
 
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_trace(WfArgs a, int depth) {
 #endif
     while (true) {
         // ---- refill: only when enough lanes are free (the ray set-up runs at the utilisation of the idle set)
-        if ((__popc(idle) >= WF_REFILL_MIN || idle == 0xffffffffu) && (feed.more || feed.cb < feed.ce)) {
+        if ((__popc(idle) >= RefillMin<MODE>::value || idle == 0xffffffffu) && (feed.more || feed.cb < feed.ce)) {
             int nq = feed_lanes(feed, cursor, n, idle, lane);
             if (nq >= 0) {
                 float4 A = pa[nq], B = pb[nq];
@@ -772,8 +776,11 @@ __global__ void __launch_bounds__(WF_THREADS, SPEC ? 1 : 2) k_tail(WfArgs a, int
 // primitive that would have won the reference's nearest-hit comparison (see trace_shadow_visible).
 // QUERY (BDPT connections): instead of adding a contribution, report per queue item (sb.w) the distance to the target when it is
 // the nearest hit, -1 otherwise.
+#ifndef WF_SHADOW_MIN_BLOCKS
+#define WF_SHADOW_MIN_BLOCKS 5      // 48 registers, no spills: 5 CTAs per SM (C2 shadow stages 5.38 -> 5.31 ms)
+#endif
 template <int MODE, bool QUERY = false>
-__global__ void __launch_bounds__(WF_THREADS) k_shadow(WfArgs a, int depth) {
+__global__ void __launch_bounds__(WF_THREADS, WF_SHADOW_MIN_BLOCKS) k_shadow(WfArgs a, int depth) {
     grid_dep_wait(); grid_dep_launch();
     if (tail_took_over(a, depth)) return;
     const int n = a.ctr->nshadow[depth];
@@ -794,7 +801,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_shadow(WfArgs a, int depth) {
     unsigned long long cnt_nodes = 0, cnt_leaves = 0;
 #endif
     while (true) {
-        if ((__popc(idle) >= WF_REFILL_MIN || idle == 0xffffffffu) && (feed.more || feed.cb < feed.ce)) {
+        if ((__popc(idle) >= RefillMin<MODE>::value || idle == 0xffffffffu) && (feed.more || feed.cb < feed.ce)) {
             int nq = feed_lanes(feed, cursor, n, idle, lane);
             if (nq >= 0) {
                 float4 A = a.sa[depth & 1][nq], B = a.sb[depth & 1][nq];
