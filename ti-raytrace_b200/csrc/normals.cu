@@ -99,9 +99,7 @@ extern "C" int tr_process_normal(tr_ctx* ctx) {
     int g = (ctx->nv + 127) / 128;
     k_smooth_normals<<<g, 128, 0, ctx->stream>>>(ctx->d_vertex, ctx->d_prim, ctx->nv, ctx->d_nodes, ctx->d_leaves, d_smooth);
     k_write_normals<<<g, 128, 0, ctx->stream>>>(ctx->d_vertex, d_smooth, ctx->nv);
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) return tr_fail(ctx, TR_ERR_CUDA, "tr_process_normal: %s", cudaGetErrorString(e));
-    TR_CHECK_LAUNCH(ctx);
+    TR_CHECK_LAUNCH(ctx);              // asynchronous like the build: a fault surfaces at the next synchronising call
     ctx->shade_ready = false; ctx->fh_ready = false; ctx->gen++;    // shading records hold normals
     return TR_OK;
 }

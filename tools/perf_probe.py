@@ -41,20 +41,28 @@ if args.e2e:
     import time
     sc = ex.scene
     for rep in range(3):
+        ctx.synchronize()
         t = [time.perf_counter()]
+
+        def mark(sync=True):
+            if sync:
+                ctx.synchronize()
+            t.append(time.perf_counter())
         ctx.scene_upload(sc.vertex_np, sc.primitive_np, sc.material_np, sc.shape_np if sc.shape_count else None,
-                         sc.light_np if sc.light_count else None, sc.minboundarynp, sc.maxboundarynp); t.append(time.perf_counter())
-        sc.env.setup_data_gpu(sc.env_power); t.append(time.perf_counter())
-        ctx.bvh_build(); t.append(time.perf_counter())
+                         sc.light_np if sc.light_count else None, sc.minboundarynp, sc.maxboundarynp); mark(False); mark()
+        sc.env.setup_data_gpu(sc.env_power); mark()
+        ctx.bvh_build(); mark(False); mark()
         build_ms = ctx.stats()["ms_build"]
         if wl["normals"]:
             ctx.process_normal()
-        ctx.synchronize(); t.append(time.perf_counter())
+        mark()
         cam.dirty = True; ctx.film_clear(); cam.frame = 0; cam.frame_cpu[0] = 0
-        integ.render_frames(wl["spp"]); ctx.synchronize(); t.append(time.perf_counter())
-        ctx.tonemap(0.5); ctx.film_download(True, True); t.append(time.perf_counter())
-        names = ["scene_upload", "env_upload", "bvh_build(host wall)", "process_normal", "render", "tonemap+download"]
-        print("e2e pieces ms:", ", ".join("%s %.2f" % (n, (b - a) * 1e3) for n, a, b in zip(names, t[:-1], t[1:])), "| bvh device ms %.3f" % build_ms, flush=True)
+        integ.render_frames(wl["spp"], stats=False); mark(False); mark()
+        ctx.film_reduce(); ctx.tonemap(0.5); mark()
+        ctx.film_download(False, True, view=True); mark()
+        names = ["scene_upload(host)", "+sync", "env_upload", "bvh_build(host)", "+sync", "process_normal", "render(enqueue)", "+sync", "reduce+tonemap", "download rgb"]
+        print("e2e pieces ms:", ", ".join("%s %.2f" % (n, (b - a) * 1e3) for n, a, b in zip(names, t[:-1], t[1:])),
+              "| total %.2f | bvh device ms %.3f" % ((t[-1] - t[0]) * 1e3, build_ms), flush=True)
 for b in [int(x) for x in args.batch.split(",")]:
     ctx.set_option("batch_frames", b)
     best = None
