@@ -600,7 +600,26 @@ inline LightSample sample_li(const Scene& s, V3 p, float u_idx, float a, float b
     float NdotL = fabsf(dot(dir, nor));
     L.dir_pdf = CosineHemisphere_pdf(NdotL);
     L.pos = pos; L.normal = nor; L.dir = dir; L.dist = dist; L.prim = pi;
-    // spot / laser branches (Scene.py:495-516) are only reachable from prism_rainbow / BDPT: out of scope
+    if (prim_type(s, pi) != PRIM_TRI) {     // Scene.py:493-516: spot falloff / laser radius cut-off scale the emission
+        int sid = prim_vindex(s, pi); int st = shape_type(s, sid);
+        const float* sp = &s.shape[(size_t)sid * SHA_N];
+        float visable = 1.0f;
+        if (st == SHAPE_SPOT) {
+            L.dir_pdf = 1.0f;
+            float x1 = sp[4], x2 = sp[5];   // UF.get_shape_xita
+            float x = tr_acosf(NdotL);
+            if (x > x2) visable = 0.0f;
+            else if (x > x1) visable *= 1.0f - (x - x1) / (x2 - x1);
+        } else if (st == SHAPE_LASER) {
+            L.choice_pdf = 1.0f / (float)s.nl;
+            float proj = dot(dir, nor) * dist;
+            float r = sqrtf(dist * dist - proj * proj);
+            float limit_r = shape_radius(s, sid);
+            if (r > limit_r) visable = 0.0f;
+            L.dir_pdf = 1.0f;
+        }
+        L.emission = L.emission * visable;
+    }
     return L;
 }
 

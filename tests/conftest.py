@@ -34,10 +34,13 @@ def oracle_tables():
     from oracle import objload
     cache = {}
 
-    def get(name, sphere_light=False, glass0=False, spectral_walls=False, mirror0=False):
-        key = (name, sphere_light, glass0, spectral_walls, mirror0)
+    def get(name, sphere_light=False, glass0=False, spectral_walls=False, mirror0=False, beam_lights=False):
+        key = (name, sphere_light, glass0, spectral_walls, mirror0, beam_lights)
         if key not in cache:
             shapes = [objload.sphere_light_rows()] if sphere_light else []
+            if beam_lights:
+                shapes += [([float(t), *pos, p0, p1, p2, *nor], [objload.MAT_LIGHT, 0.0, *col, 0, 0, 0, 0, 0])
+                           for t, pos, (p0, p1, p2), nor, col in BEAM_LIGHTS]
 
             def edit(mats):
                 if glass0:
@@ -52,7 +55,13 @@ def oracle_tables():
     return get
 
 
-def make_product_scene(name, sphere_light=False, glass0=False, env_power=0.0, spectral_walls=False, mirror0=False):
+# a laser (SHPAE_LASER = 4: radius, normal; example/prism_rainbow.py:37-50) and a spot light (SHPAE_SPOT = 3: xita1, xita2, scale,
+# normal) inside the Cornell box, both pointing down: (type, pos, params 0..2, normal, colour)
+BEAM_LIGHTS = [(4, (278.0, 500.0, -279.6), (60.0, 0.0, 0.0), (0.0, -1.0, 0.0), (4.0e5, 1.0e5, 1.0e5)),
+               (3, (150.0, 450.0, -200.0), (0.3, 0.6, 1.0), (0.0, -1.0, 0.0), (2.0e4, 8.0e4, 2.0e4))]
+
+
+def make_product_scene(name, sphere_light=False, glass0=False, env_power=0.0, spectral_walls=False, mirror0=False, beam_lights=False):
     """product-side Scene (host packing only; no device calls)"""
     import Scene
     import SceneData as SCD
@@ -70,6 +79,16 @@ def make_product_scene(name, sphere_light=False, glass0=False, env_power=0.0, sp
         sh = SCD.Shape(); sh.type = SCD.SHPAE_SPHERE; sh.pos = [0.0, 20.0, 0.0]; sh.setRadius(5.0)
         mt = SCD.Material(); mt.type = SCD.MAT_LIGHT; mt.setColor([50.0, 50.0, 50.0])
         s.add_shape(sh, mt)
+    if beam_lights:
+        for t, pos, (p0, p1, p2), nor, col in BEAM_LIGHTS:
+            sh = SCD.Shape(); sh.type = t; sh.pos = list(pos)
+            if t == SCD.SHPAE_LASER:
+                sh.setRadius(p0)
+            else:
+                sh.setXita(p0, p1); sh.setScale(p2)
+            sh.setNormal(list(nor))
+            mt = SCD.Material(); mt.type = SCD.MAT_LIGHT; mt.setColor(list(col))
+            s.add_shape(sh, mt)
     if env_power:
         s.add_env("image/env.png", env_power)
     return s

@@ -156,10 +156,10 @@ def test_film_download_views_and_validation(gpu_ctx):
         gpu_ctx.set_option("max_paths", -5)
     with pytest.raises(RuntimeError, match="out of range"):
         gpu_ctx.set_option("chains", 99)
-    # emitter shapes other than spheres are refused (the SPOT / LASER branches of Scene.sample_li are out of scope)
+    # a QUAD emitter has no area in the reference (Scene.get_prim_area returns 0): refused instead of rendered wrong
     import SceneData as SCD
     sc = make_product_scene("cornell")
-    sh = SCD.Shape(); sh.type = SCD.SHPAE_SPOT; sh.pos = [0.0, 20.0, 0.0]; sh.setRadius(5.0)
+    sh = SCD.Shape(); sh.type = SCD.SHPAE_QUAD; sh.pos = [0.0, 20.0, 0.0]; sh.setRadius(5.0)
     mt = SCD.Material(); mt.type = SCD.MAT_LIGHT; mt.setColor([50.0, 50.0, 50.0])
     sc.add_shape(sh, mt); sc.setup_data_cpu()
     with pytest.raises(RuntimeError, match="emitter shape"):

@@ -151,3 +151,15 @@ def test_cpp_oracle_pt_rgb_matches_literal_python_transliteration(oracle_tables)
           assert bad.mean() <= 0.01, (frame, int(bad.sum()))
           assert abs(nc - cnt["closest"]) <= 0.005 * cnt["closest"] and abs(ns - cnt["shadow"]) <= 0.005 * cnt["shadow"]
           assert ref.max() > 1.0 and (ref.max(axis=2) > 0).mean() > (0.02 if glass0 else 0.5)
+
+
+def test_spot_and_laser_emitters_light_through_nee(oracle_tables):
+    """Scene.sample_li's SPOT / LASER branches (Scene.py:493-516): both shapes have an empty box and are never hit, a laser of
+    radius 60 pointing down lights a disc of the Cornell floor under it and nothing outside its beam"""
+    from test_gpu_parity import build_oracle_scene
+    W = 64
+    plain, _ = build_oracle_scene(oracle_tables("cornell"), W, W).render_pt_rgb(W, W, 0, 4)
+    lit, cnt = build_oracle_scene(oracle_tables("cornell", beam_lights=True), W, W).render_pt_rgb(W, W, 0, 4)
+    assert np.isfinite(lit).all() and cnt["shadow"] > 0
+    assert lit[..., 0].mean() > 1.05 * plain[..., 0].mean()
+    assert ((lit - plain).sum(axis=2) > 0.05).sum() > 50                # directly lit pixels exist

@@ -635,6 +635,7 @@ static int render_bdpt(tr_ctx* ctx, int frame_begin, int n_frames, uint64_t seed
     if (!ctx->h_ring) TR_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_ring, sizeof(TrCounters) * TR_MAX_CHAINS * TR_RING_BATCHES, cudaHostAllocDefault));
     if ((rc = fill_args(ctx, a, false))) return rc;
     if (ctx->nl <= 0) return tr_fail(ctx, TR_ERR_INVALID, "tr_render_bdpt_rgb: the scene has no emitter (Scene.sample_light needs one)");
+    if (ctx->has_beam_light) return tr_fail(ctx, TR_ERR_INVALID, "tr_render_bdpt_rgb: spot / laser emitters are not supported by the light sub-path (Scene.sample_light, Scene.py:449-472); PT_RGB and PT_Spec render them");
     if (!ctx->view_set) return tr_fail(ctx, TR_ERR_INVALID, "tr_render_bdpt_rgb: tr_camera_set was called without the view matrix (Camera.get_image_point needs it)");
     const bool wave = ctx->opt_bdpt_wavefront != 0;
     // bytes per sample: 13 vertex records + 21 contributions + 26 queue items + depths; the wavefront pipeline adds two path-queue

@@ -268,8 +268,15 @@ __device__ __forceinline__ void flush_retired(const WfArgs& a, int depth, const 
     __syncwarp();
 }
 
+#ifndef WF_TRACE_MIN_BLOCKS
+#define WF_TRACE_MIN_BLOCKS 4
+#endif
+#ifndef WF_TRACE_MIN_BLOCKS_GLOBAL
+#define WF_TRACE_MIN_BLOCKS_GLOBAL 4
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(WF_THREADS) k_trace(WfArgs a, int depth) {
+__global__ void __launch_bounds__(WF_THREADS, (MODE == TM_GLOBAL || MODE == TM_GTOP) ? WF_TRACE_MIN_BLOCKS_GLOBAL : WF_TRACE_MIN_BLOCKS)
+k_trace(WfArgs a, int depth) {
     grid_dep_wait(); grid_dep_launch();
     if (tail_took_over(a, depth)) return;
     // surplus CTAs of a short queue leave BEFORE staging the tree (deep bounces, small shards: the per-stage floor)
@@ -420,6 +427,20 @@ __device__ __forceinline__ LightSample sample_li(const WfArgs& a, V3 p, float u_
     L.choice_pdf = 1.0f / ((float)a.nl * q2.w);
     nor = normalize3(nor);      // Scene.py:486
     V3 dir = p - pos; float dist = length3(dir); dir = dir / dist;
+    if (kind >= 2) {            // Scene.py:493-516: spot falloff (kind 2) / laser radius cut-off (kind 3) scale the emission
+        float visable = 1.0f;
+        if (kind == 2) {
+            float x = tr_acosf(fabsf(dot3(dir, nor)));
+            if (x > q2.y) visable = 0.0f;
+            else if (x > q2.x) visable *= 1.0f - (x - q2.x) / (q2.y - q2.x);
+        } else if (kind == 3) {
+            L.choice_pdf = 1.0f / (float)a.nl;
+            float proj = dot3(dir, nor) * dist;
+            float r = sqrtf(dist * dist - proj * proj);
+            if (r > q2.x) visable = 0.0f;
+        }
+        L.emission = L.emission * visable;
+    }
     L.pos = pos; L.normal = nor; L.dir = dir; L.dist = dist; L.prim = pi;
     return L;
 }
@@ -936,9 +957,10 @@ __global__ void k_shade_table(const float* __restrict__ vertex, const int* __res
         float area = 0.0f;
         if (st == TR_SHAPE_SPHERE || st == TR_SHAPE_SPOT || st == TR_SHAPE_LASER) area = sp[4] * sp[4] * TR_PI_ENV;
         s.q[0] = make_float4(sp[1], sp[2], sp[3], __int_as_float(mat));
+        // kind: 1 sphere (q1.x radius), 2 spot (q1 normal, q2 = xita1, xita2, scale), 3 laser (q1 normal, q2.x radius), 4 others
         if (st == TR_SHAPE_SPHERE) s.q[1] = make_float4(sp[4], 0.0f, 0.0f, __int_as_float(1));
-        else s.q[1] = make_float4(sp[7], sp[8], sp[9], __int_as_float(2));
-        s.q[2] = make_float4(0.0f, 0.0f, 0.0f, area);
+        else s.q[1] = make_float4(sp[7], sp[8], sp[9], __int_as_float(st == TR_SHAPE_SPOT ? 2 : (st == TR_SHAPE_LASER ? 3 : 4)));
+        s.q[2] = make_float4(st == TR_SHAPE_SPHERE ? 0.0f : sp[4], st == TR_SHAPE_SPOT ? sp[5] : 0.0f, st == TR_SHAPE_SPOT ? sp[6] : 0.0f, area);
         s.q[3] = s.q[4] = s.q[5] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     out[i] = s;
