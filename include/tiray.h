@@ -105,7 +105,8 @@ int tr_bvh_download(tr_ctx* ctx, int32_t* morton_sorted, float* bvh_node, float*
 /* unsorted Morton codes as written by build_morton_3d (accel/LBvh.py:318-336): n x 2 i32 */
 int tr_morton_download(tr_ctx* ctx, int32_t* morton_unsorted);
 
-/* replaces Scene.process_normal (Scene.py:754-798) and Scene.total_area (:747-750) */
+/* replaces Scene.process_normal (Scene.py:754-798) and Scene.total_area (:747-750).  tr_process_normal is asynchronous (enqueued on
+ * the context stream behind the build); tr_vertex_download / tr_total_area synchronise. */
 int tr_process_normal(tr_ctx* ctx);
 int tr_vertex_download(tr_ctx* ctx, float* vertex /* nv x 9 */);
 int tr_total_area(tr_ctx* ctx, float* area);
