@@ -61,13 +61,53 @@ def workload_config(wl):
 
 # --------------------------------------------------------------------------------------------- helpers
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    """SM clock, throttle reasons and power DURING the timed region (B200_PROFILING.md recipe).  NVML is polled from a thread
+    every 2 ms (one sample is taken when the region starts and one when it ends, so even a 50 ms region at N = 8 is covered);
+    `nvidia-smi -lms` is the fallback when the NVML binding is missing (it needs ~0.3 s to start: useless for short regions)."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))   # nvmlClocksThrottleReason*
 
     def __init__(self, gpu_index):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+        self.idx, self.rows, self.proc, self.h, self.nv, self.run = gpu_index, [], None, None, None, False
+        self.samples, self.smax, self.thread = [], None, None
+        try:                                      # NVML start-up happens here, before the warm-up, not inside the timed region
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            phys = int(ids[gpu_index]) if ids and all(v.isdigit() for v in ids) and gpu_index < len(ids) else gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys); self.nv = pynvml
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _sample(self):
+        nv = self.nv
+        try:
+            sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            try:
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            try:
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+            except Exception:
+                pw = None
+            self.samples.append((sm, mask, pw))
+        except Exception:
+            pass
+
+    def _poll(self):
+        while self.run:
+            self._sample()
+            time.sleep(0.002)
 
     def start(self):
+        if self.h is not None:
+            self._sample()
+            self.run = True
+            self.thread = threading.Thread(target=self._poll, daemon=True); self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -80,6 +120,16 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.h is not None:
+            self._sample()
+            self.run = False
+            if self.thread is not None:
+                self.thread.join(timeout=1.0)
+            sm = sorted(v[0] for v in self.samples)
+            reasons = sorted({name for _, mask, _ in self.samples for bit, name in self.REASONS if mask & bit})
+            power = [v[2] for v in self.samples if v[2] is not None]
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.smax, "reasons": reasons,
+                    "power_w_max": max(power) if power else None, "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -95,7 +145,7 @@ class ClockSampler:
                 pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "power_w_max": max(power) if power else None, "samples": len(sm)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "source": "nvidia-smi"}
 
 
 def measured_peak_gbs():
@@ -294,11 +344,12 @@ def measure_native(args, name, steps, warmup, rank, world, local, D, detail=True
         integ.render_frames(spp, stats=False)           # asynchronous: the film reduce is enqueued right behind the last kernel
         ctx.film_reduce()                               # ncclReduce on the render stream (no-op for one rank)
 
+    sampler = ClockSampler(local)                # NVML start-up before the warm-up, sampling only inside the timed region
     for _ in range(warmup):
         one_step()
     torch.cuda.synchronize(local)
     D.barrier()
-    sampler = ClockSampler(local); sampler.start()
+    sampler.start()
     rays = 0; launches = 0; ms = 0.0
     t_wall0 = time.perf_counter()
     for _ in range(steps):
