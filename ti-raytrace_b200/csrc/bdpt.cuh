@@ -641,7 +641,7 @@ static int render_bdpt(tr_ctx* ctx, int frame_begin, int n_frames, uint64_t seed
     // bytes per sample: 13 vertex records + 21 contributions + 26 queue items + depths; the wavefront pipeline adds two path-queue
     // slots (PT_RGB's 252 B each) and a worst-case connection shadow queue (26 x (32 B + 4 B))
     const size_t per_sample = (size_t)BD_NVERT * 80 + BD_NCONTRIB * 16 + BD_NSTRAT * 4 + 8 + (wave ? 2 * 252 + BD_NSTRAT * 36 : 0);
-    size_t budget = ctx->opt_max_paths * 252 / per_sample;
+    size_t budget = ctx->opt_max_paths * 2 * 252 / per_sample;     // twice PT's byte budget (2.9 KB per sample): 32 spp of a 512^2 image = 8.4 M samples = 25 GB = ONE batch (C5: 6 batches 70.2, 2: 67.4, 1: 66.4 ms/step)
     const size_t npix = (size_t)(a.npix > 0 ? a.npix : 1);
     int F = ctx->opt_batch_frames > 0 ? ctx->opt_batch_frames : (int)(budget / npix);
     if (F < 1) F = 1; if (F > n_frames) F = n_frames;

@@ -29,13 +29,27 @@ __device__ __forceinline__ float tri_angle(const float* __restrict__ vertex, int
     return tr_acosf(ret);
 }
 
-__global__ void k_smooth_normals(const float* __restrict__ vertex, const int* __restrict__ prim, int nv,
-                                 const TrNode* __restrict__ nodes, const TrLeaf* __restrict__ leaves, float* __restrict__ smooth) {
+// Per vertex, what every query that finds it adds: w = (normalize(n) * angle at the vertex) * area of its triangle -- the
+// expression of Scene.py:778-790, which depends on the found vertex only.  Computing it once per vertex (coherent, streaming)
+// instead of inside every divergent tree walk that reaches the vertex keeps the bits and takes the acos / sqrt chains out of
+// the walk.
+__global__ void k_normal_terms(const float* __restrict__ vertex, int nv, float4* __restrict__ w4, float4* __restrict__ n4) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nv) return;
-    V3 v = ldpos(vertex, i), n = normalize3(ldnor(vertex, i));
-    int own_vi = (i / 3) * 3;                       // vertex soup: 3 vertices per triangle, in primitive order
-    V3 sm = (n * tri_angle(vertex, own_vi, v)) * tri_area(vertex, own_vi);
+    int vi = (i / 3) * 3;                           // vertex soup: 3 vertices per triangle, in primitive order
+    V3 nn = normalize3(ldnor(vertex, i));
+    float ang = tri_angle(vertex, vi, ldpos(vertex, i));
+    V3 w = (nn * ang) * tri_area(vertex, vi);
+    w4[i] = make_float4(w.x, w.y, w.z, 0.0f); n4[i] = make_float4(nn.x, nn.y, nn.z, 0.0f);
+}
+
+__global__ void k_smooth_normals(const float* __restrict__ vertex, const int* __restrict__ prim, int nv,
+                                 const TrNode* __restrict__ nodes, const TrLeaf* __restrict__ leaves,
+                                 const float4* __restrict__ w4, const float4* __restrict__ n4, float* __restrict__ smooth) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nv) return;
+    V3 v = ldpos(vertex, i), n = f4xyz(n4[i]);
+    V3 sm = f4xyz(w4[i]);
     int stack[PN_STACK + 2];
     stack[0] = 0; int sp = 0;
     while (sp >= 0 && sp < PN_STACK) {
@@ -51,11 +65,8 @@ __global__ void k_smooth_normals(const float* __restrict__ vertex, const int* __
                 for (int j = 0; j < 3; ++j) {
                     int nb = vi + j;
                     if (i != nb) {
-                        V3 nvp = ldpos(vertex, nb), nn = normalize3(ldnor(vertex, nb));
-                        if (length3(v - nvp) < 0.000001f && dot3(nn, n) > 0.5f) {
-                            float ang = tri_angle(vertex, vi, nvp);
-                            sm = sm + (nn * ang) * tri_area(vertex, vi);
-                        }
+                        V3 nvp = ldpos(vertex, nb), nn = f4xyz(n4[nb]);
+                        if (length3(v - nvp) < 0.000001f && dot3(nn, n) > 0.5f) sm = sm + f4xyz(w4[nb]);
                     }
                 }
             }
@@ -94,10 +105,14 @@ extern "C" int tr_process_normal(tr_ctx* ctx) {
     if (!ctx || !ctx->bvh_ready) return tr_fail(ctx, TR_ERR_INVALID, "tr_process_normal: BVH not built");
     TR_CUDA(ctx, cudaSetDevice(ctx->device));
     // the vertex soup must be 3 consecutive vertices per triangle primitive (Scene.py:94-141)
-    int rc; if ((rc = tr_realloc(ctx, &ctx->d_smooth, (size_t)ctx->nv * 3))) return rc;
+    // scratch: smooth normals (nv x 3) | per-vertex terms w4 (nv float4) | normalised normals n4 (nv float4)
+    const size_t off4 = ((size_t)ctx->nv * 3 + 3) & ~(size_t)3;
+    int rc; if ((rc = tr_realloc(ctx, &ctx->d_smooth, off4 + (size_t)ctx->nv * 8))) return rc;
     float* d_smooth = ctx->d_smooth;
+    float4* w4 = reinterpret_cast<float4*>(d_smooth + off4); float4* n4 = w4 + ctx->nv;
     int g = (ctx->nv + 127) / 128;
-    k_smooth_normals<<<g, 128, 0, ctx->stream>>>(ctx->d_vertex, ctx->d_prim, ctx->nv, ctx->d_nodes, ctx->d_leaves, d_smooth);
+    k_normal_terms<<<g, 128, 0, ctx->stream>>>(ctx->d_vertex, ctx->nv, w4, n4);
+    k_smooth_normals<<<g, 128, 0, ctx->stream>>>(ctx->d_vertex, ctx->d_prim, ctx->nv, ctx->d_nodes, ctx->d_leaves, w4, n4, d_smooth);
     k_write_normals<<<g, 128, 0, ctx->stream>>>(ctx->d_vertex, d_smooth, ctx->nv);
     TR_CHECK_LAUNCH(ctx);              // asynchronous like the build: a fault surfaces at the next synchronising call
     ctx->shade_ready = false; ctx->fh_ready = false; ctx->gen++;    // shading records hold normals
