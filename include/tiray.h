@@ -178,7 +178,9 @@ int tr_first_hit_download(tr_ctx* ctx, float* t, int32_t* prim, float* uv /*2*/,
 /* replaces UF.tone_map (UtilsFunc.py:583-586): rgb = srgb(ACES(hdr * exposure)) */
 int tr_tonemap(tr_ctx* ctx, float exposure);
 int tr_stats_get(tr_ctx* ctx, tr_stats* out);
-/* tuning: "batch_frames" (0 = auto), "max_paths", "chains" (parallel wavefront chains per batch), "stage_timing", "graph"
+/* tuning: "batch_frames" (0 = auto: as many frames per batch as "max_paths" allows), "max_paths" (path slots per batch, 252 B each;
+ * default 64 Mi = a 64-spp step of a 1024^2 film in ONE batch; BDPT takes twice the byte budget for its 2.9 KB samples),
+ * "chains" (parallel wavefront chains per batch), "chain_skew" (percent of a batch's frames given to chain 0), "stage_timing", "graph"
  * (CUDA-graph replay), "smem_bvh" (TMA staging of small trees into shared memory), "replicas" (their bank-conflict-free
  * 8-way replicated image), "top_nodes" (large trees: breadth-first top nodes staged per CTA, 0 = off), "tail_max", "tail_chunk",
  * "shadow_overlap", "pdl", "bdpt_wavefront".  Out-of-range values are rejected with TR_ERR_INVALID. */

@@ -20,6 +20,8 @@ class Texture:
         bgr = img.astype(np.int32)
         packed = (bgr[:, :, 2] << 16) | (bgr[:, :, 1] << 8) | bgr[:, :, 0]     # [row][col]
         self.np_img = np.ascontiguousarray(packed[::-1, :].T)                  # [x][H-1-row]
+        import _native
+        self._pin = _native.pin_array(self.np_img)                             # re-uploaded by every Scene.setup_data_gpu(): direct DMA
 
     def setup_data_gpu(self, power=0.0):
         import _native
