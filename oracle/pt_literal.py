@@ -1,6 +1,6 @@
 """ORACLE CROSS-CHECK (test infrastructure): PathTrace.render of integrator/PT_RGB.py:44-136 for one pixel and one frame,
 transliterated a second time in plain Python with numpy float32 scalars (triangle scenes without environment light: the Cornell
-box).  It shares nothing with oracle/tiray_oracle.cpp's pt_rgb_pixel except the BVH queries (closet_hit / closet_hit_shadow
+box; emitters may be triangles, spheres, spot and laser lights).  It shares nothing with oracle/tiray_oracle.cpp's pt_rgb_pixel except the BVH queries (closet_hit / closet_hit_shadow
 through orc_trace) and the Philox stream (orc_rng): hit attributes, light sampling, the Disney and glass BSDFs, NEE with the
 power heuristic, the throughput recursion and the RNG block order are restated here from the reference.  numpy's float32
 sin / cos / pow differ from glibc's by ULPs, so the comparison in tests/test_oracle.py uses a relative tolerance.
@@ -11,6 +11,8 @@ from oracle.bdpt_literal import (f32, PI_REF, v3, dot, length, normalized, disne
 
 INF_VALUE = f32(1000000.0)
 MAT_DISNEY, MAT_GLASS, MAT_LIGHT = 0, 1, 2
+PRIMITIVE_TRI = 1
+SHPAE_SPHERE, SHPAE_SPOT, SHPAE_LASER = 1, 3, 4
 MAX_DEPTH = 15
 
 
@@ -100,23 +102,60 @@ class Tracer:
         return t, pos, gn, nor, prim
 
     def prim_area(self, p):                                                      # Scene.py:324-350
+        if int(self.t.primitive[p, 0]) != PRIMITIVE_TRI:
+            sh = self.t.shape[int(self.t.primitive[p, 1])]
+            if int(sh[0]) in (SHPAE_SPHERE, SHPAE_SPOT, SHPAE_LASER):
+                r = f32(sh[4]); return r * r * f32(3.1415926)
+            return f32(0.0)
         vi = int(self.t.primitive[p, 1]); V = self.t.vertex
         a, b, c = length(V[vi, 0:3] - V[vi + 1, 0:3]), length(V[vi, 0:3] - V[vi + 2, 0:3]), length(V[vi + 2, 0:3] - V[vi + 1, 0:3])
         sm = ((a + b) + c) * f32(0.5)
         return np.sqrt(sm * (sm - a) * (sm - b) * (sm - c))
 
-    def sample_li(self, pos, u_idx, a, b):                                       # Scene.py:477-518, 381-428
+    def prim_random_point_normal(self, pi, a, b):                                # Scene.py:381-420
+        pos, nor = np.zeros(3, f32), np.zeros(3, f32)
+        if int(self.t.primitive[pi, 0]) == PRIMITIVE_TRI:
+            vi = int(self.t.primitive[pi, 1]); V = self.t.vertex
+            if a + b > 1.0: a = f32(1.0) - a; b = f32(1.0) - b
+            pos = (V[vi, 0:3] + (V[vi + 2, 0:3] - V[vi, 0:3]) * a) + (V[vi + 1, 0:3] - V[vi, 0:3]) * b
+            nor = normalized(((f32(1.0) - a - b) * V[vi, 3:6] + V[vi + 1, 3:6] * a) + V[vi + 2, 3:6] * b)
+        else:
+            sh = self.t.shape[int(self.t.primitive[pi, 1])].astype(f32); st = int(sh[0])
+            if st == SHPAE_SPHERE:                                               # UniformSampleSphere, Scene.py:315-322
+                z = f32(1.0) - f32(2.0) * a
+                r = np.sqrt(min(max(f32(1.0) - z * z, f32(0.0)), f32(1.0))); phi = f32(2.0) * f32(3.1415926) * b
+                nor = v3(r * np.cos(phi, dtype=f32), r * np.sin(phi, dtype=f32), z); pos = sh[1:4] + nor * sh[4]
+            elif st in (SHPAE_SPOT, SHPAE_LASER):
+                nor = sh[7:10].copy(); pos = sh[1:4].copy()
+        return pos, normalized(nor)
+
+    def sample_li(self, pos, u_idx, a, b):                                       # Scene.py:477-518
         index = int(u_idx * f32(self.nl))
         if index >= self.nl: index = self.nl - 1
-        pi = int(self.t.light[index]); vi = int(self.t.primitive[pi, 1]); V = self.t.vertex
-        if a + b > 1.0: a = f32(1.0) - a; b = f32(1.0) - b
-        lpos = (V[vi, 0:3] + (V[vi + 2, 0:3] - V[vi, 0:3]) * a) + (V[vi + 1, 0:3] - V[vi, 0:3]) * b
-        nor = normalized(((f32(1.0) - a - b) * V[vi, 3:6] + V[vi + 1, 3:6] * a) + V[vi + 2, 3:6] * b)
-        nor = normalized(normalized(nor))
+        pi = int(self.t.light[index])
+        lpos, nor = self.prim_random_point_normal(pi, a, b)
         emission = self.t.material[int(self.t.primitive[pi, 2]), 2:5].astype(f32)
         choice_pdf = f32(1.0) / (f32(self.nl) * self.prim_area(pi))
+        nor = normalized(nor)
         d = pos - lpos; dist = length(d); d = d / dist
-        return lpos, nor, d, emission, dist, choice_pdf
+        ndl = abs(dot(d, nor))
+        visable = f32(1.0)
+        if int(self.t.primitive[pi, 0]) != PRIMITIVE_TRI:
+            sh = self.t.shape[int(self.t.primitive[pi, 1])].astype(f32); st = int(sh[0])
+            if st == SHPAE_SPOT:                                                 # :499-506
+                x1, x2 = sh[4], sh[5]
+                x = np.arccos(ndl, dtype=f32)
+                if x > x2:
+                    visable = f32(0.0)
+                elif x > x1:
+                    visable = visable * (f32(1.0) - (x - x1) / (x2 - x1))
+            elif st == SHPAE_LASER:                                              # :508-515
+                choice_pdf = f32(1.0) / f32(self.nl)
+                proj = dot(d, nor) * dist
+                r = np.sqrt(dist * dist - proj * proj)
+                if r > sh[4]:
+                    visable = f32(0.0)
+        return lpos, nor, d, emission * visable, dist, choice_pdf
 
     def pixel(self, i, j, frame):
         """-> radiance (3,) f32, (closest-hit calls, shadow calls)"""

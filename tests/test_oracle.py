@@ -133,8 +133,10 @@ def test_cpp_oracle_pt_rgb_matches_literal_python_transliteration(oracle_tables)
     rel 1e-4, and <= 1 % of the pixels may differ more (a path that changes a branch at a float boundary)"""
     from oracle import pt_literal as PL
     W = H = 24
-    for glass0, frames in ((False, (0, 1, 3)), (True, (0, 3))):       # second pass: the white walls / boxes become glass (ior 1.3, extinction 5)
-      t = oracle_tables("cornell", glass0=glass0)
+    # second pass: the white walls / boxes become glass (ior 1.3, extinction 5); third: a laser and a spot light are added
+    # (Scene.sample_li's SPOT / LASER branches, Scene.py:493-516, restated independently in pt_literal.sample_li)
+    for glass0, beams, frames in ((False, False, (0, 1, 3)), (True, False, (0, 3)), (False, True, (0, 2))):
+      t = oracle_tables("cornell", glass0=glass0, beam_lights=beams)
       s = oracle.OracleScene(t).build()
       cam = oracle.fit_camera(t, W, H)
       s.set_camera(cam[1], cam[2], *cam[3:])
