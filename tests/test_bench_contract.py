@@ -46,3 +46,42 @@ def test_native_arm_needs_a_gpu():
         pytest.skip("a CUDA device is present")
     r = _run(["--steps", "1", "--warmup", "0", "--no-cpu"])
     assert r.returncode != 0 and r.stdout.strip() == ""          # no JSON line from a CPU fallback
+
+
+def test_clock_sampler_polls_nvml_inside_the_region(monkeypatch):
+    """the `clocks` object of the bench line: NVML polled from a thread while the timed region runs (a stub NVML here: the
+    median SM clock, the maximum, every throttle reason seen, at least the start and end samples even for a 1 ms region);
+    without NVML and without nvidia-smi the object says so instead of inventing numbers"""
+    import time
+    import types
+    sys.path.insert(0, ROOT)
+    import bench
+    calls = {"n": 0}
+    nv = types.ModuleType("pynvml")
+    nv.NVML_CLOCK_SM = 1
+    nv.nvmlInit = lambda: None
+    nv.nvmlDeviceGetHandleByIndex = lambda i: ("gpu", i)
+    nv.nvmlDeviceGetMaxClockInfo = lambda h, c: 1965
+    def clock(h, c):
+        calls["n"] += 1
+        return 1965 if calls["n"] != 2 else 1500
+    nv.nvmlDeviceGetClockInfo = clock
+    nv.nvmlDeviceGetCurrentClocksThrottleReasons = lambda h: 0x4 if calls["n"] == 2 else 0      # sw_power_cap once
+    nv.nvmlDeviceGetPowerUsage = lambda h: 300000
+    monkeypatch.setitem(sys.modules, "pynvml", nv)
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "3,5")
+    s = bench.ClockSampler(1)
+    assert s.h == ("gpu", 5)                                   # local rank 1 of CUDA_VISIBLE_DEVICES=3,5 is physical GPU 5
+    s.start(); time.sleep(0.03); c = s.stop()
+    assert c["source"] == "nvml" and c["samples"] >= 3 and c["sm_mhz"] == 1965.0 and c["sm_max_mhz"] == 1965.0
+    assert c["reasons"] == ["sw_power_cap"] and c["power_w_max"] == 300.0
+    s = bench.ClockSampler(0); s.start(); c = s.stop()         # the shortest possible region still has its two end samples
+    assert c["samples"] >= 2
+    broken = types.ModuleType("pynvml")
+    def boom():
+        raise RuntimeError("no driver")
+    broken.nvmlInit = boom
+    monkeypatch.setitem(sys.modules, "pynvml", broken)
+    monkeypatch.setenv("PATH", "/nonexistent")
+    s = bench.ClockSampler(0); s.start(); c = s.stop()
+    assert c["sm_mhz"] is None and c["reasons"] == ["nvidia-smi unavailable"]
