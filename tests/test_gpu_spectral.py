@@ -103,6 +103,20 @@ def test_pt_spec_cornell_matches_oracle(gpu_ctx, oracle_tables):
     assert st["rays_closest"] == c3["closest"] and st["rays_shadow"] == c3["shadow"]
 
 
+def test_pt_spec_spot_and_laser_emitters_match_oracle(gpu_ctx, oracle_tables):
+    """PT_Spec with a laser and a spot light in the box: the spectral integrator ignores sample_li's emission (it uses the D65
+    table, integrator/PT_Spec.py:257) but takes its light choice, point and the laser's choice pdf (Scene.py:508-510)"""
+    W = H = 64
+    scene, cam, integ = build_gpu_spectral(W, H, beam_lights=True)
+    st = integ.render_frames(3)
+    g = integ.hdr.to_numpy()
+    o = spectral_oracle(oracle_tables, W, H, beam_lights=True)
+    ref, cnt = spectral.render_pt_spec(o, W, H, 0, 3)
+    assert np.array_equal(g, ref, equal_nan=True)
+    plain, _ = spectral.render_pt_spec(spectral_oracle(oracle_tables, W, H), W, H, 0, 3)
+    assert not np.array_equal(ref, plain)                      # the extra emitters do change the film
+
+
 def test_pt_spec_glass_and_rgb_materials_match_oracle(gpu_ctx, oracle_tables):
     """material 0 (floor, ceiling, back wall, boxes) as dispersive glass: Sellmeier ior per hero wavelength, paths leave
     through the glass into the sky dome; material 1 (red wall) as an RGB Disney surface through rgb2spec; material 2 stays
