@@ -93,6 +93,9 @@ TRM_FN float tr_cosf(float x) {
     return v;
 }
 
+/* tan = sin / cos (one IEEE division): only the spot light's cone radius uses it (Scene.py:456-457) */
+TRM_FN float tr_tanf(float x) { return tr_sinf(x) / tr_cosf(x); }
+
 /* ---- exp ------------------------------------------------------------------------------------------------------------------
  * n = floor(x*log2(e) + 0.5); r = (x - n*C1) - n*C2 (C1 + C2 = ln 2, n*C1 exact); e^r by a degree-5 polynomial; scaled by 2^n in
  * two exact power-of-two multiplications so that gradual underflow rounds once. */

@@ -569,7 +569,7 @@ inline float CosineHemisphere_pdf(float c) { return fmaxf(0.01f, c / REF_PIf); }
 
 struct LightSample { V3 pos, normal, dir, emission; float dist; int prim; float choice_pdf, dir_pdf; };
 // Scene.py:477-518 with :423-428 and :381-420 inlined; randoms: u_idx, a, b
-inline LightSample sample_li(const Scene& s, V3 p, float u_idx, float a, float b) {
+inline LightSample sample_li(const Scene& s, V3 p, float u_idx, float a, float b, bool li_terms = true) {
     LightSample L;
     int index = (int)(u_idx * (float)s.nl); if (index >= s.nl) index = s.nl - 1;
     int pi = s.light[index];
@@ -600,7 +600,7 @@ inline LightSample sample_li(const Scene& s, V3 p, float u_idx, float a, float b
     float NdotL = fabsf(dot(dir, nor));
     L.dir_pdf = CosineHemisphere_pdf(NdotL);
     L.pos = pos; L.normal = nor; L.dir = dir; L.dist = dist; L.prim = pi;
-    if (prim_type(s, pi) != PRIM_TRI) {     // Scene.py:493-516: spot falloff / laser radius cut-off scale the emission
+    if (li_terms && prim_type(s, pi) != PRIM_TRI) {     // Scene.py:493-516: spot falloff / laser radius cut-off scale the emission
         int sid = prim_vindex(s, pi); int st = shape_type(s, sid);
         const float* sp = &s.shape[(size_t)sid * SHA_N];
         float visable = 1.0f;

@@ -113,3 +113,67 @@ def test_cpp_oracle_matches_literal_python_transliteration(oracle_tables):
                         assert (u * 65536 + v if u >= 0 else -1) == int(ref[3]), (name, i, j, frame, l)
                     n_strat += 1; n_weighted += bool(rgb[0] > 0 and rgb[1] > 0 and rgb[2] > 0 and l + e != 2)
         assert n_strat > 500 and n_weighted > 50, (n_strat, n_weighted)
+
+
+def test_sample_light_spot_and_laser_against_a_literal_restatement(oracle_tables):
+    """Scene.sample_light (Scene.py:430-474) restated here in numpy f32 for all four emitter kinds of the beam-light Cornell box
+    (two triangles of the area light, a laser, a spot light): vertex 0 of the C++ oracle's light sub-path -- position, normal,
+    beta = emission / choice pdf, first direction, pdf -- agrees for every sampled pixel (numpy's sin / cos / tan differ from
+    include/trmath.h by ULPs: rel 2e-5)"""
+    from oracle import pt_literal as PL
+    from conftest import BEAM_LIGHTS
+    f = np.float32
+    W = H = 48
+    t = oracle_tables("cornell", beam_lights=True)
+    s = oracle.OracleScene(t).build()
+    cam = oracle.fit_camera(t, W, H, 0.8)
+    s.set_camera(cam[1], cam[2], *cam[3:]); s.set_camera_view(cam[0], W, H)
+    tr = PL.Tracer(s, t, cam)
+    nl = int(t.light.size); assert nl == 4
+    PI = PL.PI_REF if hasattr(PL, "PI_REF") else f(3.1415956)
+
+    def map_to_disk(u1, u2):                                 # UtilsFunc.py:322-345
+        a, b = f(2.0) * u1 - f(1.0), f(2.0) * u2 - f(1.0)
+        if a > -b:
+            if a > b: return a, (PI / f(4.0)) * (b / a)
+            return b, (PI / f(4.0)) * (f(2.0) - a / b)
+        if a < b: return -a, (PI / f(4.0)) * (f(4.0) + b / a)
+        return -b, (f(0.0) if b == 0.0 else (PI / f(4.0)) * (f(6.0) - a / b))
+
+    kinds = {1: 0, 3: 0, 4: 0}
+    rng = np.random.RandomState(11)
+    for i, j in zip(rng.randint(0, W, 160), rng.randint(0, H, 160)):
+        frame = 3
+        ov, od, _ = s.bdpt_pixel_dump(int(i), int(j), frame)
+        Ra, Rb = tr.rng(int(i), int(j), frame, 40), tr.rng(int(i), int(j), frame, 41)
+        index = min(int(Ra[0] * f(nl)), nl - 1); pi = int(t.light[index])
+        pos, nor = tr.prim_random_point_normal(pi, Ra[1], Ra[2])
+        emission = t.material[int(t.primitive[pi, 2]), 2:5].astype(f)
+        choice = f(1.0) / (f(nl) * tr.prim_area(pi))
+        nor = PL.normalized(nor)
+        p = PL.cosine_sample_hemisphere(Rb[0], Rb[1])
+        dir_pdf = max(f(0.01), p[2] / PI)
+        d = PL.inverse_transform(p, nor)
+        kind = 1
+        if int(t.primitive[pi, 0]) != 1:
+            sh = t.shape[int(t.primitive[pi, 1])].astype(f); kind = int(sh[0])
+            if kind == 3:                                    # spot
+                scale = sh[6]; dir_pdf = f(1.0)
+                r, phi = map_to_disk(Rb[2], Rb[3])
+                r1, r2 = scale * np.tan(sh[4], dtype=f), scale * np.tan(sh[5], dtype=f)
+                r = r * r2
+                if r > r1: emission = emission * (f(1.0) - (r - r1) / (r2 - r1))
+                sp = np.array([r * np.cos(phi, dtype=f), r * np.sin(phi, dtype=f), np.sqrt(max(f(0.0), scale * scale - r * r))], f)
+                d = PL.inverse_transform(sp, nor)
+            elif kind == 4:                                  # laser
+                choice = f(1.0) / f(nl)
+                r = sh[4]; phi = Rb[2] * PI * f(2.0)
+                pos = pos + PL.inverse_transform(np.array([r * np.cos(phi, dtype=f), r * np.sin(phi, dtype=f), 0.0], f), nor)
+                d = nor; dir_pdf = f(1.0)
+        kinds[kind] += 1
+        v0 = ov[7]
+        tol = dict(rtol=2e-5, atol=2e-4)
+        assert np.allclose(v0[0:3], pos, **tol) and np.allclose(v0[3:6], nor, **tol), (i, j, kind)
+        assert np.allclose(v0[9:12], emission / choice, rtol=2e-4) and np.allclose(v0[12:15], d, **tol), (i, j, kind)
+        assert np.isclose(v0[15], choice, rtol=1e-5), (i, j, kind)
+    assert min(kinds.values()) > 15, kinds                   # every emitter kind was sampled

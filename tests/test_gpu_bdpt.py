@@ -111,6 +111,38 @@ def test_bdpt_sphere_emitter(gpu_ctx, oracle_tables):
     assert int(st["rays_closest"]) == cnt["closest"] and int(st["rays_shadow"]) == cnt["shadow"]
 
 
+def test_bdpt_spot_and_laser_emitters(gpu_ctx, oracle_tables):
+    """Scene.sample_light's SPOT / LASER branches (Scene.py:449-472: direction through a disk at distance `scale` with the cone
+    falloff; rim point of the laser, direction = its normal, choice pdf 1 / light_count) and sample_li's (:493-516) in the
+    connections: Cornell box with one of each next to the area light; vertices and strategies bit for bit, film within the
+    float-atomic splat tolerance"""
+    W = H = 64
+    scene, cam, integ = build_gpu("cornell", W, H, 0.8, False, beam_lights=True)
+    o = build_oracle(oracle_tables("cornell", beam_lights=True), W, H, 0.8, False)
+    rng = np.random.RandomState(3)
+    px = rng.randint(0, W, 300).astype(np.int32); py = rng.randint(0, H, 300).astype(np.int32)
+    gpu_ctx.film_clear(); cam.frame = 2; cam.frame_cpu[0] = 2
+    integ.render()
+    verts, depths, contrib = gpu_ctx.test_bdpt_dump(px, py)
+    beam_starts = 0
+    for k in range(px.size):
+        ov, od, oc = o.bdpt_pixel_dump(int(px[k]), int(py[k]), 2)
+        assert tuple(depths[k]) == od, (int(px[k]), int(py[k]))
+        for v in list(range(od[0])) + [7 + i for i in range(od[1])]:
+            assert np.array_equal(verts[k, v], ov[v], equal_nan=True), (int(px[k]), int(py[k]), v)
+        for e in range(2, od[0] + 1):
+            for l in range(0, od[1] + 1):
+                assert np.array_equal(contrib[k, e - 1, l, :3], oc[e - 1, l, :3], equal_nan=True), (int(px[k]), int(py[k]), e, l)
+        beam_starts += bool(abs(float(ov[7][1]) - 500.0) < 1e-3 or abs(float(ov[7][1]) - 450.0) < 1e-3)   # light vertex 0 at y = 500 (laser) / 450 (spot)
+    assert beam_starts > px.size // 4                      # two of the four emitters are beams
+    gpu_ctx.film_clear(); cam.frame = 0; cam.frame_cpu[0] = 0
+    st = integ.render_frames(3)
+    g = integ.hdr.to_numpy()
+    ref, cnt = o.render_bdpt_rgb(W, H, 0, 3)
+    assert np.isfinite(g).all() and np.allclose(g, ref, rtol=1e-5, atol=1e-6)
+    assert int(st["rays_closest"]) == cnt["closest"] and int(st["rays_shadow"]) == cnt["shadow"]
+
+
 def test_bdpt_batched_equals_framewise(gpu_ctx):
     """several frames per batch == frame-by-frame render() calls (own terms are summed in a fixed order; only the float
     atomics of the splats may reorder)"""

@@ -247,9 +247,8 @@ def test_pt_rgb_glass_env_sphere_light_matches_oracle(gpu_ctx, oracle_tables):
 
 def test_pt_rgb_spot_and_laser_emitters_match_oracle(gpu_ctx, oracle_tables):
     """Scene.sample_li's SPOT falloff and LASER radius cut-off (Scene.py:493-516): Cornell box with one of each next to the
-    area light; the shapes have an empty box and are never hit (Scene.py:596-597), they only light through NEE.  BDPT's light
-    sub-path does not start at them: it refuses the scene."""
-    import BDPT_RGB
+    area light; the shapes have an empty box and are never hit (Scene.py:596-597), they only light through NEE.  (BDPT:
+    test_gpu_bdpt.py::test_bdpt_spot_and_laser_emitters.)"""
     W = H = 96
     scene, cam, integ = build_gpu_scene("cornell", W, H, beam_lights=True)
     st = integ.render_frames(4)
@@ -260,9 +259,6 @@ def test_pt_rgb_spot_and_laser_emitters_match_oracle(gpu_ctx, oracle_tables):
     assert int(st["rays_closest"]) == cnt["closest"] and int(st["rays_shadow"]) == cnt["shadow"]
     plain, _ = build_oracle_scene(oracle_tables("cornell"), W, H).render_pt_rgb(W, H, 0, 4)
     assert ref[..., 0].mean() > 1.05 * plain[..., 0].mean()                # the red laser really lights the scene (+12 %)
-    bd = BDPT_RGB.BDPT(W, H, cam, scene, 64); bd.setup_data_cpu()
-    with pytest.raises(RuntimeError, match="spot / laser"):
-        bd.render()
 
 
 def test_pt_rgb_teapot_mc_matches_oracle(gpu_ctx, oracle_tables):

@@ -192,7 +192,6 @@ extern "C" {
 static int validate_scene(tr_ctx* ctx, const float* vertex, int nv, const int32_t* prim, int np, const float* material, int nm,
                           const float* shape, int ns, const int32_t* light, int nl) {
     (void)vertex;
-    ctx->has_beam_light = false;
     for (int i = 0; i < np; ++i) {
         const int type = prim[i * 3], idx = prim[i * 3 + 1], mat = prim[i * 3 + 2];
         if (mat < 0 || mat >= nm) return tr_fail(ctx, TR_ERR_INVALID, "tr_scene_upload: primitive %d: material index %d out of range (%d materials)", i, mat, nm);
@@ -200,15 +199,11 @@ static int validate_scene(tr_ctx* ctx, const float* vertex, int nv, const int32_
             if (idx < 0 || (long long)idx + 2 >= (long long)nv) return tr_fail(ctx, TR_ERR_INVALID, "tr_scene_upload: primitive %d: vertex index %d + 2 out of range (%d vertices)", i, idx, nv);
         } else if (type == 2) {
             if (!shape || idx < 0 || idx >= ns) return tr_fail(ctx, TR_ERR_INVALID, "tr_scene_upload: primitive %d: shape index %d out of range (%d shapes)", i, idx, ns);
-            // emitters: triangle, sphere, spot and laser lights (Scene.sample_li, Scene.py:477-518).  A QUAD emitter has no area in
-            // the reference (get_prim_area returns 0 -> infinite choice pdf): rejected instead of rendered wrong.  The light
-            // sub-path of BDPT_RGB starts at triangle / sphere emitters only (tr_render_bdpt_rgb checks).
+            // emitters: triangle, sphere, spot and laser lights (Scene.sample_li / sample_light, Scene.py:430-518).  A QUAD emitter
+            // has no area in the reference (get_prim_area returns 0 -> infinite choice pdf): rejected instead of rendered wrong.
             const int st = (int)shape[(size_t)idx * 10];
-            if ((int)material[(size_t)mat * 10] == TR_MAT_LIGHT) {
-                if (st != TR_SHAPE_SPHERE && st != TR_SHAPE_SPOT && st != TR_SHAPE_LASER)
-                    return tr_fail(ctx, TR_ERR_INVALID, "tr_scene_upload: primitive %d: emitter shape type %d is not supported (triangle, sphere, spot and laser emitters only)", i, st);
-                if (st != TR_SHAPE_SPHERE) ctx->has_beam_light = true;
-            }
+            if ((int)material[(size_t)mat * 10] == TR_MAT_LIGHT && st != TR_SHAPE_SPHERE && st != TR_SHAPE_SPOT && st != TR_SHAPE_LASER)
+                return tr_fail(ctx, TR_ERR_INVALID, "tr_scene_upload: primitive %d: emitter shape type %d is not supported (triangle, sphere, spot and laser emitters only)", i, st);
         } else return tr_fail(ctx, TR_ERR_INVALID, "tr_scene_upload: primitive %d: unknown primitive type %d", i, type);
     }
     for (int i = 0; i < nl; ++i)

@@ -122,6 +122,19 @@ __device__ __forceinline__ BdStep bd_vertex(const bool LIGHT, const WfArgs& a, c
     return st;
 }
 
+// UtilsFunc.py:322-345
+__device__ __forceinline__ void map_to_disk(float u1, float u2, float& r, float& phi) {
+    phi = 0.0f; r = 0.0f;
+    const float a = 2.0f * u1 - 1.0f, b = 2.0f * u2 - 1.0f;
+    if (a > -b) {
+        if (a > b) { r = a; phi = (TR_PI_REF / 4.0f) * (b / a); }
+        else { r = b; phi = (TR_PI_REF / 4.0f) * (2.0f - a / b); }
+    } else {
+        if (a < b) { r = -a; phi = (TR_PI_REF / 4.0f) * (4.0f + b / a); }
+        else { r = -b; phi = (b == 0.0f) ? 0.0f : (TR_PI_REF / 4.0f) * (6.0f - a / b); }
+    }
+}
+
 // vertex 0 of a sub-path and its first ray: the lens (eye_path :108-116) or a sampled emitter point with a cosine-hemisphere
 // direction (light_path :194-211, Scene.sample_light Scene.py:430-474: point as in sample_li)
 template <bool LIGHT>
@@ -136,10 +149,24 @@ __device__ __forceinline__ void bd_vertex0(const WfArgs& a, const BdArgs& b, con
         beta = mk3(1.f, 1.f, 1.f); pdfFwd = 1.0f;
     } else {
         float4 Ra = rng4(bp.seed, pix, frame, 40u), Rb = rng4(bp.seed, pix, frame, 41u);
-        LightSample ls = sample_li(a, mk3(0.f, 0.f, 0.f), Ra.x, Ra.y, Ra.z);
+        LightSample ls = sample_li(a, mk3(0.f, 0.f, 0.f), Ra.x, Ra.y, Ra.z, false);
         V3 p = cosine_sample_hemisphere(Rb.x, Rb.y);
         pdfFwd = cosine_hemisphere_pdf(p.z);
         dir = inverse_transform(p, ls.normal);
+        if (ls.kind == 2) {                          // spot light (Scene.py:449-463): a direction through a disk at distance `scale`
+            const float scale = ls.p2;
+            pdfFwd = 1.0f;
+            float r, phi; map_to_disk(Rb.z, Rb.w, r, phi);
+            const float r1 = scale * tr_tanf(ls.p0), r2 = scale * tr_tanf(ls.p1);
+            r *= r2;
+            if (r > r1) ls.emission = ls.emission * (1.0f - (r - r1) / (r2 - r1));
+            dir = inverse_transform(mk3(r * tr_cosf(phi), r * tr_sinf(phi), sqrtf(fmaxf(0.0f, scale * scale - r * r))), ls.normal);
+        } else if (ls.kind == 3) {                   // laser (Scene.py:464-472): along the normal from a point of the rim
+            ls.choice_pdf = 1.0f / (float)a.nl;
+            const float r = ls.p0, phi = (Rb.z * TR_PI_REF) * 2.0f;
+            ls.pos = ls.pos + inverse_transform(mk3(r * tr_cosf(phi), r * tr_sinf(phi), 0.0f), ls.normal);
+            dir = ls.normal; pdfFwd = 1.0f;
+        }
         const float light_pdf = ls.choice_pdf;
         origin = ls.pos;
         v0.pos = ls.pos; v0.normal = ls.normal; v0.beta = ls.emission / light_pdf; v0.fpdf = light_pdf; v0.wo = dir; v0.type = BD_VERTEX_LIGHT;
@@ -635,7 +662,6 @@ static int render_bdpt(tr_ctx* ctx, int frame_begin, int n_frames, uint64_t seed
     if (!ctx->h_ring) TR_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_ring, sizeof(TrCounters) * TR_MAX_CHAINS * TR_RING_BATCHES, cudaHostAllocDefault));
     if ((rc = fill_args(ctx, a, false))) return rc;
     if (ctx->nl <= 0) return tr_fail(ctx, TR_ERR_INVALID, "tr_render_bdpt_rgb: the scene has no emitter (Scene.sample_light needs one)");
-    if (ctx->has_beam_light) return tr_fail(ctx, TR_ERR_INVALID, "tr_render_bdpt_rgb: spot / laser emitters are not supported by the light sub-path (Scene.sample_light, Scene.py:449-472); PT_RGB and PT_Spec render them");
     if (!ctx->view_set) return tr_fail(ctx, TR_ERR_INVALID, "tr_render_bdpt_rgb: tr_camera_set was called without the view matrix (Camera.get_image_point needs it)");
     const bool wave = ctx->opt_bdpt_wavefront != 0;
     // bytes per sample: 13 vertex records + 21 contributions + 26 queue items + depths; the wavefront pipeline adds two path-queue

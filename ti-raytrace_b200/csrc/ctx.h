@@ -69,7 +69,6 @@ struct tr_ctx {
 
     // LBVH build products
     bool bvh_ready = false;
-    bool has_beam_light = false;   // the scene holds a spot or laser emitter (Scene.sample_li handles them; BDPT's sample_light here does not)
     int*   d_morton_unsorted = nullptr;  // n x 2
     int*   d_keys[2] = {nullptr, nullptr};
     int*   d_vals[2] = {nullptr, nullptr};

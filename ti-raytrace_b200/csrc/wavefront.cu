@@ -400,10 +400,10 @@ __device__ __forceinline__ V3 env_texture2d(const WfArgs& a, float u, float v) {
                 mix3(env_texel(a, lx, ly + 1.0f), env_texel(a, lx + 1.0f, ly + 1.0f), wlr), wbt);
 }
 
-struct LightSample { V3 pos, normal, dir, emission; float dist, choice_pdf; int prim; };
+struct LightSample { V3 pos, normal, dir, emission; float dist, choice_pdf; int prim; int kind; float p0, p1, p2; };   // kind / p*: shading-table kind and shape parameters of the emitter
 // Scene.sample_li (Scene.py:477-518) with get_random_light_prim_index (:423-428),
 // get_prim_random_point_normal (:381-420) and get_prim_area (:324-350, precomputed per primitive)
-__device__ __forceinline__ LightSample sample_li(const WfArgs& a, V3 p, float u_idx, float ua, float ub) {
+__device__ __forceinline__ LightSample sample_li(const WfArgs& a, V3 p, float u_idx, float ua, float ub, bool li_terms = true) {
     LightSample L;
     int index = (int)(u_idx * (float)a.nl); if (index >= a.nl) index = a.nl - 1;
     int pi = __ldg(a.light + index);
@@ -427,7 +427,7 @@ __device__ __forceinline__ LightSample sample_li(const WfArgs& a, V3 p, float u_
     L.choice_pdf = 1.0f / ((float)a.nl * q2.w);
     nor = normalize3(nor);      // Scene.py:486
     V3 dir = p - pos; float dist = length3(dir); dir = dir / dist;
-    if (kind >= 2) {            // Scene.py:493-516: spot falloff (kind 2) / laser radius cut-off (kind 3) scale the emission
+    if (kind >= 2 && li_terms) { // Scene.py:493-516: spot falloff (kind 2) / laser radius cut-off (kind 3) scale the emission
         float visable = 1.0f;
         if (kind == 2) {
             float x = tr_acosf(fabsf(dot3(dir, nor)));
@@ -442,6 +442,7 @@ __device__ __forceinline__ LightSample sample_li(const WfArgs& a, V3 p, float u_
         L.emission = L.emission * visable;
     }
     L.pos = pos; L.normal = nor; L.dir = dir; L.dist = dist; L.prim = pi;
+    L.kind = kind; L.p0 = q2.x; L.p1 = q2.y; L.p2 = q2.z;
     return L;
 }
 
