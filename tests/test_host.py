@@ -26,6 +26,18 @@ def test_scene_packing_matches_oracle_loader(oracle_tables, name):
     assert s.primitive_count == t.primitive.shape[0] and s.vertex_count == t.vertex.shape[0]
 
 
+def test_spot_and_laser_shapes_pack_like_the_reference_rows(oracle_tables):
+    """SceneData.Shape.fillStruct for SHPAE_LASER / SHPAE_SPOT (type, pos, radius | xita1 xita2 scale, normal: SceneData.py:88-131)
+    through Scene.add_shape == the rows the oracle-side loader writes by hand; both are emitters (light list) and shape primitives"""
+    s = make_product_scene("cornell", beam_lights=True); s.setup_data_cpu()
+    t = oracle_tables("cornell", beam_lights=True)
+    assert np.array_equal(s.shape_np, t.shape) and np.array_equal(s.primitive_np, t.primitive) and np.array_equal(s.material_np, t.material)
+    assert s.light_cpu == [34, 35, 36, 37] and np.array_equal(np.asarray(s.light_cpu, np.int32), t.light)
+    assert s.shape_np[0, 0] == 4.0 and s.shape_np[0, 4] == 60.0 and s.shape_np[0, 7:10].tolist() == [0.0, -1.0, 0.0]      # laser: radius, normal
+    assert s.shape_np[1, 0] == 3.0 and np.allclose(s.shape_np[1, 4:7], [0.3, 0.6, 1.0])                                    # spot: xita1, xita2, scale
+    assert s.primitive_np[36].tolist() == [2, 0, 4] and s.primitive_np[37].tolist() == [2, 1, 5]
+
+
 def test_cornell_material_classes():
     s = make_product_scene("cornell"); s.setup_data_cpu()
     assert s.material_np[:, 0].tolist() == [0.0, 0.0, 0.0, 2.0]          # white, red, green disney; light
