@@ -1027,6 +1027,7 @@ static int fill_args(tr_ctx* ctx, WfArgs& a, bool spec = false) {
 static int ensure_wavefront(tr_ctx* ctx, size_t slots) {
     if (slots <= ctx->wf_cap) return TR_OK;
     int rc;
+    ctx->wf_cap = 0;                 // a growth that fails half-way (out of memory) must not leave the old capacity standing over freed buffers
     for (int k = 0; k < 2; ++k) for (int j = 0; j < 3; ++j) if ((rc = tr_realloc(ctx, &ctx->d_path[k][j], slots))) return rc;
     if ((rc = tr_realloc(ctx, &ctx->d_hit, slots))) return rc;
     if ((rc = tr_realloc(ctx, &ctx->d_cls, slots * 3))) return rc;
